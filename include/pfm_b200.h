@@ -1,0 +1,130 @@
+/*
+ * pfm_b200.h -- C ABI of the B200-native hot path of ewencedr/particle_fm.
+ *
+ * One shared library (particle_fm_b200/lib/libpfm_b200.so, hand-written CUDA for sm_100a) that a
+ * host binds through FFI (ctypes in this repo).  No torch / C++ types cross the
+ * boundary: plain pointers, sizes and a CUDA stream handle.
+ *
+ * Each entry point names the reference interface it replaces (paths under the reference tree):
+ *   pfm_epic_forward   <- CNF.forward                 particle_fm/models/flow_matching_module.py:191-204
+ *                          EPiC_encoder.forward        particle_fm/models/components/epic.py:304-391
+ *                          EPiC_layer.forward          particle_fm/models/components/epic.py:85-203
+ *   pfm_epic_sample    <- CNF.decode (euler/midpoint)  flow_matching_module.py:245-287
+ *                          + torchdyn fixed-step loop (third party; restated in oracle/ode_oracle.py)
+ *                          + ode_wrapper.forward       flow_matching_module.py:62-71
+ *   pfm_epic_loss_*    <- FlowMatchingLoss / ConditionalFlowMatchingLoss / DroidLoss .forward
+ *                          particle_fm/models/components/losses.py:38-77, :101-136, :308-342
+ *                          and the autograd backward of the network the reference gets from torch
+ *
+ * Conventions
+ *   - every function returns 0 (PFM_OK) or a negative pfm_status; the message of the last failure
+ *     on the calling thread is pfm_last_error().  No C++ exception crosses the ABI.
+ *   - all data pointers are CALLER-OWNED DEVICE memory, contiguous fp32 unless stated, valid until
+ *     the stream reaches the call.  The handle owns only its packed weights and workspaces.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *   - a handle is bound to one device and is not thread-safe; one handle per rank.
+ *   - there is no CPU fallback: without a CUDA device pfm_epic_create fails with PFM_ERR_CUDA.
+ */
+#ifndef PFM_B200_H
+#define PFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFM_VERSION 100
+
+typedef enum {
+  PFM_OK = 0,
+  PFM_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  PFM_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  PFM_ERR_STATE = -3,       /* e.g. weights not set */
+  PFM_ERR_UNSUPPORTED = -4  /* shape not supported by the selected precision path */
+} pfm_status;
+
+/* Arithmetic of the per-particle contractions.
+ * FP32: CUDA-core fp32 FMA everywhere (strict mode; per-step parity 1e-3 and far below).
+ * BF16: tcgen05 tensor-core GEMMs with bf16 operands, fp32 accumulation in TMEM, fp32 residual
+ *       stream, fp32 pooling inputs rounded to bf16 (per-step parity 2e-2).  Requires hid == 128. */
+typedef enum { PFM_PREC_FP32 = 0, PFM_PREC_BF16 = 1 } pfm_precision;
+
+typedef enum { PFM_SOLVER_EULER = 0, PFM_SOLVER_MIDPOINT = 1 } pfm_solver;
+
+/* loss kinds of losses.py: FM-OT :38-77, CFM :101-136, droid :308-342 */
+typedef enum { PFM_LOSS_FM_OT = 0, PFM_LOSS_CFM = 1, PFM_LOSS_DROID = 2 } pfm_loss_kind;
+
+/* Resolved constructor arguments of EPiC_encoder (epic.py:226-243). */
+typedef struct {
+  int32_t feats;           /* output features per particle                      (feats)        */
+  int32_t input_dim;       /* per-particle input width                          (input_dim)    */
+  int32_t hid;             /* hidden width of the per-particle MLPs             (hid_d)        */
+  int32_t latent;          /* width of the per-jet global vector                (latent)       */
+  int32_t layers;          /* number of EPiC layers                             (equiv_layers) */
+  int32_t t_dim;           /* width of the time code = 2*frequencies                             */
+  int32_t t_local_cat;     /* time code concatenated to every per-particle linear               */
+  int32_t t_global_cat;    /* time code concatenated to every per-jet linear                    */
+  int32_t global_cond_dim; /* conditioning width on per-jet linears (0 = none)                  */
+  int32_t local_cond_dim;  /* conditioning width on per-particle linears (0 or global_cond_dim) */
+  float sum_scale;         /* factor on the sum pooling (1e-2)                                   */
+  float neg_slope;         /* leaky_relu slope (0.01, F.leaky_relu default)                      */
+} pfm_epic_cfg;
+
+typedef struct pfm_epic pfm_epic;
+
+int pfm_version(void);
+const char* pfm_last_error(void);
+
+/* Create / destroy a network handle on CUDA device `device`. */
+int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out);
+void pfm_epic_destroy(pfm_epic* h);
+
+/* Number of linears (4 + 4*layers + 1) and, for linear i in state_dict order
+ * (fc_l1, fc_l2, fc_g1, fc_g2, nn_list.{l}.fc_global1, .fc_global2, .fc_local1, .fc_local2, fc_l3),
+ * its (out, in) shape as the reference constructs it (epic.py:66-81, :262-300). */
+int pfm_epic_num_linears(const pfm_epic* h);
+int pfm_epic_linear_shape(const pfm_epic* h, int i, int32_t* out_features, int32_t* in_features);
+
+/* Hand over the FOLDED weights (W = g*v/||v||, row-major [out,in]) and biases of all linears, in
+ * the order above, as arrays of n device pointers (the pointer arrays themselves are host memory).
+ * The library repacks into its own layouts and keeps the packed copy; call again whenever the
+ * parameters change (optimizer step, EMA swap). */
+int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* const* biases, int n,
+                         void* stream);
+
+int pfm_epic_set_precision(pfm_epic* h, int precision /* pfm_precision */);
+
+/* One evaluation of the vector field (CNF.forward after the time embedding).
+ *   t_code  [t_rows, t_dim]   time code; t_rows == 1 (one time for the whole batch, sampling) or
+ *                             t_rows == B (one time per jet, training).  May be NULL iff t_dim == 0.
+ *   x       [B, N, input_dim] per-particle input (already holds the time code if add_time_to_input)
+ *   mask    [B, N]            non-zero = real particle; NULL = all real
+ *   cond    [B, cond_dim]     NULL iff global_cond_dim == 0 and local_cond_dim == 0
+ *   out     [B, N, feats]     = leaky_relu(fc_l3(...)) * mask; a jet without real particles is NaN
+ *                             in every entry, as in the reference (0/0 mean, epic.py:161,370)   */
+int pfm_epic_forward(pfm_epic* h, const float* t_code, int t_rows, const float* x, const float* mask,
+                     const float* cond, float* out, int B, int N, void* stream);
+
+/* Fixed-step integration of dx/dt = v(t, x) from t = 1 to t = 0 with the state resident on chip:
+ * ONE launch for all steps.
+ *   x_inout    [B, N, feats]     in: initial noise (already multiplied by mask); out: end point
+ *   t_codes    [n_evals, t_dim]  time code of every network evaluation, in evaluation order
+ *                                (n_evals = n_steps for Euler, 2*n_steps for midpoint)
+ *   t_codes_in [n_evals, t_in]   extra per-particle input columns prepended to x at every
+ *                                evaluation (add_time_to_input: t_in = input_dim - feats); else NULL
+ *   dt         [n_steps]         host-computed fp32 step sizes of the reversed-time grid
+ * Euler:    x <- x + dt*(-v(t_k, x));   midpoint: x <- x + dt*(-v(t_k+dt/2, x + 0.5*dt*(-v(t_k, x)))) */
+int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float* cond,
+                    const float* t_codes, const float* t_codes_in, const float* dt, int solver,
+                    int n_steps, int B, int N, void* stream);
+
+/* Introspection for tests / bench: kernels launched by the last call on this handle and the
+ * number of CTA work groups the last plan produced. */
+int pfm_epic_last_launches(const pfm_epic* h);
+int pfm_epic_last_groups(const pfm_epic* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFM_B200_H */

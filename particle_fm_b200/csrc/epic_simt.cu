@@ -1,0 +1,504 @@
+// fp32 CUDA-core ("strict") path of the EPiC vector field + fixed-step integrator.
+//
+// One persistent CTA owns a GROUP of consecutive jets whose REAL particles (padding is skipped --
+// exact) fit its shared-memory row budget, and keeps for the whole integration
+//   - the ODE state of those particles            xs / x0s   [rows, feats]
+//   - the per-particle hidden features             hs         [rows, hid]    fp32
+//   - the per-jet pooled / global vectors, biases  (small)
+// so that a full sample() is ONE launch: jets are independent, no grid-wide sync is needed.
+// Per evaluation it performs exactly the arithmetic of EPiC_encoder.forward (epic.py:304-391) in the
+// hoisted form: every concat-linear  W.[time | main | global | cond] + b  is evaluated as
+//   W_main . main  +  (b + W_time . time)  [bias table, per evaluation]  +  W_cond . cond  [per jet]
+//   (+ W_glob . g  per jet, for fc_local1),
+// which is the same sum in a different association order (fp32 rounding only).
+#include "pfm_internal.cuh"
+
+namespace pfm {
+
+static constexpr int kThreads = 256;
+static constexpr int kWarps = kThreads / 32;
+
+struct SimtParams {
+  int F, Kx, Kxp, x_ld, xin_off, H, Hp, LDH, Z, L, n_lin;
+  int R_cap, J_cap, KC, LDX;
+  float sum_scale, slope;
+  const Lin* lin;
+  const float* tbias; const float* cbias; int bstride; int tbias_per_jet;
+  const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
+  const float* x_in; float* x_out; int B, N;
+  int n_evals, solver, n_steps; const float* dt;
+  // shared-memory carve-up (float offsets)
+  int o_xs, o_x0, o_hs, o_tmp, o_wbuf, o_pool, o_g, o_g1, o_bl1, o_bl2, o_v, o_int, total_floats;
+  int wbuf_floats, LDB, LDP;
+};
+
+__device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---------------------------------------------------------------------------------------------
+// Row-block GEMM on CUDA cores.  Every warp owns RB consecutive rows of the current chunk and all
+// `out` columns (lane l holds columns l, l+32, ...: TC per lane).  The k-major weight block
+// Wt[K, ldo] streams through a double-buffered shared-memory stage shared by the 8 warps.
+//   acc[r][i] = sum_k A[row0 + r][k] * Wt[k][lane + 32 i]
+// A rows are zero in their padding columns [K, round_up(K,4)), so the k loop runs on multiples of 4.
+// ---------------------------------------------------------------------------------------------
+template <int TC, int RB>
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int K,
+                                          int ldo, float* wbuf, int wbuf_half, int KC, float (&acc)[RB][TC]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int i = 0; i < TC; ++i) acc[r][i] = 0.f;
+  const int Kp = (K + 3) & ~3;
+  const int n_chunks = (Kp + KC - 1) / KC;
+  const float* Arow = A + (size_t)(warp * RB) * lda;
+  // prologue: chunk 0
+  {
+    int kc = Kp < KC ? Kp : KC;
+    int n16 = kc * ldo / 4;
+    for (int i = tid; i < n16; i += kThreads) cp_async16(wbuf + i * 4, Wt + i * 4);
+    cp_async_commit();
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int k0 = c * KC;
+    if (c + 1 < n_chunks) {
+      int k1 = k0 + KC;
+      int kc = (Kp - k1) < KC ? (Kp - k1) : KC;
+      int n16 = kc * ldo / 4;
+      float* dst = wbuf + ((c + 1) & 1) * wbuf_half;
+      const float* src = Wt + (size_t)k1 * ldo;
+      for (int i = tid; i < n16; i += kThreads) cp_async16(dst + i * 4, src + i * 4);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = wbuf + (c & 1) * wbuf_half;
+    const int kc = (Kp - k0) < KC ? (Kp - k0) : KC;
+    for (int kk = 0; kk < kc; kk += 4) {
+      float4 a[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a[r] = *reinterpret_cast<const float4*>(Arow + (size_t)r * lda + k0 + kk);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float w[TC];
+#pragma unroll
+        for (int i = 0; i < TC; ++i) w[i] = wb[(kk + q) * ldo + lane + 32 * i];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const float av = q == 0 ? a[r].x : (q == 1 ? a[r].y : (q == 2 ? a[r].z : a[r].w));
+#pragma unroll
+          for (int i = 0; i < TC; ++i) acc[r][i] = fmaf(av, w[i], acc[r][i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// per-jet effective bias of one linear: time table row + cond table row (+ W_glob . g)
+__device__ __forceinline__ float bias_of(const SimtParams& p, const Lin& L, int eval, int jet_global, int o) {
+  const int trow = p.tbias_per_jet ? jet_global : eval;
+  float b = p.tbias[(size_t)trow * p.bstride + L.bias_off + o];
+  if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + L.bias_off + o];
+  return b;
+}
+
+template <int TC, int RB>
+__global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem + p.o_xs;      // [R_cap, LDX]   current network input (state or midpoint state)
+  float* x0 = smem + p.o_x0;      // [R_cap, F]     state at the start of the step
+  float* hs = smem + p.o_hs;      // [R_cap, LDH]
+  float* tmp = smem + p.o_tmp;    // [8*RB, LDH]
+  float* wbuf = smem + p.o_wbuf;  // 2 stages
+  float* pool = smem + p.o_pool;  // [J_cap, LDP]   (LDP >= 2H + Z)
+  float* gv = smem + p.o_g;       // [J_cap, Z]
+  float* g1 = smem + p.o_g1;      // [J_cap, Hp]
+  float* bl1 = smem + p.o_bl1;    // [J_cap, LDB]
+  float* bl2 = smem + p.o_bl2;    // [J_cap, LDB]
+  float* vbuf = smem + p.o_v;     // [R_cap, F]     network output
+  int* ints = reinterpret_cast<int*>(smem + p.o_int);
+  int* jrow0 = ints;                       // [J_cap + 1] first row of every jet of the group
+  int* s_group = ints + p.J_cap + 1;       // [2]
+  short* rjet = reinterpret_cast<short*>(ints + p.J_cap + 4);   // [R_cap] jet (inside the group) of a row
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, Z = p.Z, F = p.F, LDH = p.LDH, LDX = p.LDX, LDB = p.LDB, LDP = p.LDP;
+  const int CR = kWarps * RB;
+  const int n_groups = *p.n_groups;
+  const Lin* lin = p.lin;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_group[0] = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int gidx = s_group[0];
+    if (gidx >= n_groups) break;
+    const int2 grp = p.groups[gidx];
+    const int j0 = grp.x, nj = grp.y;
+    if (tid == 0) {
+      int r = 0;
+      for (int j = 0; j < nj; ++j) { jrow0[j] = r; r += p.n_real[j0 + j]; }
+      jrow0[nj] = r;
+    }
+    __syncthreads();
+    const int R = jrow0[nj];
+    // zero everything that later relies on zero padding, then load the group's particles
+    for (int i = tid; i < p.R_cap * LDX; i += kThreads) xs[i] = 0.f;
+    for (int i = tid; i < p.R_cap * LDH; i += kThreads) hs[i] = 0.f;
+    for (int i = tid; i < CR * LDH; i += kThreads) tmp[i] = 0.f;
+    __syncthreads();
+    for (int j = 0; j < nj; ++j) {
+      const int r0 = jrow0[j], n = jrow0[j + 1] - r0;
+      for (int i = tid; i < n; i += kThreads) rjet[r0 + i] = (short)j;
+      for (int i = tid; i < n * p.Kx; i += kThreads) {
+        const int r = i / p.Kx, c = i - r * p.Kx;
+        const int part = p.ridx[(size_t)(j0 + j) * p.N + r];
+        const float v = p.x_in[((size_t)(j0 + j) * p.N + part) * p.x_ld + c];
+        xs[(r0 + r) * LDX + c] = v;
+        if (p.solver >= 0) x0[(r0 + r) * F + c] = v;
+      }
+    }
+    __syncthreads();
+
+    for (int ev = 0; ev < p.n_evals; ++ev) {
+      // ---------------- stem: fc_l1, fc_l2 (epic.py:360-366) ----------------
+      {
+        const Lin L1 = lin[LIN_L1], L2 = lin[LIN_L2];
+        for (int i = tid; i < nj * H; i += kThreads) {
+          const int j = i / H, o = i - j * H;
+          bl1[j * LDB + o] = bias_of(p, L1, ev, j0 + j, o);
+          bl2[j * LDB + o] = bias_of(p, L2, ev, j0 + j, o);
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < R; c0 += CR) {
+          float acc[RB][TC];
+          gemm_rows<TC, RB>(xs + (size_t)c0 * LDX, LDX, L1.Wt + (size_t)(L1.m_off + p.xin_off) * L1.ldo, p.Kx, L1.ldo,
+                            wbuf, p.wbuf_floats, p.KC, acc);
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int row = c0 + warp * RB + r;
+            if (row < R) {
+              const float* bj = bl1 + rjet[row] * LDB;
+#pragma unroll
+              for (int i = 0; i < TC; ++i) {
+                const int o = lane + 32 * i;
+                if (o < H) tmp[(warp * RB + r) * LDH + o] = lrelu(acc[r][i] + bj[o], p.slope);
+              }
+            }
+          }
+          __syncwarp();
+          gemm_rows<TC, RB>(tmp, LDH, L2.Wt + (size_t)L2.m_off * L2.ldo, H, L2.ldo, wbuf, p.wbuf_floats, p.KC, acc);
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int row = c0 + warp * RB + r;
+            if (row < R) {
+              const float* bj = bl2 + rjet[row] * LDB;
+#pragma unroll
+              for (int i = 0; i < TC; ++i) {
+                const int o = lane + 32 * i;
+                if (o < H) hs[(size_t)row * LDH + o] = lrelu(acc[r][i] + bj[o] + tmp[(warp * RB + r) * LDH + o], p.slope);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+      }
+      // ---------------- stem pooling + fc_g1, fc_g2 (epic.py:369-380) ----------------
+      {
+        for (int i = tid; i < nj * H; i += kThreads) {
+          const int j = i / H, o = i - j * H;
+          const int r0 = jrow0[j], r1 = jrow0[j + 1];
+          float s = 0.f;
+          for (int r = r0; r < r1; ++r) s += hs[(size_t)r * LDH + o];
+          pool[j * LDP + o] = s * p.sum_scale;                    // (sum, mean) order in the stem, :373
+          pool[j * LDP + H + o] = s / (float)(r1 - r0);
+        }
+        __syncthreads();
+        const Lin G1 = lin[LIN_G1], G2 = lin[LIN_G2];
+        for (int i = tid; i < nj * H; i += kThreads) {
+          const int j = i / H, o = i - j * H;
+          float a = bias_of(p, G1, ev, j0 + j, o);
+          const float* w = G1.Wt + (size_t)G1.m_off * G1.ldo + o;
+          const float* in = pool + j * LDP;
+#pragma unroll 4
+          for (int k = 0; k < 2 * H; ++k) a = fmaf(__ldg(w + (size_t)k * G1.ldo), in[k], a);
+          g1[j * p.Hp + o] = lrelu(a, p.slope);
+        }
+        __syncthreads();
+        for (int i = tid; i < nj * Z; i += kThreads) {
+          const int j = i / Z, o = i - j * Z;
+          float a = bias_of(p, G2, ev, j0 + j, o);
+          const float* w = G2.Wt + (size_t)G2.m_off * G2.ldo + o;
+          const float* in = g1 + j * p.Hp;
+#pragma unroll 4
+          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * G2.ldo), in[k], a);
+          gv[j * Z + o] = lrelu(a, p.slope);                       // no residual in the stem, :378-380
+        }
+        __syncthreads();
+      }
+      // ---------------- EPiC layers (epic.py:85-203) ----------------
+      for (int l = 0; l < p.L; ++l) {
+        const Lin Ga = lin[LIN_LAYER0 + 4 * l + 0], Gb = lin[LIN_LAYER0 + 4 * l + 1];
+        const Lin La = lin[LIN_LAYER0 + 4 * l + 2], Lb = lin[LIN_LAYER0 + 4 * l + 3];
+        for (int i = tid; i < nj * H; i += kThreads) {
+          const int j = i / H, o = i - j * H;
+          const int r0 = jrow0[j], r1 = jrow0[j + 1];
+          float s = 0.f;
+          for (int r = r0; r < r1; ++r) s += hs[(size_t)r * LDH + o];
+          pool[j * LDP + o] = s / (float)(r1 - r0);                // (mean, sum, global) order, :164-171
+          pool[j * LDP + H + o] = s * p.sum_scale;
+        }
+        for (int i = tid; i < nj * Z; i += kThreads) {
+          const int j = i / Z, o = i - j * Z;
+          pool[j * LDP + 2 * H + o] = gv[j * Z + o];
+        }
+        __syncthreads();
+        for (int i = tid; i < nj * H; i += kThreads) {            // fc_global1, :180-182
+          const int j = i / H, o = i - j * H;
+          float a = bias_of(p, Ga, ev, j0 + j, o);
+          const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + o;
+          const float* in = pool + j * LDP;
+          const int K = 2 * H + Z;
+#pragma unroll 4
+          for (int k = 0; k < K; ++k) a = fmaf(__ldg(w + (size_t)k * Ga.ldo), in[k], a);
+          g1[j * p.Hp + o] = lrelu(a, p.slope);
+        }
+        __syncthreads();
+        for (int i = tid; i < nj * Z; i += kThreads) {            // fc_global2 + residual, :184-186
+          const int j = i / Z, o = i - j * Z;
+          float a = bias_of(p, Gb, ev, j0 + j, o);
+          const float* w = Gb.Wt + (size_t)Gb.m_off * Gb.ldo + o;
+          const float* in = g1 + j * p.Hp;
+#pragma unroll 4
+          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * Gb.ldo), in[k], a);
+          // the new global vector is written to the pool row first (gv is still being read as the residual
+          // by other threads only through gv[j*Z+o] of the SAME (j,o) -> safe in place)
+          gv[j * Z + o] = lrelu(a + gv[j * Z + o], p.slope);
+        }
+        __syncthreads();
+        for (int i = tid; i < nj * H; i += kThreads) {            // per-jet bias of fc_local1 / fc_local2
+          const int j = i / H, o = i - j * H;
+          float a = bias_of(p, La, ev, j0 + j, o);
+          const float* w = La.Wt + (size_t)La.g_off * La.ldo + o;
+          const float* in = gv + j * Z;
+          for (int k = 0; k < Z; ++k) a = fmaf(__ldg(w + (size_t)k * La.ldo), in[k], a);
+          bl1[j * LDB + o] = a;
+          bl2[j * LDB + o] = bias_of(p, Lb, ev, j0 + j, o);
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < R; c0 += CR) {                      // fc_local1, fc_local2 + residual, :189-200
+          float acc[RB][TC];
+          gemm_rows<TC, RB>(hs + (size_t)c0 * LDH, LDH, La.Wt + (size_t)La.m_off * La.ldo, H, La.ldo, wbuf,
+                            p.wbuf_floats, p.KC, acc);
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int row = c0 + warp * RB + r;
+            if (row < R) {
+              const float* bj = bl1 + rjet[row] * LDB;
+#pragma unroll
+              for (int i = 0; i < TC; ++i) {
+                const int o = lane + 32 * i;
+                if (o < H) tmp[(warp * RB + r) * LDH + o] = lrelu(acc[r][i] + bj[o], p.slope);
+              }
+            }
+          }
+          __syncwarp();
+          gemm_rows<TC, RB>(tmp, LDH, Lb.Wt + (size_t)Lb.m_off * Lb.ldo, H, Lb.ldo, wbuf, p.wbuf_floats, p.KC, acc);
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int row = c0 + warp * RB + r;
+            if (row < R) {
+              const float* bj = bl2 + rjet[row] * LDB;
+#pragma unroll
+              for (int i = 0; i < TC; ++i) {
+                const int o = lane + 32 * i;
+                if (o < H) {
+                  float* hp = hs + (size_t)row * LDH + o;
+                  *hp = lrelu(acc[r][i] + bj[o] + *hp, p.slope);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+      }
+      // ---------------- head fc_l3 + leaky_relu (epic.py:387-389) ----------------
+      {
+        const Lin L3 = lin[p.n_lin - 1];
+        const float* w3 = L3.Wt + (size_t)L3.m_off * L3.ldo;
+        for (int i = tid; i < R * F; i += kThreads) {
+          const int row = i / F, f = i - row * F;
+          float a = bias_of(p, L3, ev, j0 + rjet[row], f);
+          const float* hr = hs + (size_t)row * LDH;
+          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w3 + (size_t)k * L3.ldo + f), hr[k], a);
+          vbuf[i] = lrelu(a, p.slope);
+        }
+        __syncthreads();
+      }
+      // ---------------- integrator (torchdyn fixed step, restated in oracle/ode_oracle.py) ----------------
+      if (p.solver >= 0) {
+        const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
+        const int step = mid ? (ev >> 1) : ev;
+        const float dt = p.dt[step];
+        const bool first_stage = mid && ((ev & 1) == 0);
+        const float hdt = __fmul_rn(0.5f, dt);
+        for (int i = tid; i < R * F; i += kThreads) {
+          const int row = i / F, f = i - row * F;
+          const float k = -vbuf[i];
+          if (first_stage) {
+            xs[row * LDX + f] = __fadd_rn(x0[i], __fmul_rn(hdt, k));     // x + 0.5*dt*k1
+          } else {
+            const float xn = __fadd_rn(x0[i], __fmul_rn(dt, k));         // x + dt*f_(...)
+            x0[i] = xn;
+            xs[row * LDX + f] = xn;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---------------- write back: real particles from the resident buffers, padding = 0 ----------------
+    {
+      const float* src = p.solver >= 0 ? x0 : vbuf;
+      for (int j = 0; j < nj; ++j) {
+        const int n = jrow0[j + 1] - jrow0[j];
+        const float fill = n == 0 ? __int_as_float(0x7fc00000) : 0.f;   // empty jet -> NaN like the reference
+        float* dst = p.x_out + (size_t)(j0 + j) * p.N * F;
+        for (int i = tid; i < p.N * F; i += kThreads) dst[i] = fill;
+      }
+      __syncthreads();
+      for (int i = tid; i < R * F; i += kThreads) {
+        const int row = i / F, f = i - row * F;
+        const int j = rjet[row];
+        const int part = p.ridx[(size_t)(j0 + j) * p.N + (row - jrow0[j])];
+        p.x_out[((size_t)(j0 + j) * p.N + part) * F + f] = src[i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct SimtShape { int TC, RB, KC, R_cap, J_cap; SimtParams p; size_t smem; };
+
+static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s) {
+  const pfm_epic_cfg& c = h->cfg;
+  const int H = c.hid, Z = c.latent, F = c.feats;
+  if (H > 320) { set_error("fp32 path supports hid <= 320 (got %d)", H); return PFM_ERR_UNSUPPORTED; }
+  s->TC = H <= 128 ? 4 : (H <= 160 ? 5 : 10);
+  s->RB = H <= 160 ? 8 : 4;
+  const int Hp = (H + 3) & ~3;
+  const int LDH = Hp + 4;
+  const int Kxmax = c.input_dim > F ? c.input_dim : F;
+  const int LDX = ((Kxmax + 3) & ~3) + 4;
+  const int ldo_max = Hp;
+  int J_cap = (H <= 160 && Z <= 32) ? 16 : 4;
+  const int LDB = Hp, LDP = ((2 * H + Z + 3) & ~3);
+  const int CR = kWarps * s->RB;
+  const int budget = h->max_smem_optin / 4;   // floats
+  int KC = 16;
+  int R_cap = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int wbuf = KC * ldo_max + 32 * s->TC + 32;   // + slack for the unguarded column reads
+    const int per_jet = LDP + Z + Hp + 2 * LDB;
+    const int fixed = CR * LDH + 2 * wbuf + J_cap * per_jet + (J_cap + 8) + 64;
+    const int per_row = LDX + 2 * F + LDH + 1;          // xs, x0, vbuf, hs, rjet(short, rounded up)
+    R_cap = (budget - fixed) / per_row;
+    s->KC = KC;
+    if (pass == 0) {            // size the per-jet arrays for ~3x the jets that fit at full multiplicity
+      int want = R_cap > 0 ? (3 * R_cap + N - 1) / N : 1;
+      int jc = want < 2 ? 2 : (want > J_cap ? J_cap : want);
+      if (jc != J_cap) { J_cap = jc; continue; }
+    }
+    if (R_cap >= N || KC == 8) break;
+    KC = 8;
+  }
+  if (R_cap < N) {
+    set_error("fp32 path: a jet of %d particles does not fit the shared-memory row budget (%d rows at hid=%d)", N,
+              R_cap, H);
+    return PFM_ERR_UNSUPPORTED;
+  }
+  if (R_cap > 1024) R_cap = 1024;
+  s->R_cap = R_cap; s->J_cap = J_cap;
+  SimtParams& p = s->p;
+  memset(&p, 0, sizeof(p));
+  p.F = F; p.H = H; p.Hp = Hp; p.LDH = LDH; p.Z = Z; p.L = c.layers; p.n_lin = h->n_lin;
+  p.R_cap = R_cap; p.J_cap = J_cap; p.KC = s->KC; p.LDX = LDX; p.LDB = LDB; p.LDP = LDP;
+  p.sum_scale = c.sum_scale; p.slope = c.neg_slope;
+  const int wbuf = s->KC * ldo_max + 32 * s->TC + 32;
+  p.wbuf_floats = (wbuf + 3) & ~3;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  p.o_xs = take(R_cap * LDX);
+  p.o_x0 = take(R_cap * F);
+  p.o_hs = take(R_cap * LDH);
+  p.o_tmp = take(CR * LDH);
+  p.o_wbuf = take(2 * p.wbuf_floats);
+  p.o_pool = take(J_cap * LDP);
+  p.o_g = take(J_cap * Z);
+  p.o_g1 = take(J_cap * Hp);
+  p.o_bl1 = take(J_cap * LDB);
+  p.o_bl2 = take(J_cap * LDB);
+  p.o_v = take(R_cap * F);
+  p.o_int = take(J_cap + 8 + (R_cap + 1) / 2);
+  p.total_floats = o;
+  s->smem = (size_t)o * 4;
+  if ((int)s->smem > h->max_smem_optin) {
+    set_error("fp32 path: shared-memory plan %zu B exceeds the device limit %d B", s->smem, h->max_smem_optin);
+    return PFM_ERR_UNSUPPORTED;
+  }
+  (void)Kx;
+  return PFM_OK;
+}
+
+int simt_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap) {
+  SimtShape s;
+  int rc = simt_shape(h, N, 0, &s);
+  if (rc != PFM_OK) return rc;
+  *R_cap = s.R_cap; *J_cap = s.J_cap;
+  return PFM_OK;
+}
+
+template <int TC, int RB>
+static int launch_simt(const pfm_epic* h, const SimtShape& s, int grid, cudaStream_t st) {
+  auto kern = epic_simt_kernel<TC, RB>;
+  PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
+  kern<<<grid, kThreads, s.smem, st>>>(s.p);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
+  SimtShape s;
+  int rc = simt_shape(h, a.N, a.Kx, &s);
+  if (rc != PFM_OK) return rc;
+  SimtParams& p = s.p;
+  p.Kx = a.Kx; p.Kxp = (a.Kx + 3) & ~3; p.x_ld = a.Kx; p.xin_off = a.xin_off;
+  p.lin = h->lin_dev;
+  p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride;
+  p.tbias_per_jet = a.tbias_per_jet;
+  p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
+  p.counter = h->plan.counter;
+  p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
+  p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
+  // persistent CTAs: one per SM, but never more than there can be groups (every group has >= 1 jet)
+  int grid = h->sm_count < a.B ? h->sm_count : a.B;
+  if (s.TC == 4) return launch_simt<4, 8>(h, s, grid, st);
+  if (s.TC == 5) return launch_simt<5, 8>(h, s, grid, st);
+  return launch_simt<10, 4>(h, s, grid, st);
+}
+
+}  // namespace pfm

@@ -1,0 +1,430 @@
+// C ABI of libpfm_b200.so: handle management, weight repacking, jet packing plan, hoisted bias
+// tables, dispatch to the fp32 CUDA-core or bf16 tcgen05 kernels.  See include/pfm_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "pfm_internal.cuh"
+
+namespace pfm {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// weight repack:  Wt[k*ldo + o] = W[o*in + k]   (k-major fp32 copy, zero in the o-padding)
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_weight_kernel(const float* __restrict__ W, float* __restrict__ Wt, int out, int in,
+                                        int ldo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = in * ldo;
+  if (idx >= total) return;
+  int k = idx / ldo, o = idx - k * ldo;
+  Wt[idx] = (o < out) ? W[(size_t)o * in + k] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hoisted bias tables
+//   tbias[row][boff + o] = b[o] + sum_k W[o][t_off + k] * code[row][k]   (+ input-time columns of fc_l1)
+//   cbias[jet][boff + o] =        sum_k W[o][c_off + k] * cond[jet][k]
+// grid = (rows, n_lin), block = 128 threads striding over the outputs
+// ---------------------------------------------------------------------------------------------
+__global__ void tbias_kernel(const Lin* __restrict__ lin, const float* __restrict__ code, int t_dim,
+                             const float* __restrict__ code_in, int t_in, float* __restrict__ tbias, int bstride) {
+  const Lin L = lin[blockIdx.y];
+  const int row = blockIdx.x;
+  for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
+    float acc = L.b[o];
+    if (L.t_len > 0) {
+      const float* c = code + (size_t)row * t_dim;
+      for (int k = 0; k < L.t_len; ++k) acc = fmaf(L.Wt[(size_t)(L.t_off + k) * L.ldo + o], c[k], acc);
+    }
+    if (blockIdx.y == 0 && t_in > 0) {   // add_time_to_input: first t_in columns of fc_l1's main block
+      const float* c = code_in + (size_t)row * t_in;
+      for (int k = 0; k < t_in; ++k) acc = fmaf(L.Wt[(size_t)(L.m_off + k) * L.ldo + o], c[k], acc);
+    }
+    tbias[(size_t)row * bstride + L.bias_off + o] = acc;
+  }
+}
+
+__global__ void cbias_kernel(const Lin* __restrict__ lin, const float* __restrict__ cond, int cond_dim,
+                             float* __restrict__ cbias, int bstride) {
+  const Lin L = lin[blockIdx.y];
+  const int jet = blockIdx.x;
+  const float* c = cond + (size_t)jet * cond_dim;
+  for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < L.c_len; ++k) acc = fmaf(L.Wt[(size_t)(L.c_off + k) * L.ldo + o], c[k], acc);
+    cbias[(size_t)jet * bstride + L.bias_off + o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: count + compact the real particles of every jet (one warp per jet), then pack consecutive
+// jets greedily into groups of <= R_cap rows and <= J_cap jets (one CTA work item each).
+// ---------------------------------------------------------------------------------------------
+__global__ void plan_count_kernel(const float* __restrict__ mask, int B, int N, int* __restrict__ n_real,
+                                  uint16_t* __restrict__ ridx) {
+  int jet = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (jet >= B) return;
+  int count = 0;
+  for (int p0 = 0; p0 < N; p0 += 32) {
+    int p = p0 + lane;
+    bool real = p < N && (mask == nullptr || mask[(size_t)jet * N + p] != 0.f);
+    unsigned bal = __ballot_sync(0xffffffffu, real);
+    if (real) ridx[(size_t)jet * N + count + __popc(bal & ((1u << lane) - 1))] = (uint16_t)p;
+    count += __popc(bal);
+  }
+  if (lane == 0) n_real[jet] = count;
+}
+
+__global__ void plan_group_kernel(const int* __restrict__ n_real, int B, int R_cap, int J_cap,
+                                  int2* __restrict__ groups, int* __restrict__ n_groups, int* __restrict__ counter) {
+  extern __shared__ int s_n[];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s_n[i] = n_real[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int g = 0, first = 0, rows = 0, cnt = 0;
+    for (int j = 0; j < B; ++j) {
+      int n = s_n[j];
+      if (cnt > 0 && (rows + n > R_cap || cnt >= J_cap)) {
+        groups[g++] = make_int2(first, cnt);
+        first = j; rows = 0; cnt = 0;
+      }
+      rows += n; cnt += 1;
+    }
+    if (cnt > 0) groups[g++] = make_int2(first, cnt);
+    *n_groups = g;
+    *counter = 0;
+  }
+}
+
+static int ensure_plan(pfm_epic* h, int B, int N) {
+  Plan& p = h->plan;
+  if (B > p.capB) {
+    if (p.n_real) cudaFree(p.n_real);
+    if (p.groups) cudaFree(p.groups);
+    PFM_CUDA_CHECK(cudaMalloc(&p.n_real, sizeof(int) * B));
+    PFM_CUDA_CHECK(cudaMalloc(&p.groups, sizeof(int2) * B));
+    p.capB = B;
+  }
+  if ((long long)B * N > p.capBN) {
+    if (p.ridx) cudaFree(p.ridx);
+    PFM_CUDA_CHECK(cudaMalloc(&p.ridx, sizeof(uint16_t) * (size_t)B * N));
+    p.capBN = B * N;
+  }
+  if (!p.n_groups) {
+    PFM_CUDA_CHECK(cudaMalloc(&p.n_groups, sizeof(int)));
+    PFM_CUDA_CHECK(cudaMalloc(&p.counter, sizeof(int)));
+  }
+  return PFM_OK;
+}
+
+static int ensure_floats(float** buf, size_t* cap, size_t need) {
+  if (need > *cap) {
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    PFM_CUDA_CHECK(cudaMalloc(buf, sizeof(float) * need));
+    *cap = need;
+  }
+  return PFM_OK;
+}
+
+static const int kMaxJetsPerCall = 12000;   // plan_group_kernel stages n_real in 48 KB of shared memory
+
+// Everything one hot-path call needs besides the kernel itself.
+static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_jet_t, const float* t_code_in,
+                       int t_in, const float* x_in, float* x_out, const float* mask, const float* cond,
+                       int B, int N, int Kx, int xin_off, int n_evals, int solver, int n_steps,
+                       const float* dt, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  if (!h->weights_set) { set_error("weights not set (call pfm_epic_set_weights first)"); return PFM_ERR_STATE; }
+  if (B <= 0 || N <= 0) { set_error("B and N must be positive (B=%d N=%d)", B, N); return PFM_ERR_INVALID; }
+  if (N > 65535) { set_error("N=%d exceeds 65535", N); return PFM_ERR_INVALID; }
+  const int cond_dim = c.global_cond_dim > c.local_cond_dim ? c.global_cond_dim : c.local_cond_dim;
+  if (cond_dim > 0 && cond == nullptr) { set_error("cond is NULL but the net is conditioned"); return PFM_ERR_INVALID; }
+  const bool any_t = (c.t_local_cat || c.t_global_cat) && c.t_dim > 0;
+  if ((any_t || t_in > 0) && t_code == nullptr && t_code_in == nullptr) {
+    set_error("time code is NULL but the net takes a time code"); return PFM_ERR_INVALID;
+  }
+  cudaError_t e0 = cudaSetDevice(h->device);
+  if (e0 != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e0)); return PFM_ERR_CUDA; }
+  h->last_launches = 0;
+  h->last_groups_host = 0;
+
+  int R_cap = 0, J_cap = 0, rc;
+  if (h->precision == PFM_PREC_BF16) {
+    rc = tc_supported(h, N);
+    if (rc != PFM_OK) return rc;
+    rc = tc_plan_caps(h, N, &R_cap, &J_cap);
+  } else {
+    rc = simt_plan_caps(h, N, &R_cap, &J_cap);
+  }
+  if (rc != PFM_OK) return rc;
+
+  // time bias table: shared by all jets (rows = evaluations) or one row per jet
+  const int trows = per_jet_t ? B : (t_rows > 0 ? t_rows : 1);
+  rc = ensure_floats(&h->tbias, &h->tbias_cap, (size_t)trows * h->bstride);
+  if (rc != PFM_OK) return rc;
+  tbias_kernel<<<dim3(trows, h->n_lin), 128, 0, st>>>(h->lin_dev, t_code, c.t_dim, t_code_in, t_in, h->tbias,
+                                                     h->bstride);
+  h->last_launches++;
+  if (cond_dim > 0) {
+    rc = ensure_floats(&h->cbias, &h->cbias_cap, (size_t)B * h->bstride);
+    if (rc != PFM_OK) return rc;
+    cbias_kernel<<<dim3(B, h->n_lin), 128, 0, st>>>(h->lin_dev, cond, cond_dim, h->cbias, h->bstride);
+    h->last_launches++;
+  }
+  PFM_CUDA_CHECK(cudaGetLastError());
+
+  for (int b0 = 0; b0 < B; b0 += kMaxJetsPerCall) {
+    const int nb = (B - b0 < kMaxJetsPerCall) ? (B - b0) : kMaxJetsPerCall;
+    rc = ensure_plan(h, nb, N);
+    if (rc != PFM_OK) return rc;
+    const float* mk = mask ? mask + (size_t)b0 * N : nullptr;
+    plan_count_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mk, nb, N, h->plan.n_real, h->plan.ridx);
+    plan_group_kernel<<<1, 1024, sizeof(int) * nb, st>>>(h->plan.n_real, nb, R_cap, J_cap, h->plan.groups,
+                                                         h->plan.n_groups, h->plan.counter);
+    h->last_launches += 2;
+    PFM_CUDA_CHECK(cudaGetLastError());
+    RunArgs a;
+    a.x_in = x_in + (size_t)b0 * N * Kx;
+    a.x_out = x_out + (size_t)b0 * N * c.feats;
+    a.B = nb; a.N = N; a.Kx = Kx; a.xin_off = xin_off;
+    a.n_evals = n_evals; a.solver = solver; a.n_steps = n_steps; a.dt = dt;
+    a.tbias_per_jet = per_jet_t ? 1 : 0;
+    a.has_cbias = cond_dim > 0;
+    // per-jet tables are indexed by the jet index inside this chunk
+    float* tb_save = h->tbias; float* cb_save = h->cbias;
+    if (per_jet_t) h->tbias += (size_t)b0 * h->bstride;
+    if (cond_dim > 0) h->cbias += (size_t)b0 * h->bstride;
+    rc = (h->precision == PFM_PREC_BF16) ? tc_run(h, a, st) : simt_run(h, a, st);
+    h->tbias = tb_save; h->cbias = cb_save;
+    if (rc != PFM_OK) return rc;
+    h->last_launches++;
+  }
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+}  // namespace pfm
+
+using namespace pfm;
+
+// =============================================================================================
+// exported C ABI
+// =============================================================================================
+extern "C" {
+
+int pfm_version(void) { return PFM_VERSION; }
+
+const char* pfm_last_error(void) { return g_err; }
+
+static void linear_layout(const pfm_epic_cfg& c, int i, int n_lin, Lin* L) {
+  const int H = c.hid, Z = c.latent;
+  const int tl = c.t_local_cat ? c.t_dim : 0, tg = c.t_global_cat ? c.t_dim : 0;
+  const int cl = c.local_cond_dim, cg = c.global_cond_dim;
+  memset(L, 0, sizeof(Lin));
+  bool local;
+  int main_len, g_len = 0, out;
+  if (i == LIN_L1) { local = true; main_len = c.input_dim; out = H; }
+  else if (i == LIN_L2) { local = true; main_len = H; out = H; }
+  else if (i == LIN_G1) { local = false; main_len = 2 * H; out = H; }
+  else if (i == LIN_G2) { local = false; main_len = H; out = Z; }
+  else if (i == n_lin - 1) { local = true; main_len = H; out = c.feats; }
+  else {
+    int r = (i - LIN_LAYER0) & 3;
+    if (r == 0) { local = false; main_len = 2 * H + Z; out = H; }
+    else if (r == 1) { local = false; main_len = H; out = Z; }
+    else if (r == 2) { local = true; main_len = H; g_len = Z; out = H; }
+    else { local = true; main_len = H; out = H; }
+  }
+  L->out = out;
+  L->t_off = 0; L->t_len = local ? tl : tg;
+  L->m_off = L->t_len; L->m_len = main_len;
+  L->g_off = L->m_off + main_len; L->g_len = g_len;
+  L->c_off = L->g_off + g_len; L->c_len = local ? cl : cg;
+  L->in = L->c_off + L->c_len;
+  L->ldo = round_up(out, 4);
+}
+
+int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
+  if (!cfg || !out) { set_error("null argument"); return PFM_ERR_INVALID; }
+  *out = nullptr;
+  const pfm_epic_cfg& c = *cfg;
+  if (c.feats <= 0 || c.input_dim <= 0 || c.hid <= 0 || c.latent <= 0 || c.layers < 0 || c.t_dim < 0) {
+    set_error("invalid dims: feats=%d input_dim=%d hid=%d latent=%d layers=%d t_dim=%d", c.feats, c.input_dim,
+              c.hid, c.latent, c.layers, c.t_dim);
+    return PFM_ERR_INVALID;
+  }
+  if (c.local_cond_dim != 0 && c.local_cond_dim != c.global_cond_dim && c.global_cond_dim != 0) {
+    set_error("local_cond_dim (%d) must be 0 or equal to global_cond_dim (%d): the reference feeds ONE cond tensor "
+              "to both (epic.py:347-357)", c.local_cond_dim, c.global_cond_dim);
+    return PFM_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); libpfm_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return PFM_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return PFM_ERR_INVALID; }
+  PFM_CUDA_CHECK(cudaSetDevice(device));
+  pfm_epic* h = new pfm_epic();
+  h->cfg = c;
+  h->device = device;
+  h->n_lin = 4 + 4 * c.layers + 1;
+  h->precision = PFM_PREC_FP32;
+  h->weights_set = false;
+  h->lin_dev = nullptr; h->wt_store = nullptr; h->b_store = nullptr; h->tc_store = nullptr; h->tc_bytes = 0;
+  h->tbias = nullptr; h->tbias_cap = 0; h->cbias = nullptr; h->cbias_cap = 0;
+  memset(&h->plan, 0, sizeof(h->plan));
+  h->last_launches = 0; h->last_groups_host = 0;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  h->lin_host.resize(h->n_lin);
+  size_t wt = 0, bf = 0;
+  int boff = 0;
+  for (int i = 0; i < h->n_lin; ++i) {
+    Lin& L = h->lin_host[i];
+    linear_layout(c, i, h->n_lin, &L);
+    L.bias_off = boff;
+    boff += L.ldo;
+    wt += (size_t)(L.in + 8) * L.ldo;   // +8 slack rows: kernels may read (never use) up to 3 rows past a block
+    bf += L.ldo;
+  }
+  h->bstride = boff;
+  h->wt_floats = wt + 1024;
+  h->b_floats = bf;
+  cudaError_t e1 = cudaMalloc(&h->wt_store, sizeof(float) * h->wt_floats);
+  cudaError_t e2 = cudaMalloc(&h->b_store, sizeof(float) * h->b_floats);
+  cudaError_t e3 = cudaMalloc(&h->lin_dev, sizeof(Lin) * h->n_lin);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    set_error("cudaMalloc failed for packed weights");
+    pfm_epic_destroy(h);
+    return PFM_ERR_CUDA;
+  }
+  cudaMemset(h->wt_store, 0, sizeof(float) * h->wt_floats);
+  cudaMemset(h->b_store, 0, sizeof(float) * h->b_floats);
+  size_t wo = 0, bo = 0;
+  for (int i = 0; i < h->n_lin; ++i) {
+    Lin& L = h->lin_host[i];
+    L.Wt = h->wt_store + wo;
+    L.b = h->b_store + bo;
+    wo += (size_t)(L.in + 8) * L.ldo;
+    bo += L.ldo;
+  }
+  cudaMemcpy(h->lin_dev, h->lin_host.data(), sizeof(Lin) * h->n_lin, cudaMemcpyHostToDevice);
+  *out = h;
+  return PFM_OK;
+}
+
+void pfm_epic_destroy(pfm_epic* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->lin_dev) cudaFree(h->lin_dev);
+  if (h->wt_store) cudaFree(h->wt_store);
+  if (h->b_store) cudaFree(h->b_store);
+  if (h->tc_store) cudaFree(h->tc_store);
+  if (h->tbias) cudaFree(h->tbias);
+  if (h->cbias) cudaFree(h->cbias);
+  if (h->plan.n_real) cudaFree(h->plan.n_real);
+  if (h->plan.ridx) cudaFree(h->plan.ridx);
+  if (h->plan.groups) cudaFree(h->plan.groups);
+  if (h->plan.n_groups) cudaFree(h->plan.n_groups);
+  if (h->plan.counter) cudaFree(h->plan.counter);
+  delete h;
+}
+
+int pfm_epic_num_linears(const pfm_epic* h) { return h ? h->n_lin : PFM_ERR_INVALID; }
+
+int pfm_epic_linear_shape(const pfm_epic* h, int i, int32_t* out_features, int32_t* in_features) {
+  if (!h || i < 0 || i >= h->n_lin) { set_error("linear index out of range"); return PFM_ERR_INVALID; }
+  if (out_features) *out_features = h->lin_host[i].out;
+  if (in_features) *in_features = h->lin_host[i].in;
+  return PFM_OK;
+}
+
+int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* const* biases, int n,
+                         void* stream) {
+  if (!h || !weights || !biases) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (n != h->n_lin) { set_error("expected %d linears, got %d", h->n_lin, n); return PFM_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PFM_CUDA_CHECK(cudaSetDevice(h->device));
+  for (int i = 0; i < n; ++i) {
+    const Lin& L = h->lin_host[i];
+    if (!weights[i] || !biases[i]) { set_error("null weight/bias pointer for linear %d", i); return PFM_ERR_INVALID; }
+    int total = L.in * L.ldo;
+    transpose_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(weights[i], const_cast<float*>(L.Wt), L.out, L.in,
+                                                                 L.ldo);
+    PFM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(L.b), biases[i], sizeof(float) * L.out,
+                                   cudaMemcpyDeviceToDevice, st));
+  }
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->weights_set = true;
+  if (h->precision == PFM_PREC_BF16) {
+    int rc = tc_pack_weights(h, st);
+    if (rc != PFM_OK) return rc;
+  }
+  return PFM_OK;
+}
+
+int pfm_epic_set_precision(pfm_epic* h, int precision) {
+  if (!h) { set_error("null handle"); return PFM_ERR_INVALID; }
+  if (precision != PFM_PREC_FP32 && precision != PFM_PREC_BF16) { set_error("unknown precision %d", precision); return PFM_ERR_INVALID; }
+  if (precision == PFM_PREC_BF16) {
+    int rc = tc_supported(h, 1);
+    if (rc != PFM_OK) return rc;
+  }
+  int old = h->precision;
+  h->precision = precision;
+  if (precision == PFM_PREC_BF16 && h->weights_set && (old != precision || !h->tc_store)) {
+    int rc = tc_pack_weights(h, 0);
+    if (rc != PFM_OK) { h->precision = old; return rc; }
+  }
+  return PFM_OK;
+}
+
+int pfm_epic_forward(pfm_epic* h, const float* t_code, int t_rows, const float* x, const float* mask,
+                     const float* cond, float* out, int B, int N, void* stream) {
+  if (!h || !x || !out) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (t_rows != 1 && t_rows != B) { set_error("t_rows must be 1 or B (got %d, B=%d)", t_rows, B); return PFM_ERR_INVALID; }
+  const bool per_jet = (t_rows == B) && B > 1;
+  return run_chunked(h, t_code, per_jet ? B : 1, per_jet, nullptr, 0, x, out, mask, cond, B, N, h->cfg.input_dim, 0,
+                     1, -1, 0, nullptr, (cudaStream_t)stream);
+}
+
+int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float* cond, const float* t_codes,
+                    const float* t_codes_in, const float* dt, int solver, int n_steps, int B, int N, void* stream) {
+  if (!h || !x_inout || !dt) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (solver != PFM_SOLVER_EULER && solver != PFM_SOLVER_MIDPOINT) { set_error("unknown solver %d", solver); return PFM_ERR_INVALID; }
+  if (n_steps <= 0) { set_error("n_steps must be positive"); return PFM_ERR_INVALID; }
+  const int t_in = h->cfg.input_dim - h->cfg.feats;
+  if (t_in < 0) { set_error("input_dim < feats"); return PFM_ERR_INVALID; }
+  if (t_in > 0 && !t_codes_in) { set_error("input_dim > feats needs t_codes_in (add_time_to_input)"); return PFM_ERR_INVALID; }
+  const int n_evals = n_steps * (solver == PFM_SOLVER_MIDPOINT ? 2 : 1);
+  return run_chunked(h, t_codes, n_evals, false, t_codes_in, t_in, x_inout, x_inout, mask, cond, B, N, h->cfg.feats,
+                     t_in, n_evals, solver, n_steps, dt, (cudaStream_t)stream);
+}
+
+int pfm_epic_last_launches(const pfm_epic* h) { return h ? h->last_launches : PFM_ERR_INVALID; }
+
+int pfm_epic_last_groups(const pfm_epic* h) {
+  if (!h || !h->plan.n_groups) return PFM_ERR_INVALID;
+  int g = 0;
+  cudaSetDevice(h->device);
+  if (cudaMemcpy(&g, h->plan.n_groups, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return PFM_ERR_CUDA;
+  return g;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Internal declarations shared by the translation units of libpfm_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pfm_b200.h"
+
+namespace pfm {
+
+// One weight-normed linear of the encoder after folding, split by what its input columns multiply
+// (concat orders: epic.py:361,365,376,379 stem; :180-196 layers; :388 head).
+//   [ time | main | (global, fc_local1 only) | cond ]
+struct Lin {
+  int out, in;
+  int t_off, t_len;   // time-code columns          -> hoisted into the per-evaluation bias table
+  int m_off, m_len;   // per-particle (local linears) or per-jet vector (global linears) columns
+  int g_off, g_len;   // fc_local1: columns multiplying the broadcast global vector
+  int c_off, c_len;   // conditioning columns       -> hoisted into the per-jet bias table
+  int bias_off;       // offset of this linear inside one bias-table row
+  int ldo;            // leading dimension of the k-major (transposed) fp32 copy, round_up(out, 4)
+  const float* Wt;    // k-major fp32 copy  Wt[k*ldo + o] = W[o][k],  k in [0, in)  (+ slack rows)
+  const float* b;     // [out]
+};
+
+enum LinIdx { LIN_L1 = 0, LIN_L2 = 1, LIN_G1 = 2, LIN_G2 = 3, LIN_LAYER0 = 4 };
+// layer l: LIN_LAYER0 + 4*l + {0: fc_global1, 1: fc_global2, 2: fc_local1, 3: fc_local2}; last: fc_l3
+
+struct Plan {          // device buffers describing how jets are packed into CTA work groups
+  int* n_real;         // [B]     real particles per jet
+  uint16_t* ridx;      // [B*N]   ridx[b*N + r] = particle index of the r-th real particle of jet b
+  int2* groups;        // [B]     (first jet, number of jets) of every group
+  int* n_groups;       // [1]
+  int* counter;        // [1]     dynamic work counter for persistent CTAs
+  int capB, capBN;
+};
+
+}  // namespace pfm
+
+struct pfm_epic {
+  pfm_epic_cfg cfg;
+  int device;
+  int n_lin;
+  int precision;
+  bool weights_set;
+  int sm_count;
+  int max_smem_optin;
+  std::vector<pfm::Lin> lin_host;   // host copy (device pointers inside)
+  pfm::Lin* lin_dev;                // device copy of the descriptors
+  float* wt_store;                  // all k-major fp32 copies
+  float* b_store;                   // all biases
+  size_t wt_floats, b_floats;
+  int bstride;                      // floats per bias-table row
+  // bf16 tensor-core path: pre-swizzled shared-memory images of the H x H per-particle weights
+  void* tc_store;
+  size_t tc_bytes;
+  // workspaces (grown on demand)
+  float* tbias; size_t tbias_cap;   // [rows, bstride]  b + W_t . time_code
+  float* cbias; size_t cbias_cap;   // [B, bstride]     W_c . cond
+  pfm::Plan plan;
+  int last_launches, last_groups_host;
+};
+
+namespace pfm {
+
+void set_error(const char* fmt, ...);
+#define PFM_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      pfm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PFM_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+struct RunArgs {
+  const float* x_in;      // forward: [B,N,input_dim]; sample: [B,N,feats] (in/out)
+  float* x_out;           // forward: [B,N,feats];     sample: same buffer as x_in
+  int B, N;
+  int Kx;                 // per-particle input columns read from x_in (input_dim or feats)
+  int xin_off;            // first row of fc_l1's main block used for those columns
+  int n_evals;            // network evaluations (1 for forward)
+  int solver;             // -1: forward only; else pfm_solver
+  int n_steps;
+  const float* dt;        // [n_steps] device
+  int tbias_per_jet;      // 0: bias-table row = evaluation index; 1: row = jet index
+  bool has_cbias;
+};
+
+// fp32 CUDA-core path (epic_simt.cu)
+int simt_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap);
+int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st);
+// bf16 tcgen05 path (epic_tc.cu)
+int tc_supported(const pfm_epic* h, int N);
+int tc_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap);
+int tc_pack_weights(pfm_epic* h, cudaStream_t st);
+int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st);
+
+}  // namespace pfm

@@ -1,0 +1,179 @@
+"""Host-side handle around the C ABI: owns one ``pfm_epic`` per (module, device) and feeds it torch
+CUDA tensors as raw device pointers.  PyTorch is plumbing here (device memory + streams)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+@dataclass(frozen=True)
+class EpicDims:
+    """Resolved EPiC_encoder constructor arguments (epic.py:226-243)."""
+    feats: int
+    input_dim: int
+    hid: int
+    latent: int
+    layers: int
+    t_dim: int
+    t_local_cat: bool
+    t_global_cat: bool
+    global_cond_dim: int = 0
+    local_cond_dim: int = 0
+    sum_scale: float = 1e-2
+    neg_slope: float = 0.01
+
+    @property
+    def cond_dim(self) -> int:
+        return max(self.global_cond_dim, self.local_cond_dim)
+
+    @property
+    def takes_time(self) -> bool:
+        return self.t_dim > 0 and (self.t_local_cat or self.t_global_cat)
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: Tensor, device) -> Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class EpicEngine:
+    """One packed copy of the network on one GPU."""
+
+    def __init__(self, dims: EpicDims, device: torch.device, precision: str = "fp32"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.PfmError(f"particle_fm_b200 runs on CUDA devices only (got {device}); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.dims = dims
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        cfg = _lib.EpicCfgC(dims.feats, dims.input_dim, dims.hid, dims.latent, dims.layers, dims.t_dim,
+                            int(dims.t_local_cat), int(dims.t_global_cat), dims.global_cond_dim, dims.local_cond_dim,
+                            dims.sum_scale, dims.neg_slope)
+        h = C.c_void_p()
+        _lib.check(self.lib.pfm_epic_create(C.byref(cfg), self.index, C.byref(h)), "pfm_epic_create")
+        self._h = h
+        self.n_lin = self.lib.pfm_epic_num_linears(self._h)
+        self.precision = "fp32"
+        self.set_precision(precision)
+        self.weights_key = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pfm_epic_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_precision(self, precision: str):
+        code = {"fp32": _lib.PFM_PREC_FP32, "bf16": _lib.PFM_PREC_BF16}.get(precision)
+        if code is None:
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        _lib.check(self.lib.pfm_epic_set_precision(self._h, code), "pfm_epic_set_precision")
+        self.precision = precision
+
+    def linear_shapes(self):
+        out = []
+        o, i = C.c_int32(), C.c_int32()
+        for k in range(self.n_lin):
+            _lib.check(self.lib.pfm_epic_linear_shape(self._h, k, C.byref(o), C.byref(i)), "pfm_epic_linear_shape")
+            out.append((o.value, i.value))
+        return out
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_weights(self, weights: Sequence[Tensor], biases: Sequence[Tensor], key=None):
+        """weights[i]: folded [out,in] fp32; biases[i]: [out]; order = state_dict order of the linears."""
+        if len(weights) != self.n_lin or len(biases) != self.n_lin:
+            raise ValueError(f"expected {self.n_lin} linears, got {len(weights)}/{len(biases)}")
+        ws = [_f32c(w, self.device) for w in weights]
+        bs = [_f32c(b, self.device) for b in biases]
+        for k, ((o, i), w, b) in enumerate(zip(self.linear_shapes(), ws, bs)):
+            if tuple(w.shape) != (o, i) or tuple(b.shape) != (o,):
+                raise ValueError(f"linear {k}: expected weight {(o, i)} / bias {(o,)}, got {tuple(w.shape)} / {tuple(b.shape)}")
+        wp = (C.c_void_p * self.n_lin)(*[w.data_ptr() for w in ws])
+        bp = (C.c_void_p * self.n_lin)(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_set_weights(self._h, wp, bp, self.n_lin, self._stream()), "pfm_epic_set_weights")
+        self._keepalive = (ws, bs)      # until the stream has consumed them
+        self.weights_key = key
+
+    # -- hot path ------------------------------------------------------------------------------
+    def forward(self, t_code: Optional[Tensor], x: Tensor, mask: Optional[Tensor], cond: Optional[Tensor]) -> Tensor:
+        """t_code [1|B, t_dim], x [B,N,input_dim], mask [B,N] (or [B,N,1]), cond [B,C] -> [B,N,feats]."""
+        d = self.dims
+        B, N = int(x.shape[0]), int(x.shape[1])
+        x = _f32c(x, self.device)
+        if x.shape[2] != d.input_dim:
+            raise ValueError(f"x has {x.shape[2]} columns, the net expects input_dim={d.input_dim}")
+        mask = None if mask is None else _f32c(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        t_rows = 1
+        if d.takes_time:
+            if t_code is None:
+                raise ValueError("t_local_cat/t_global_cat is set but no time code was given (epic.py:317-321)")
+            t_code = _f32c(t_code, self.device).reshape(-1, d.t_dim)
+            t_rows = int(t_code.shape[0])
+            if t_rows not in (1, B):
+                raise ValueError(f"time code must have 1 or B={B} rows, got {t_rows}")
+        else:
+            t_code = None
+        out = torch.empty(B, N, d.feats, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_forward(self._h, _ptr(t_code), t_rows, _ptr(x), _ptr(mask), _ptr(cond),
+                                                 _ptr(out), B, N, self._stream()), "pfm_epic_forward")
+        return out
+
+    def sample(self, z: Tensor, mask: Optional[Tensor], cond: Optional[Tensor], t_codes: Optional[Tensor],
+               t_codes_in: Optional[Tensor], dt: Tensor, solver: str) -> Tensor:
+        """Integrate in place on a copy of z [B,N,feats] (already masked).  t_codes [n_evals,t_dim]."""
+        d = self.dims
+        B, N = int(z.shape[0]), int(z.shape[1])
+        x = z.detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+        mask = None if mask is None else _f32c(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        code = {"euler": _lib.PFM_SOLVER_EULER, "midpoint": _lib.PFM_SOLVER_MIDPOINT}[solver]
+        dt = _f32c(dt, self.device).reshape(-1)
+        n_steps = int(dt.numel())
+        n_evals = n_steps * (2 if solver == "midpoint" else 1)
+        if t_codes is not None:
+            t_codes = _f32c(t_codes, self.device).reshape(n_evals, -1)
+        if t_codes_in is not None:
+            t_codes_in = _f32c(t_codes_in, self.device).reshape(n_evals, -1)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_sample(self._h, _ptr(x), _ptr(mask), _ptr(cond), _ptr(t_codes),
+                                                _ptr(t_codes_in), _ptr(dt), code, n_steps, B, N, self._stream()),
+                       "pfm_epic_sample")
+        return x
+
+    def _cond(self, cond: Optional[Tensor], B: int) -> Optional[Tensor]:
+        d = self.dims
+        if d.cond_dim == 0:
+            return None        # unconditional nets ignore whatever cond the datamodule hands over (epic.py:347-350)
+        if cond is None:
+            raise ValueError(f"global_cond_dim={d.global_cond_dim}, local_cond_dim={d.local_cond_dim} but cond is None "
+                             "(epic.py:309-313)")
+        cond = _f32c(cond, self.device).reshape(B, -1)
+        if cond.shape[1] != d.cond_dim:
+            raise ValueError(f"cond has {cond.shape[1]} columns, expected {d.cond_dim}")
+        return cond
+
+    def last_launches(self) -> int:
+        return int(self.lib.pfm_epic_last_launches(self._h))
+
+    def last_groups(self) -> int:
+        return int(self.lib.pfm_epic_last_groups(self._h))
