@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: EPiC-FM JetNet-150 generation, jets/s (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--precision fp32|bf16] [--batch B]
+    python bench.py --impl reference ...          # the CPU port of the reference, same metric/config
+
+A "step" is one full ``sample()`` pass of one batch of B jets per GPU: midpoint, ode_steps=200
+(199 steps, 398 network evaluations), random-init default JetNet net (configs/model/flow_matching.yaml),
+synthetic variable-multiplicity prefix masks (n_real ~ U[15,150]).  Jets are sharded over the ranks
+(no data-path collective; a final gather of the results to rank 0 is inside the timed region for N>1).
+
+value     device-timed throughput with the step's inputs already resident in HBM
+e2e       the same through the public API (SetFlowMatchingLitModule.sample(...).cpu()): CPU-generator
+          noise, pinned-host -> device copies and the device -> host read of the result inside the timing
+roofline  algorithmic FLOPs of the fused network/integrator kernel (real particles only, hoisted form,
+          SURVEY 8d) / its CUDA-event duration, against MEASURED_PEAKS.json
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PART, FEATS, ODE_STEPS, SOLVER = 150, 3, 200, "midpoint"
+NFE = 2 * (ODE_STEPS - 1)
+YAML_NET = dict(features=FEATS, hidden_dim=128, num_particles=N_PART, frequencies=16, layers=6, latent=10,
+                t_emb="cosine", t_local_cat=True, t_global_cat=True, add_time_to_input=False)
+WORKLOAD = ("EPiC-FM JetNet-150 (150x3, variable-multiplicity masks) midpoint ode_steps=200 generation, "
+            "random-init default net (H128 Z10 L6 T32), jets sharded over ranks")
+# FLOP per real particle per evaluation and per jet per evaluation (hoisted form)
+FLOP_PER_PARTICLE, FLOP_PER_JET = 427_520, 684_096
+
+
+def synth_masks(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    n_real = torch.randint(max(1, N_PART // 10), N_PART + 1, (B,), generator=g)
+    mask = (torch.arange(N_PART)[None, :] < n_real[:, None]).float().unsqueeze(-1)
+    return mask, n_real
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6552.0), tf_burst=d.get("bf16_tflops", 1648.4),
+                    tf_sustained=d.get("bf16_tflops_sustained", 1383.1), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_sampler():
+    """CPU port of the reference path (oracle/): same net, same seeds, fp32, all host threads."""
+    from oracle import epic_oracle as eo, loss_oracle as lo
+    cfg = eo.EpicCfg(feats=FEATS, input_dim=FEATS, hid=128, latent=10, layers=6, t_dim=32, t_local_cat=True,
+                     t_global_cat=True)
+    torch.manual_seed(12345)
+    from particle_fm_b200.models.flow_matching_module import SetFlowMatchingLitModule
+    m = SetFlowMatchingLitModule(optimizer=None, **YAML_NET)            # default init, seed 12345 (fm_tops150.yaml:19)
+    sd = {k[len("flows.0.net."):]: v.detach() for k, v in m.state_dict().items() if k.startswith("flows.0.net.")}
+
+    def run(z, mask):
+        vf = lambda t, y: eo.cnf_forward(sd, cfg, t, y, None, mask, t_emb="cosine", frequencies=16,
+                                         add_time_to_input=False)
+        with torch.no_grad():
+            return lo.sample(vf, z, mask, SOLVER, ODE_STEPS)
+    return run
+
+
+def time_cpu(run, n_jets, seed, reps=1):
+    mask, n_real = synth_masks(n_jets, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    z = torch.randn(n_jets, N_PART, FEATS, generator=g)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run(z, mask)
+    dt = (time.perf_counter() - t0) / reps
+    return n_jets / dt, dt, float(n_real.float().mean())
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; torchdyn/Lightning are
+    not installable here), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    run = oracle_sampler()
+    n_jets = args.ref_jets
+    for _ in range(max(1, min(args.warmup, 1))):
+        time_cpu(run, n_jets, 9999)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        time_cpu(run, n_jets, 9999 + s)
+    dt = time.perf_counter() - t0
+    value = n_jets * args.steps / dt
+    sample = f"{n_jets} jets per step, full midpoint ode_steps=200 (398 evaluations), mean multiplicity ~82"
+    line = {"impl": "reference", "metric": "generated_jets_per_s", "value": value, "unit": "jets/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ode_steps": ODE_STEPS, "solver": SOLVER, "nfe": NFE},
+            "cpu_baseline": {"value": value, "unit": "jets/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PFM_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=0, help="jets per GPU per step (default: 16384 bf16 / 4096 fp32)")
+    ap.add_argument("--all-real", action="store_true", help="every particle real (roofline variant)")
+    ap.add_argument("--ref-jets", type=int, default=8, help="jets per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-jets", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3                                            # timing rule: >= 3 warm-up steps
+
+    import torch.distributed as dist
+    from particle_fm_b200.models.flow_matching_module import SetFlowMatchingLitModule
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or (16384 if args.precision == "bf16" else 4096)
+
+    torch.manual_seed(12345)                                       # the configs' seed (fm_tops150.yaml:19)
+    model = SetFlowMatchingLitModule(optimizer=None, **YAML_NET).to(dev)
+    model.set_precision(args.precision)
+    cnf = model.flows[0]
+    eng = cnf.net.engine()
+    eng.set_timing(True)
+
+    # this rank's shard of the request: masks + CPU-generator noise, resident in HBM before the timed region
+    mask_h, n_real = synth_masks(B, 9999 + rank)
+    if args.all_real:
+        mask_h = torch.ones_like(mask_h); n_real = torch.full_like(n_real, N_PART)
+    g = torch.Generator().manual_seed(4242 + rank)
+    z_h = torch.randn(B, N_PART, FEATS, generator=g) * mask_h
+    mask_d, z_d = mask_h.to(dev), z_h.to(dev)
+    gather_buf = [torch.empty(B, N_PART, FEATS, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step():
+        out = cnf.decode(z_d, None, mask_d, ode_solver=SOLVER, ode_steps=ODE_STEPS)
+        if world > 1:
+            dist.gather(out, gather_buf, dst=0)
+        return out
+
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = eng.last_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                                      # flush L2 between timed iterations (not timed)
+        ev[s][0].record()
+        step()
+        ev[s][1].record()
+        ev[s][1].synchronize()
+        kernel_ms.append(eng.last_kernel_ms())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public API: CPU noise, H2D of inputs, integration, D2H of the result ----
+    mask_pin = mask_h.pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS).cpu()       # warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS).cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+    h2d = B * N_PART * FEATS * 4 + B * N_PART * 4 + NFE * 32 * 4 + (ODE_STEPS - 1) * 4
+    d2h = B * N_PART * FEATS * 4
+
+    if rank == 0:
+        peaks = measured_peaks()
+        flops = (float(n_real.sum()) * FLOP_PER_PARTICLE + B * FLOP_PER_JET) * NFE          # per launch, this rank
+        k_ms = statistics.mean(kernel_ms)
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        peak = peaks["tf_sustained"]
+        line = {"metric": "generated_jets_per_s", "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "ode_steps": ODE_STEPS, "solver": SOLVER, "nfe": NFE,
+                           "precision": args.precision, "mean_real_particles": float(n_real.float().mean()),
+                           "all_real": bool(args.all_real), "l2": "flushed between timed steps (256 MB write)",
+                           "parallelism": f"jets sharded x{world}, final gather to rank 0"},
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "SetFlowMatchingLitModule.sample(n, mask=pinned).cpu()"},
+                "gpu_launches": launches_per_step * args.steps,
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "kernel": "epic_tc_kernel" if args.precision == "bf16" else "epic_simt_kernel",
+                             "kernel_ms": k_ms, "algorithmic_flop_per_launch": flops,
+                             "peak_source": f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)"}}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            run = oracle_sampler()
+            jps, secs, mean_n = time_cpu(run, args.cpu_baseline_jets, 9999)
+            line["cpu_baseline"] = {"value": jps, "unit": "jets/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_baseline_jets} jets of the same workload (full 398 evaluations, "
+                                              f"mean multiplicity {mean_n:.1f}), {secs:.1f} s, torch CPU fp32 oracle"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,12 @@ int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float*
 int pfm_epic_last_launches(const pfm_epic* h);
 int pfm_epic_last_groups(const pfm_epic* h);
 
+/* Optional device-side timing of the dominant (fused network/integrator) kernel: when enabled, CUDA
+ * events are recorded on the launching stream around that kernel only.  pfm_epic_last_kernel_ms
+ * synchronises on the stop event and returns the summed duration of the last call (ms), < 0 if none. */
+int pfm_epic_set_timing(pfm_epic* h, int enable);
+float pfm_epic_last_kernel_ms(pfm_epic* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "pfm_epic_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),
+    "pfm_epic_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "pfm_epic_last_kernel_ms": (C.c_float, [C.c_void_p]),
 }
 
 _lib = None

@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs]
     subprocess.run(link, check=True)
     for o in objs:
         os.remove(o)

@@ -160,6 +160,7 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
   if (e0 != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e0)); return PFM_ERR_CUDA; }
   h->last_launches = 0;
   h->last_groups_host = 0;
+  h->ev_used = 0;
 
   int R_cap = 0, J_cap = 0, rc;
   if (h->precision == PFM_PREC_BF16) {
@@ -207,7 +208,19 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
     float* tb_save = h->tbias; float* cb_save = h->cbias;
     if (per_jet_t) h->tbias += (size_t)b0 * h->bstride;
     if (cond_dim > 0) h->cbias += (size_t)b0 * h->bstride;
+    cudaEvent_t e_start = nullptr, e_stop = nullptr;
+    if (h->timing) {
+      while ((int)h->ev_pool.size() < h->ev_used + 2) {
+        cudaEvent_t e;
+        PFM_CUDA_CHECK(cudaEventCreate(&e));
+        h->ev_pool.push_back(e);
+      }
+      e_start = h->ev_pool[h->ev_used]; e_stop = h->ev_pool[h->ev_used + 1];
+      h->ev_used += 2;
+      PFM_CUDA_CHECK(cudaEventRecord(e_start, st));
+    }
     rc = (h->precision == PFM_PREC_BF16) ? tc_run(h, a, st) : simt_run(h, a, st);
+    if (h->timing && rc == PFM_OK) PFM_CUDA_CHECK(cudaEventRecord(e_stop, st));
     h->tbias = tb_save; h->cbias = cb_save;
     if (rc != PFM_OK) return rc;
     h->last_launches++;
@@ -290,6 +303,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->tbias = nullptr; h->tbias_cap = 0; h->cbias = nullptr; h->cbias_cap = 0;
   memset(&h->plan, 0, sizeof(h->plan));
   h->last_launches = 0; h->last_groups_host = 0;
+  h->timing = false; h->ev_used = 0;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   h->lin_host.resize(h->n_lin);
@@ -343,6 +357,7 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->plan.groups) cudaFree(h->plan.groups);
   if (h->plan.n_groups) cudaFree(h->plan.n_groups);
   if (h->plan.counter) cudaFree(h->plan.counter);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -425,6 +440,25 @@ int pfm_epic_last_groups(const pfm_epic* h) {
   cudaSetDevice(h->device);
   if (cudaMemcpy(&g, h->plan.n_groups, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return PFM_ERR_CUDA;
   return g;
+}
+
+int pfm_epic_set_timing(pfm_epic* h, int enable) {
+  if (!h) { set_error("null handle"); return PFM_ERR_INVALID; }
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return PFM_OK;
+}
+
+float pfm_epic_last_kernel_ms(pfm_epic* h) {
+  if (!h || !h->timing || h->ev_used < 2) return -1.f;
+  float total = 0.f;
+  for (int i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->ev_pool[i + 1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) != cudaSuccess) return -1.f;
+    total += ms;
+  }
+  return total;
 }
 
 }  // extern "C"

@@ -60,6 +60,9 @@ struct pfm_epic {
   float* cbias; size_t cbias_cap;   // [B, bstride]     W_c . cond
   pfm::Plan plan;
   int last_launches, last_groups_host;
+  bool timing;
+  std::vector<cudaEvent_t> ev_pool;   // start/stop pairs of the main kernel, one pair per chunk of a call
+  int ev_used;
 };
 
 namespace pfm {

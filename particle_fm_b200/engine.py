@@ -172,6 +172,13 @@ class EpicEngine:
             raise ValueError(f"cond has {cond.shape[1]} columns, expected {d.cond_dim}")
         return cond
 
+    def set_timing(self, enable: bool):
+        _lib.check(self.lib.pfm_epic_set_timing(self._h, int(enable)), "pfm_epic_set_timing")
+
+    def last_kernel_ms(self) -> float:
+        """Device time of the fused network/integrator kernel of the last call (needs set_timing(True))."""
+        return float(self.lib.pfm_epic_last_kernel_ms(self._h))
+
     def last_launches(self) -> int:
         return int(self.lib.pfm_epic_last_launches(self._h))
 

@@ -18,7 +18,10 @@ def cosine_encoding(x: Tensor, outp_dim: int = 32, min_value: float = 0.0, max_v
     if x.shape[-1] != 1 or x.dim() == 1:
         x = x.unsqueeze(-1)
     if frequency_scaling == "exponential":
-        freqs = torch.arange(outp_dim, device=x.device).exp()
+        # exp() is evaluated on the HOST and the 32-entry table moved: CPU and CUDA expf differ in the last
+        # bit for some k, and one ulp of e^31 turns the high channels into a different hash of t.  The host
+        # table is what the CPU reference (and the oracle) use; see DESIGN.md "time code".
+        freqs = torch.arange(outp_dim).exp().to(x.device)
     elif frequency_scaling == "linear":
         freqs = torch.arange(1, outp_dim + 1, device=x.device)
     else:

@@ -166,8 +166,12 @@ class CNF(nn.Module):
                                       f"{FIXED_STEP_SOLVERS} solvers (the reference's generation configs use midpoint)")
         if self.loss_type == "diffusion":
             raise NotImplementedError("loss_type='diffusion' is out of scope of the B200 hot path")
-        t_eval, dt = fixed_step_grid(ode_steps, ode_solver)
-        codes = self.time_code(t_eval)                 # [n_evals, T], evaluated on the CPU like the oracle
+        key = (ode_steps, ode_solver)
+        cache = self.__dict__.setdefault("_grid_cache", {})
+        if key not in cache:
+            t_eval, dt = fixed_step_grid(ode_steps, ode_solver)
+            cache[key] = (self.time_code(t_eval), dt)  # [n_evals, T], evaluated on the CPU like the oracle
+        codes, dt = cache[key]
         eng = self.net.engine()
         takes = self.net.t_local_cat or self.net.t_global_cat
         return eng.sample(z, mask, cond, codes if takes else None, codes if self.add_time_to_input else None, dt,
