@@ -1,12 +1,625 @@
-// bf16 tcgen05 path -- placeholder until the tensor-core kernel lands.
+// bf16 tensor-core path (tcgen05 / TMEM / bulk async copies) of the EPiC vector field + integrator.
+//
+// One persistent CTA owns a group of jets whose real particles fill up to two 128-row tiles and runs
+// the WHOLE integration for them (one launch per sample()).  Per-particle state never leaves the SM:
+//   TMEM   cols [0,256)    fp32 hidden features h of tile A / tile B  = residual stream AND accumulator
+//                          of fc_local2 / fc_l2 (the MMA accumulates straight onto the residual)
+//          cols [256,512)  fp32 accumulators of fc_local1 per tile; the epilogue overwrites them in place
+//                          with the bf16 activations u that feed fc_local2 as a TMEM A-operand.
+//                          The pooling / global-MLP accumulators (48 columns) alias tile B's region.
+//   SMEM   h tiles as bf16 (K-major SWIZZLE_128B = A operand of fc_local1, and read "transposed" as an
+//          MN-major A operand by the pooling MMA), a 3-slot ring of 32 KB pre-swizzled weight images fed
+//          by cp.async.bulk, the jet-indicator matrix P, per-jet biases and global vectors.
+//   REGS   every epilogue thread owns one particle: its ODE state x lives in registers for all steps.
+// Masked mean/sum pooling is an MMA:  S[c][jet] = sum_rows h[row][c] * P[jet][row]  (M=128, N=16),
+// and the 256->128 part of fc_global1 is two more N=16 MMAs (W_mean . S, W_sum . S), so the serial
+// per-jet path costs ~5% extra tensor time instead of a CUDA-core GEMV.
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one lane), warps 4-7 / 8-11 = epilogue
+// warpgroups of tile A / tile B (TMEM lane quadrant = warp % 4).
 #include "pfm_internal.cuh"
+#include "tc_ptx.cuh"
+
 namespace pfm {
-int tc_supported(const pfm_epic* h, int N) {
-  (void)h; (void)N;
-  set_error("PFM_PREC_BF16: tensor-core path not built yet");
-  return PFM_ERR_UNSUPPORTED;
+
+using namespace tc;
+
+static constexpr int TCH = 128;          // hidden width this path is specialised for
+static constexpr int TC_ROWS = 256;      // 2 tiles of 128 particles
+static constexpr int TC_J = 16;          // jets per group (N of the pooling MMA)
+static constexpr int TC_ZMAX = 32;
+static constexpr int TC_KXMAX = 16;
+static constexpr int TC_THREADS = 384;
+static constexpr int TC_NSLOT = 3;
+static constexpr uint32_t TC_MAT = 32768;   // one 128x128 bf16 weight image
+
+struct TcSmem {
+  alignas(1024) uint8_t h[2][TC_MAT];          // bf16 h tiles
+  alignas(1024) uint8_t w[TC_NSLOT][TC_MAT];   // weight ring
+  alignas(1024) uint8_t P[8192];               // [16 jets x 256 rows] bf16, K-major SW128, 4 blocks of 2 KB
+  alignas(1024) uint8_t St[4096];              // [16 jets x 128 c]    bf16, K-major SW128, 2 blocks of 2 KB
+  float bl1[TC_J][TCH];
+  float bl2[TC_J][TCH];
+  float g1[TC_J][TCH];
+  float gv[TC_J][TC_ZMAX];
+  float w1s[TC_KXMAX][TCH];                    // fc_l1 rows used for the particle features (k-major)
+  float w3s[TCH][16];                          // fc_l3 (k-major, ld 16)
+  float inv_n[TC_J];
+  int jrow0[TC_J + 1];
+  int group;
+  uint32_t tmem_base;
+  uint64_t full[TC_NSLOT], empty[TC_NSLOT];
+  uint64_t hready[2], accU_full[2], u_ready[2], accH_full[2];
+  uint64_t pool_full, glob_go, glob_full, d_free;
+};
+
+struct TcParams {
+  int F, Kx, x_ld, xin_off, Z, L, n_lin, n_items;
+  float sum_scale, slope;
+  const Lin* lin;
+  const uint8_t* wimg;
+  const float* tbias; const float* cbias; int bstride; int tbias_per_jet;
+  const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
+  const float* x_in; float* x_out; int B, N;
+  int n_evals, solver, n_steps; const float* dt;
+};
+
+__device__ __forceinline__ float lrelu_tc(float v, float s) { return fmaxf(v, v * s); }   // 0 < s < 1
+
+__device__ __forceinline__ float tc_bias_of(const TcParams& p, const Lin& L, int eval, int jet_global, int o) {
+  const int trow = p.tbias_per_jet ? jet_global : eval;
+  float b = p.tbias[(size_t)trow * p.bstride + L.bias_off + o];
+  if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + L.bias_off + o];
+  return b;
 }
-int tc_plan_caps(const pfm_epic*, int, int*, int*) { return PFM_ERR_UNSUPPORTED; }
-int tc_pack_weights(pfm_epic*, cudaStream_t) { return PFM_ERR_UNSUPPORTED; }
-int tc_run(pfm_epic*, const RunArgs&, cudaStream_t) { return PFM_ERR_UNSUPPORTED; }
+
+__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// 16 MMAs: D[128 x 128] (+)= A[128 x 128] . B[128 x 128]^T, A and B K-major SW128 images in shared memory
+__device__ __forceinline__ void issue_ss_128(uint32_t d, uint32_t a_base, uint32_t b_base, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t off = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+    mma_ss(d, desc_kmajor(a_base + off), desc_kmajor(b_base + off), idesc, (acc_first || k > 0) ? 1u : 0u);
+  }
+}
+
+template <int FP>
+__global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Lin* lin = p.lin;
+  const int L = p.L, Z = p.Z, F = p.F;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
+    }
+    mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 128); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&s.tmem_base, 512);
+  {   // small fp32 weights used by every particle thread: fc_l1 feature rows, fc_l3
+    const Lin L1 = lin[LIN_L1], L3 = lin[p.n_lin - 1];
+    for (int i = tid; i < p.Kx * TCH; i += TC_THREADS) {
+      const int k = i / TCH, o = i - k * TCH;
+      s.w1s[k][o] = L1.Wt[(size_t)(L1.m_off + p.xin_off + k) * L1.ldo + o];
+    }
+    for (int i = tid; i < TCH * 16; i += TC_THREADS) {
+      const int c = i >> 4, f = i & 15;
+      s.w3s[c][f] = f < L3.ldo ? L3.Wt[(size_t)(L3.m_off + c) * L3.ldo + f] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s.tmem_base;
+  const int n_groups = *p.n_groups;
+
+  // running use counters of every barrier (parity = count & 1); each role only advances the ones it uses
+  uint32_t ring_it = 0;                                     // producer / MMA: weight items consumed so far
+  uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0}, c_globgo = 0, c_dfree = 0;           // MMA side
+  uint32_t c_accH = 0, c_accU = 0, c_pool = 0, c_glob = 0;                                    // epilogue side
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s.group = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int gidx = s.group;
+    if (gidx >= n_groups) break;
+    const int2 grp = p.groups[gidx];
+    const int j0 = grp.x, nj = grp.y;
+
+    if (warp == 0) {
+      // ================================ weight producer ================================
+      if (lane == 0) {
+        for (int ev = 0; ev < p.n_evals; ++ev) {
+          for (int it = 0; it < p.n_items; ++it, ++ring_it) {
+            const uint32_t slot = ring_it % TC_NSLOT, round = ring_it / TC_NSLOT;
+            mbar_wait(&s.empty[slot], (round & 1) ^ 1);
+            mbar_arrive_expect_tx(&s.full[slot], TC_MAT);
+            bulk_copy_g2s(s.w[slot], p.wimg + (size_t)it * TC_MAT, TC_MAT, &s.full[slot]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ================================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_pool = make_idesc_bf16(128, 16, 1, 0);
+        const uint32_t idesc_glob = make_idesc_bf16(128, 16, 0, 0);
+        const uint32_t hA = smem_u32(s.h[0]), hB = smem_u32(s.h[1]);
+        const uint32_t accH0 = tm, accH1 = tm + 128, accU0 = tm + 256, accU1 = tm + 384;
+        const uint32_t dpool = tm + 384 + 64, dglob = tm + 384 + 80;
+        auto wait_full = [&](uint32_t it) { mbar_wait(&s.full[it % TC_NSLOT], (it / TC_NSLOT) & 1); };
+        auto wslot = [&](uint32_t it) { return smem_u32(s.w[it % TC_NSLOT]); };
+        for (int ev = 0; ev < p.n_evals; ++ev) {
+          // ---- stem fc_l2: accH[t] (holds h1) += h1 . W_l2^T
+          const uint32_t it_l2 = ring_it++;
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&s.hready[t], c_hready[t]++ & 1);
+            tc_fence_after();
+            if (t == 0) wait_full(it_l2);
+            issue_ss_128(t ? accH1 : accH0, t ? hB : hA, wslot(it_l2), idesc, true);
+            mma_commit(&s.accH_full[t]);
+          }
+          mma_commit(&s.empty[it_l2 % TC_NSLOT]);
+          for (int gi = 0; gi <= L; ++gi) {
+            uint32_t it_w1 = 0;
+            if (gi != 1) {   // a new version of h is complete: pool it   S[c][jet] = sum_rows h[row][c] P[jet][row]
+              mbar_wait(&s.hready[0], c_hready[0]++ & 1);
+              mbar_wait(&s.hready[1], c_hready[1]++ & 1);
+              tc_fence_after();
+              const uint32_t pb = smem_u32(s.P);
+#pragma unroll
+              for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const uint64_t da = desc_mnmajor((t ? hB : hA) + (uint32_t)k * 2048u, 16384u, 1024u);
+                  const uint64_t db = desc_kmajor(pb + (uint32_t)(t * 2 + (k >> 2)) * 2048u + (uint32_t)(k & 3) * 32u);
+                  mma_ss(dpool, da, db, idesc_pool, (t | k) ? 1u : 0u);
+                }
+              mma_commit(&s.pool_full);
+            }
+            if (gi >= 1) {   // fc_local1 of tile A does not need the global vector: issue it right away
+              it_w1 = ring_it++;
+              wait_full(it_w1);
+              issue_ss_128(accU0, hA, wslot(it_w1), idesc, false);
+              mma_commit(&s.accU_full[0]);
+            }
+            // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . S[:, jet],  W_sum likewise
+            const uint32_t it_gm = ring_it++, it_gs = ring_it++;
+            mbar_wait(&s.glob_go, c_globgo++ & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(s.St);
+            for (int m = 0; m < 2; ++m) {
+              const uint32_t itw = m ? it_gs : it_gm;
+              wait_full(itw);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t offa = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+                const uint32_t offb = (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u;
+                mma_ss(dglob + m * 16, desc_kmajor(wslot(itw) + offa), desc_kmajor(sb + offb), idesc_glob, k ? 1u : 0u);
+              }
+            }
+            mma_commit(&s.glob_full);
+            mma_commit(&s.empty[it_gm % TC_NSLOT]);
+            mma_commit(&s.empty[it_gs % TC_NSLOT]);
+            mbar_wait(&s.d_free, c_dfree++ & 1);      // pooling / global accumulators (aliasing accU of tile B) consumed
+            tc_fence_after();
+            if (gi >= 1) {
+              issue_ss_128(accU1, hB, wslot(it_w1), idesc, false);
+              mma_commit(&s.accU_full[1]);
+              mma_commit(&s.empty[it_w1 % TC_NSLOT]);
+              const uint32_t it_w2 = ring_it++;
+              for (int t = 0; t < 2; ++t) {          // fc_local2: accH[t] += u[t] (bf16 in TMEM) . W2^T
+                mbar_wait(&s.u_ready[t], c_uready[t]++ & 1);
+                tc_fence_after();
+                if (t == 0) wait_full(it_w2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const uint32_t off = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+                  mma_ts(t ? accH1 : accH0, (t ? accU1 : accU0) + (uint32_t)k * 8u, desc_kmajor(wslot(it_w2) + off), idesc, 1u);
+                }
+                mma_commit(&s.accH_full[t]);
+              }
+              mma_commit(&s.empty[it_w2 % TC_NSLOT]);
+            }
+          }
+        }
+      }
+    } else if (warp >= 4) {
+      // ================================ epilogue / particle threads ================================
+      const int et = tid - 128;
+      const int wg = et >> 7;                    // tile
+      const int r = et & 127;                    // row in tile = TMEM lane
+      const int row = wg * 128 + r;
+      const uint32_t lane_base = tm + ((uint32_t)((warp & 3) * 32) << 16);
+      const uint32_t accH = lane_base + wg * 128, accU = lane_base + 256 + wg * 128;
+      const uint32_t dpool = lane_base + 384 + 64, dglob = lane_base + 384 + 80;
+      uint8_t* hrow = s.h[wg] + (r >> 3) * 1024 + (r & 7) * 128;       // this particle's 128-byte swizzled row (per 64-col block)
+
+      if (et == 0) {
+        int acc = 0;
+        for (int j = 0; j < nj; ++j) {
+          s.jrow0[j] = acc;
+          const int n = p.n_real[j0 + j];
+          s.inv_n[j] = 1.f / (float)n;           // n == 0 -> inf -> NaN confined to that jet, like the reference
+          acc += n;
+        }
+        for (int j = nj; j <= TC_J; ++j) s.jrow0[j] = acc;
+        for (int j = nj; j < TC_J; ++j) s.inv_n[j] = 0.f;
+      }
+      for (int i = et; i < 8192 / 16; i += 256) reinterpret_cast<uint4*>(s.P)[i] = make_uint4(0, 0, 0, 0);
+      ebar();
+      const int R = s.jrow0[nj];
+      const bool valid = row < R;
+      int myjet = 0;
+      for (int j = 1; j < nj; ++j) myjet += (row >= s.jrow0[j]) ? 1 : 0;
+      if (!valid) myjet = 0;
+      if (valid) *reinterpret_cast<__nv_bfloat16*>(s.P + sw128_offset(myjet, row, 2048)) = __float2bfloat16(1.0f);
+      const int jg = j0 + myjet;
+      float x0[FP], xc[FP], vout[FP];
+#pragma unroll
+      for (int f = 0; f < FP; ++f) { x0[f] = 0.f; xc[f] = 0.f; vout[f] = 0.f; }
+      int part = 0;
+      if (valid) {
+        part = p.ridx[(size_t)jg * p.N + (row - s.jrow0[myjet])];
+        const float* src = p.x_in + ((size_t)jg * p.N + part) * p.x_ld;
+#pragma unroll
+        for (int f = 0; f < FP; ++f)
+          if (f < p.Kx) { xc[f] = src[f]; x0[f] = xc[f]; }
+      }
+
+      for (int ev = 0; ev < p.n_evals; ++ev) {
+        // ---------------- stem biases ----------------
+        {
+          const Lin L1 = lin[LIN_L1], L2 = lin[LIN_L2];
+          for (int i = et; i < nj * TCH; i += 256) {
+            const int j = i >> 7, o = i & 127;
+            s.bl1[j][o] = tc_bias_of(p, L1, ev, j0 + j, o);
+            s.bl2[j][o] = tc_bias_of(p, L2, ev, j0 + j, o);
+          }
+        }
+        ebar();
+        // ---------------- fc_l1 on CUDA cores (K = a few features): h1 -> TMEM (fp32) + shared (bf16) ----------------
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = s.bl1[myjet][c * 32 + i];
+#pragma unroll
+            for (int f = 0; f < FP; ++f)
+              if (f < p.Kx) a = fmaf(s.w1s[f][c * 32 + i], xc[f], a);
+            a = valid ? lrelu_tc(a, p.slope) : 0.f;
+            v[i] = __float_as_uint(a);
+          }
+          tmem_st32(accH + c * 32, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            const int c16 = c * 4 + q;
+            *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
+          }
+        }
+        tmem_wait_st();
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&s.hready[wg]);
+
+        // residual update epilogue shared by the stem's fc_l2 and every fc_local2:
+        //   h = lrelu(acc + bias) -> TMEM fp32 (in place) and shared bf16; on the last layer also the head
+        auto epi_h = [&](bool write_back, bool head) {
+          mbar_wait(&s.accH_full[wg], c_accH++ & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(accH + c * 32, v);
+            tmem_wait_ld();
+            const float4* bj = reinterpret_cast<const float4*>(&s.bl2[myjet][c * 32]);
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b = bj[i4];
+              float a0 = __uint_as_float(v[i4 * 4 + 0]) + b.x, a1 = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+              float a2 = __uint_as_float(v[i4 * 4 + 2]) + b.z, a3 = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+              a0 = valid ? lrelu_tc(a0, p.slope) : 0.f; a1 = valid ? lrelu_tc(a1, p.slope) : 0.f;
+              a2 = valid ? lrelu_tc(a2, p.slope) : 0.f; a3 = valid ? lrelu_tc(a3, p.slope) : 0.f;
+              v[i4 * 4 + 0] = __float_as_uint(a0); v[i4 * 4 + 1] = __float_as_uint(a1);
+              v[i4 * 4 + 2] = __float_as_uint(a2); v[i4 * 4 + 3] = __float_as_uint(a3);
+            }
+            if (head) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float a = __uint_as_float(v[i]);
+#pragma unroll
+                for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
+              }
+            }
+            if (write_back) {
+              tmem_st32(accH + c * 32, v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                const int c16 = c * 4 + q;
+                *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
+              }
+            }
+          }
+          if (write_back) {
+            tmem_wait_st();
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&s.hready[wg]);
+          }
+        };
+        epi_h(true, false);                        // stem fc_l2 (+ residual h1)
+
+        for (int gi = 0; gi <= L; ++gi) {
+          // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
+          const Lin Ga = gi == 0 ? lin[LIN_G1] : lin[LIN_LAYER0 + 4 * (gi - 1) + 0];
+          const Lin Gb = gi == 0 ? lin[LIN_G2] : lin[LIN_LAYER0 + 4 * (gi - 1) + 1];
+          if (wg == 0) {
+            if (gi != 1) {                         // new pooled sums: TMEM -> bf16 B operand in shared memory
+              mbar_wait(&s.pool_full, c_pool++ & 1);
+              tc_fence_after();
+              uint32_t v[16];
+              tmem_ld16(dpool, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                *reinterpret_cast<__nv_bfloat16*>(s.St + sw128_offset(j, r, 2048)) = __float2bfloat16(__uint_as_float(v[j]));
+              fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive(&s.glob_go);
+            mbar_wait(&s.glob_full, c_glob++ & 1);
+            tc_fence_after();
+            uint32_t dm[16], ds[16];
+            tmem_ld16(dglob, dm);
+            tmem_ld16(dglob + 16, ds);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&s.d_free);
+            // g1[j][o = r] = lrelu(W_mean.S / n + s * W_sum.S (+ W_g . g) + bias)     (epic.py:180-182, :375-377)
+            const float* wgg = Ga.Wt + (size_t)(Ga.m_off + 2 * TCH) * Ga.ldo + r;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < nj) {
+                float a = tc_bias_of(p, Ga, ev, j0 + j, r);
+                a = fmaf(__uint_as_float(dm[j]), s.inv_n[j], a);
+                a = fmaf(__uint_as_float(ds[j]), p.sum_scale, a);
+                if (gi >= 1)
+                  for (int z = 0; z < Z; ++z) a = fmaf(__ldg(wgg + (size_t)z * Ga.ldo), s.gv[j][z], a);
+                s.g1[j][r] = lrelu_tc(a, p.slope);
+              }
+            }
+          }
+          ebar();
+          {   // fc_g2 / fc_global2 (+ residual for the layers): one warp per (jet, latent) output
+            const int ew = et >> 5;
+            for (int item = ew; item < nj * Z; item += 8) {
+              const int j = item / Z, z = item - j * Z;
+              const float* w = Gb.Wt + (size_t)Gb.m_off * Gb.ldo + z;
+              float a = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int o = lane + 32 * q;
+                a = fmaf(__ldg(w + (size_t)o * Gb.ldo), s.g1[j][o], a);
+              }
+#pragma unroll
+              for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+              if (lane == 0) {
+                a += tc_bias_of(p, Gb, ev, j0 + j, z);
+                if (gi >= 1) a += s.gv[j][z];
+                s.gv[j][z] = lrelu_tc(a, p.slope);
+              }
+            }
+          }
+          ebar();
+          if (gi == 0) continue;
+          const int l = gi - 1;
+          {   // per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
+            const Lin La = lin[LIN_LAYER0 + 4 * l + 2], Lb = lin[LIN_LAYER0 + 4 * l + 3];
+            for (int i = et; i < nj * TCH; i += 256) {
+              const int j = i >> 7, o = i & 127;
+              float a = tc_bias_of(p, La, ev, j0 + j, o);
+              const float* w = La.Wt + (size_t)La.g_off * La.ldo + o;
+              for (int z = 0; z < Z; ++z) a = fmaf(__ldg(w + (size_t)z * La.ldo), s.gv[j][z], a);
+              s.bl1[j][o] = a;
+              s.bl2[j][o] = tc_bias_of(p, Lb, ev, j0 + j, o);
+            }
+          }
+          ebar();
+          // ======== fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM ========
+          mbar_wait(&s.accU_full[wg], c_accU++ & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(accU + c * 32, v);
+            tmem_wait_ld();
+            const float4* bj = reinterpret_cast<const float4*>(&s.bl1[myjet][c * 32]);
+            uint32_t u16[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b = bj[i4];
+              float a0 = __uint_as_float(v[i4 * 4 + 0]) + b.x, a1 = __uint_as_float(v[i4 * 4 + 1]) + b.y;
+              float a2 = __uint_as_float(v[i4 * 4 + 2]) + b.z, a3 = __uint_as_float(v[i4 * 4 + 3]) + b.w;
+              a0 = valid ? lrelu_tc(a0, p.slope) : 0.f; a1 = valid ? lrelu_tc(a1, p.slope) : 0.f;
+              a2 = valid ? lrelu_tc(a2, p.slope) : 0.f; a3 = valid ? lrelu_tc(a3, p.slope) : 0.f;
+              u16[i4 * 2 + 0] = pack_bf16x2(a0, a1);
+              u16[i4 * 2 + 1] = pack_bf16x2(a2, a3);
+            }
+            tmem_st16(accU + c * 16, u16);          // columns [16c, 16c+16) were already read (c <= 2c+1)
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&s.u_ready[wg]);
+          // ======== fc_local2 epilogue (+ head after the last layer) ========
+          const bool last = (l == L - 1);
+          if (last) {
+#pragma unroll
+            for (int f = 0; f < FP; ++f) vout[f] = 0.f;
+          }
+          epi_h(!last, last);
+        }
+        // ---------------- head bias + activation, integrator step (thread-local) ----------------
+        {
+          const Lin L3 = lin[p.n_lin - 1];
+#pragma unroll
+          for (int f = 0; f < FP; ++f)
+            if (f < F) vout[f] = valid ? lrelu_tc(vout[f] + tc_bias_of(p, L3, ev, jg, f), p.slope) : 0.f;
+        }
+        if (p.solver >= 0) {
+          const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
+          const float dt = p.dt[mid ? (ev >> 1) : ev];
+          const bool first_stage = mid && ((ev & 1) == 0);
+          const float hdt = __fmul_rn(0.5f, dt);
+#pragma unroll
+          for (int f = 0; f < FP; ++f) {
+            const float k = -vout[f];
+            if (first_stage) {
+              xc[f] = __fadd_rn(x0[f], __fmul_rn(hdt, k));
+            } else {
+              x0[f] = __fadd_rn(x0[f], __fmul_rn(dt, k));
+              xc[f] = x0[f];
+            }
+          }
+        }
+        ebar();      // bl1/bl2 of this evaluation are dead before the next one rewrites them
+      }
+      // ---------------- write back ----------------
+      for (int j = 0; j < nj; ++j) {
+        const int n = s.jrow0[j + 1] - s.jrow0[j];
+        const float fill = n == 0 ? __int_as_float(0x7fc00000) : 0.f;
+        float* dst = p.x_out + (size_t)(j0 + j) * p.N * F;
+        for (int i = et; i < p.N * F; i += 256) dst[i] = fill;
+      }
+      ebar();
+      if (valid) {
+        float* dst = p.x_out + ((size_t)jg * p.N + part) * F;
+#pragma unroll
+        for (int f = 0; f < FP; ++f)
+          if (f < F) dst[f] = p.solver >= 0 ? x0[f] : vout[f];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight images: bf16, K-major SWIZZLE_128B, one 32 KB image per 128 x 128 block, in ring order
+//   stem: fc_l2 | fc_g1[mean cols] | fc_g1[sum cols]      layer l: fc_local1 | fc_global1[mean] | fc_global1[sum] | fc_local2
+// ---------------------------------------------------------------------------------------------
+struct ImgSrc { const float* Wt; int ldo; int k0; };   // image[n][k] = Wt[(k0 + k) * ldo + n]
+
+__global__ void pack_images_kernel(const ImgSrc* __restrict__ src, uint8_t* __restrict__ img) {
+  const ImgSrc S = src[blockIdx.x];
+  uint8_t* out = img + (size_t)blockIdx.x * TC_MAT;
+  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) {
+    const int k = i >> 7, n = i & 127;        // consecutive threads -> consecutive n: coalesced reads of the k-major copy
+    const float w = S.Wt[(size_t)(S.k0 + k) * S.ldo + n];
+    *reinterpret_cast<__nv_bfloat16*>(out + sw128_offset(n, k, 16384)) = __float2bfloat16(w);
+  }
+}
+
+int tc_supported(const pfm_epic* h, int N) {
+  const pfm_epic_cfg& c = h->cfg;
+  if (c.hid != TCH) { set_error("PFM_PREC_BF16 needs hid == 128 (got %d); use PFM_PREC_FP32", c.hid); return PFM_ERR_UNSUPPORTED; }
+  if (c.latent > TC_ZMAX) { set_error("PFM_PREC_BF16 needs latent <= %d (got %d)", TC_ZMAX, c.latent); return PFM_ERR_UNSUPPORTED; }
+  if (c.feats > 16) { set_error("PFM_PREC_BF16 needs feats <= 16 (got %d)", c.feats); return PFM_ERR_UNSUPPORTED; }
+  if (c.layers < 1) { set_error("PFM_PREC_BF16 needs at least one EPiC layer"); return PFM_ERR_UNSUPPORTED; }
+  if (N > TC_ROWS) { set_error("PFM_PREC_BF16: a jet of %d particles exceeds the %d-row group; use PFM_PREC_FP32", N, TC_ROWS); return PFM_ERR_UNSUPPORTED; }
+  if ((int)(sizeof(TcSmem) + 1024) > h->max_smem_optin) { set_error("PFM_PREC_BF16: not enough shared memory per block"); return PFM_ERR_UNSUPPORTED; }
+  return PFM_OK;
+}
+
+int tc_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap) {
+  (void)h; (void)N;
+  *R_cap = TC_ROWS; *J_cap = TC_J;
+  return PFM_OK;
+}
+
+int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  const int n_items = 3 + 4 * c.layers;
+  std::vector<ImgSrc> src(n_items);
+  auto mk = [&](int lin_idx, int k_off) {
+    const Lin& L = h->lin_host[lin_idx];
+    ImgSrc s; s.Wt = L.Wt; s.ldo = L.ldo; s.k0 = L.m_off + k_off; return s;
+  };
+  int it = 0;
+  src[it++] = mk(LIN_L2, 0);
+  src[it++] = mk(LIN_G1, TCH);      // stem concat order is (sum, mean): the mean block is second (epic.py:373)
+  src[it++] = mk(LIN_G1, 0);
+  for (int l = 0; l < c.layers; ++l) {
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 2, 0);       // fc_local1, particle columns
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, 0);       // fc_global1: (mean, sum, global) order (epic.py:164-171)
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, TCH);
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 3, 0);       // fc_local2
+  }
+  const size_t bytes = (size_t)n_items * TC_MAT;
+  if (h->tc_bytes < bytes + sizeof(ImgSrc) * n_items) {
+    if (h->tc_store) cudaFree(h->tc_store);
+    h->tc_store = nullptr; h->tc_bytes = 0;
+    PFM_CUDA_CHECK(cudaMalloc(&h->tc_store, bytes + sizeof(ImgSrc) * n_items));
+    h->tc_bytes = bytes + sizeof(ImgSrc) * n_items;
+  }
+  ImgSrc* dsrc = reinterpret_cast<ImgSrc*>(reinterpret_cast<uint8_t*>(h->tc_store) + bytes);
+  PFM_CUDA_CHECK(cudaMemcpyAsync(dsrc, src.data(), sizeof(ImgSrc) * n_items, cudaMemcpyHostToDevice, st));
+  PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src is a host temporary
+  pack_images_kernel<<<n_items, 256, 0, st>>>(dsrc, reinterpret_cast<uint8_t*>(h->tc_store));
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+template <int FP>
+static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
+  auto kern = epic_tc_kernel<FP>;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, TC_THREADS, smem, st>>>(p);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  if (a.Kx > TC_KXMAX) {
+    set_error("PFM_PREC_BF16: %d per-particle input columns exceed %d (add_time_to_input through pfm_epic_forward); "
+              "use PFM_PREC_FP32 or the sampling entry point, which hoists the time columns", a.Kx, TC_KXMAX);
+    return PFM_ERR_UNSUPPORTED;
+  }
+  if (!h->tc_store) { int rc = tc_pack_weights(h, st); if (rc != PFM_OK) return rc; }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.F = c.feats; p.Kx = a.Kx; p.x_ld = a.Kx; p.xin_off = a.xin_off; p.Z = c.latent; p.L = c.layers; p.n_lin = h->n_lin;
+  p.n_items = 3 + 4 * c.layers;
+  p.sum_scale = c.sum_scale; p.slope = c.neg_slope;
+  p.lin = h->lin_dev; p.wimg = reinterpret_cast<const uint8_t*>(h->tc_store);
+  p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride; p.tbias_per_jet = a.tbias_per_jet;
+  p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
+  p.counter = h->plan.counter;
+  p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
+  p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
+  const int grid = h->sm_count < a.B ? h->sm_count : a.B;
+  const int kmax = a.Kx > c.feats ? a.Kx : c.feats;
+  if (kmax <= 4) return launch_tc<4>(p, grid, st);
+  if (kmax <= 8) return launch_tc<8>(p, grid, st);
+  return launch_tc<16>(p, grid, st);
+}
+
 }  // namespace pfm
