@@ -26,12 +26,15 @@ using namespace tc;
 static constexpr int TCH = 128;          // hidden width this path is specialised for
 static constexpr int TC_ROWS = 256;      // 2 tiles of 128 particles
 static constexpr int TC_J = 16;          // jets per group (N of the pooling MMA)
-static constexpr int TC_ZMAX = 32;
-static constexpr int TC_KXMAX = 16;
+static constexpr int TC_ZMAX = 16;        // latent width (10 / 16 in the configs); the small-weight pack is laid out for 16
+static constexpr int TC_KXMAX = 8;          // per-particle input columns / features (3 JetNet, 8 JetClass)
+static constexpr uint32_t TC_SPK = 3 * 16 * 128 * 2;   // per-unit small-weight pack (bf16): W_gg | W_glob | W_g2, 12 KB
+static constexpr int TC_SBIAS = 384 + 16;               // one unit's slice of the time-bias table
 static constexpr int TC_THREADS = 384;
 static constexpr int TC_NSLOT = 3;
 static constexpr uint32_t TC_MAT = 32768;   // one 128x128 bf16 weight image
 
+template <int FP>
 struct TcSmem {
   alignas(1024) uint8_t h[2][TC_MAT];          // bf16 h tiles
   alignas(1024) uint8_t w[TC_NSLOT][TC_MAT];   // weight ring
@@ -41,8 +44,10 @@ struct TcSmem {
   float bl2[TC_J][TCH];
   float g1[TC_J][TCH];
   float gv[TC_J][TC_ZMAX];
-  float w1s[TC_KXMAX][TCH];                    // fc_l1 rows used for the particle features (k-major)
-  float w3s[TCH][16];                          // fc_l3 (k-major, ld 16)
+  float w1s[FP][TCH];                          // fc_l1 rows used for the particle features (k-major)
+  float w3s[TCH][FP];                          // fc_l3 (k-major)
+  alignas(16) __nv_bfloat16 spk[3][16][TCH];   // [0] W_gg[z][o]  [1] W_glob[z][o]  [2] W_g2[z][o]   (current unit)
+  alignas(16) float sbias[TC_SBIAS];           // time-bias slice of the current unit (4 consecutive linears)
   float inv_n[TC_J];
   int jrow0[TC_J + 1];
   int group;
@@ -50,6 +55,7 @@ struct TcSmem {
   uint64_t full[TC_NSLOT], empty[TC_NSLOT];
   uint64_t hready[2], accU_full[2], u_ready[2], accH_full[2];
   uint64_t pool_full, glob_go, glob_full, d_free;
+  uint64_t spk_full, spk_empty;
 };
 
 struct TcParams {
@@ -57,6 +63,8 @@ struct TcParams {
   float sum_scale, slope;
   const Lin* lin;
   const uint8_t* wimg;
+  const uint8_t* spk;        // [L+1] small-weight packs
+  int boff_stem, boff_layer0, boff_layer_stride, bias_chunk_floats;   // where a unit's 4 linears sit in a bias-table row
   const float* tbias; const float* cbias; int bstride; int tbias_per_jet;
   const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
   const float* x_in; float* x_out; int B, N;
@@ -86,7 +94,7 @@ __device__ __forceinline__ void issue_ss_128(uint32_t d, uint32_t a_base, uint32
 template <int FP>
 __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  TcSmem& s = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcSmem<FP>& s = *reinterpret_cast<TcSmem<FP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Lin* lin = p.lin;
   const int L = p.L, Z = p.Z, F = p.F;
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
     }
     mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 128); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 128);
+    mbar_init(&s.spk_full, 1); mbar_init(&s.spk_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&s.tmem_base, 512);
@@ -106,8 +115,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int k = i / TCH, o = i - k * TCH;
       s.w1s[k][o] = L1.Wt[(size_t)(L1.m_off + p.xin_off + k) * L1.ldo + o];
     }
-    for (int i = tid; i < TCH * 16; i += TC_THREADS) {
-      const int c = i >> 4, f = i & 15;
+    for (int i = tid; i < TCH * FP; i += TC_THREADS) {
+      const int c = i / FP, f = i - c * FP;
       s.w3s[c][f] = f < L3.ldo ? L3.Wt[(size_t)(L3.m_off + c) * L3.ldo + f] : 0.f;
     }
   }
@@ -120,7 +129,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
   // running use counters of every barrier (parity = count & 1); each role only advances the ones it uses
   uint32_t ring_it = 0;                                     // producer / MMA: weight items consumed so far
   uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0}, c_globgo = 0, c_dfree = 0;           // MMA side
-  uint32_t c_accH = 0, c_accU = 0, c_pool = 0, c_glob = 0;                                    // epilogue side
+  uint32_t c_accH = 0, c_accU = 0, c_pool = 0, c_glob = 0, c_spk = 0;                         // epilogue side
+  uint32_t spk_it = 0;                                      // producer: small-weight packs issued so far
 
   for (;;) {
     __syncthreads();
@@ -134,8 +144,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     if (warp == 0) {
       // ================================ weight producer ================================
       if (lane == 0) {
+        const bool stage_bias = !p.tbias_per_jet;
+        const uint32_t bias_bytes = stage_bias ? (uint32_t)p.bias_chunk_floats * 4u : 0u;
         for (int ev = 0; ev < p.n_evals; ++ev) {
           for (int it = 0; it < p.n_items; ++it, ++ring_it) {
+            // the small-weight pack + bias slice of unit u travel just before the unit's global-MLP images
+            const int u = it == 1 ? 0 : ((it >= 4 && ((it - 4) & 3) == 0) ? 1 + ((it - 4) >> 2) : -1);
+            if (u >= 0) {
+              mbar_wait(&s.spk_empty, (spk_it & 1) ^ 1);
+              ++spk_it;
+              mbar_arrive_expect_tx(&s.spk_full, TC_SPK + bias_bytes);
+              bulk_copy_g2s(s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
+              if (stage_bias)
+                bulk_copy_g2s(s.sbias, p.tbias + (size_t)ev * p.bstride + (u == 0 ? p.boff_stem : p.boff_layer0 + (u - 1) * p.boff_layer_stride),
+                              bias_bytes, &s.spk_full);
+            }
             const uint32_t slot = ring_it % TC_NSLOT, round = ring_it / TC_NSLOT;
             mbar_wait(&s.empty[slot], (round & 1) ^ 1);
             mbar_arrive_expect_tx(&s.full[slot], TC_MAT);
@@ -252,6 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int j = nj; j < TC_J; ++j) s.inv_n[j] = 0.f;
       }
       for (int i = et; i < 8192 / 16; i += 256) reinterpret_cast<uint4*>(s.P)[i] = make_uint4(0, 0, 0, 0);
+      for (int i = et; i < TC_J * TC_ZMAX; i += 256) (&s.gv[0][0])[i] = 0.f;
       ebar();
       const int R = s.jrow0[nj];
       const bool valid = row < R;
@@ -260,6 +284,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       if (!valid) myjet = 0;
       if (valid) *reinterpret_cast<__nv_bfloat16*>(s.P + sw128_offset(myjet, row, 2048)) = __float2bfloat16(1.0f);
       const int jg = j0 + myjet;
+      // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
+      // slow direct path when every jet has its own time (training-style forward)
+      auto unit_bias = [&](const Lin& Lx, int voff, int ev_, int jet_global, int o) -> float {
+        float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + Lx.bias_off + o] : s.sbias[voff + o];
+        if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + Lx.bias_off + o];
+        (void)ev_;
+        return b;
+      };
       float x0[FP], xc[FP], vout[FP];
 #pragma unroll
       for (int f = 0; f < FP; ++f) { x0[f] = 0.f; xc[f] = 0.f; vout[f] = 0.f; }
@@ -273,13 +305,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       }
 
       for (int ev = 0; ev < p.n_evals; ++ev) {
-        // ---------------- stem biases ----------------
+        // ---------------- unit 0 pack (stem biases + fc_g2) has landed; per-jet stem biases ----------------
+        mbar_wait(&s.spk_full, c_spk++ & 1);
+        float b3[FP];                              // head bias and step size: loaded now, used at the end of the evaluation
+        {
+          const Lin L3 = lin[p.n_lin - 1];
+#pragma unroll
+          for (int f = 0; f < FP; ++f) b3[f] = f < F ? tc_bias_of(p, L3, ev, jg, f) : 0.f;
+        }
+        const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
         {
           const Lin L1 = lin[LIN_L1], L2 = lin[LIN_L2];
           for (int i = et; i < nj * TCH; i += 256) {
             const int j = i >> 7, o = i & 127;
-            s.bl1[j][o] = tc_bias_of(p, L1, ev, j0 + j, o);
-            s.bl2[j][o] = tc_bias_of(p, L2, ev, j0 + j, o);
+            s.bl1[j][o] = unit_bias(L1, 0, ev, j0 + j, o);
+            s.bl2[j][o] = unit_bias(L2, 128, ev, j0 + j, o);
           }
         }
         ebar();
@@ -369,6 +409,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
           const Lin Ga = gi == 0 ? lin[LIN_G1] : lin[LIN_LAYER0 + 4 * (gi - 1) + 0];
           const Lin Gb = gi == 0 ? lin[LIN_G2] : lin[LIN_LAYER0 + 4 * (gi - 1) + 1];
+          const int ZP = (Z + 3) & ~3;
+          const int off_ga = gi == 0 ? 256 : 0, off_gb = gi == 0 ? 384 : 128;     // slice offsets inside sbias
+          if (gi >= 1) mbar_wait(&s.spk_full, c_spk++ & 1);                        // unit gi's pack (unit 0: waited at eval start)
           if (wg == 0) {
             if (gi != 1) {                         // new pooled sums: TMEM -> bf16 B operand in shared memory
               mbar_wait(&s.pool_full, c_pool++ & 1);
@@ -383,6 +426,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             }
             tc_fence_before();
             mbar_arrive(&s.glob_go);
+            // while the two N=16 MMAs run: bias + W_gg . g (previous global vector), all operands in shared memory
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = j < nj ? unit_bias(Ga, off_ga, ev, j0 + j, r) : 0.f;
+            if (gi >= 1) {
+              for (int z = 0; z < Z; ++z) {
+                const float w = __bfloat162float(s.spk[0][z][r]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] = fmaf(w, s.gv[j][z], a[j]);
+              }
+            }
             mbar_wait(&s.glob_full, c_glob++ & 1);
             tc_fence_after();
             uint32_t dm[16], ds[16];
@@ -392,17 +446,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             tc_fence_before();
             mbar_arrive(&s.d_free);
             // g1[j][o = r] = lrelu(W_mean.S / n + s * W_sum.S (+ W_g . g) + bias)     (epic.py:180-182, :375-377)
-            const float* wgg = Ga.Wt + (size_t)(Ga.m_off + 2 * TCH) * Ga.ldo + r;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (j < nj) {
-                float a = tc_bias_of(p, Ga, ev, j0 + j, r);
-                a = fmaf(__uint_as_float(dm[j]), s.inv_n[j], a);
-                a = fmaf(__uint_as_float(ds[j]), p.sum_scale, a);
-                if (gi >= 1)
-                  for (int z = 0; z < Z; ++z) a = fmaf(__ldg(wgg + (size_t)z * Ga.ldo), s.gv[j][z], a);
-                s.g1[j][r] = lrelu_tc(a, p.slope);
-              }
+              float v = fmaf(__uint_as_float(dm[j]), s.inv_n[j], a[j]);
+              v = fmaf(__uint_as_float(ds[j]), p.sum_scale, v);
+              s.g1[j][r] = lrelu_tc(v, p.slope);
             }
           }
           ebar();
@@ -410,36 +458,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             const int ew = et >> 5;
             for (int item = ew; item < nj * Z; item += 8) {
               const int j = item / Z, z = item - j * Z;
-              const float* w = Gb.Wt + (size_t)Gb.m_off * Gb.ldo + z;
-              float a = 0.f;
+              float acc = 0.f;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int o = lane + 32 * q;
-                a = fmaf(__ldg(w + (size_t)o * Gb.ldo), s.g1[j][o], a);
+                acc = fmaf(__bfloat162float(s.spk[2][z][o]), s.g1[j][o], acc);
               }
 #pragma unroll
-              for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+              for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
               if (lane == 0) {
-                a += tc_bias_of(p, Gb, ev, j0 + j, z);
-                if (gi >= 1) a += s.gv[j][z];
-                s.gv[j][z] = lrelu_tc(a, p.slope);
+                acc += unit_bias(Gb, off_gb, ev, j0 + j, z);
+                if (gi >= 1) acc += s.gv[j][z];
+                s.gv[j][z] = lrelu_tc(acc, p.slope);
               }
             }
           }
+          if (gi == 0) {                           // the stem has no per-particle linears of its own after the pooling
+            mbar_arrive(&s.spk_empty);
+            ebar();
+            continue;
+          }
           ebar();
-          if (gi == 0) continue;
           const int l = gi - 1;
           {   // per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
             const Lin La = lin[LIN_LAYER0 + 4 * l + 2], Lb = lin[LIN_LAYER0 + 4 * l + 3];
-            for (int i = et; i < nj * TCH; i += 256) {
-              const int j = i >> 7, o = i & 127;
-              float a = tc_bias_of(p, La, ev, j0 + j, o);
-              const float* w = La.Wt + (size_t)La.g_off * La.ldo + o;
-              for (int z = 0; z < Z; ++z) a = fmaf(__ldg(w + (size_t)z * La.ldo), s.gv[j][z], a);
-              s.bl1[j][o] = a;
-              s.bl2[j][o] = tc_bias_of(p, Lb, ev, j0 + j, o);
+            const int o = et & 127;
+            for (int j = et >> 7; j < nj; j += 2) {
+              float acc = unit_bias(La, 128 + ZP, ev, j0 + j, o);
+              for (int z = 0; z < Z; ++z) acc = fmaf(__bfloat162float(s.spk[1][z][o]), s.gv[j][z], acc);
+              s.bl1[j][o] = acc;
+              s.bl2[j][o] = unit_bias(Lb, 256 + ZP, ev, j0 + j, o);
             }
           }
+          mbar_arrive(&s.spk_empty);               // pack + bias slice of this unit are dead: the producer may refill
           ebar();
           // ======== fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM ========
           mbar_wait(&s.accU_full[wg], c_accU++ & 1);
@@ -475,15 +526,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           epi_h(!last, last);
         }
         // ---------------- head bias + activation, integrator step (thread-local) ----------------
-        {
-          const Lin L3 = lin[p.n_lin - 1];
 #pragma unroll
-          for (int f = 0; f < FP; ++f)
-            if (f < F) vout[f] = valid ? lrelu_tc(vout[f] + tc_bias_of(p, L3, ev, jg, f), p.slope) : 0.f;
-        }
+        for (int f = 0; f < FP; ++f)
+          if (f < F) vout[f] = valid ? lrelu_tc(vout[f] + b3[f], p.slope) : 0.f;
         if (p.solver >= 0) {
           const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
-          const float dt = p.dt[mid ? (ev >> 1) : ev];
+          const float dt = dt_ev;
           const bool first_stage = mid && ((ev & 1) == 0);
           const float hdt = __fmul_rn(0.5f, dt);
 #pragma unroll
@@ -536,14 +584,29 @@ __global__ void pack_images_kernel(const ImgSrc* __restrict__ src, uint8_t* __re
   }
 }
 
+// small-weight pack of unit u (bf16): [0] W_gg[z][o] = fc_global1[o][2H + z]   [1] W_glob[z][o] = fc_local1[o][H + z]
+//                                      [2] W_g2[z][o] = fc_global2[z][o] (fc_g2 for the stem); zero padding to 16 rows
+struct SpkSrc { const float* gg; int gg_ldo; const float* gl; int gl_ldo; const float* g2; int g2_ldo; int Z; };
+
+__global__ void pack_spk_kernel(const SpkSrc* __restrict__ src, __nv_bfloat16* __restrict__ out) {
+  const SpkSrc S = src[blockIdx.x];
+  __nv_bfloat16* o = out + (size_t)blockIdx.x * (TC_SPK / 2);
+  for (int i = threadIdx.x; i < 16 * TCH; i += blockDim.x) {
+    const int z = i >> 7, c = i & 127;
+    o[i] = __float2bfloat16((S.gg && z < S.Z) ? S.gg[(size_t)z * S.gg_ldo + c] : 0.f);
+    o[16 * TCH + i] = __float2bfloat16((S.gl && z < S.Z) ? S.gl[(size_t)z * S.gl_ldo + c] : 0.f);
+    o[32 * TCH + i] = __float2bfloat16(z < S.Z ? S.g2[(size_t)c * S.g2_ldo + z] : 0.f);
+  }
+}
+
 int tc_supported(const pfm_epic* h, int N) {
   const pfm_epic_cfg& c = h->cfg;
   if (c.hid != TCH) { set_error("PFM_PREC_BF16 needs hid == 128 (got %d); use PFM_PREC_FP32", c.hid); return PFM_ERR_UNSUPPORTED; }
   if (c.latent > TC_ZMAX) { set_error("PFM_PREC_BF16 needs latent <= %d (got %d)", TC_ZMAX, c.latent); return PFM_ERR_UNSUPPORTED; }
-  if (c.feats > 16) { set_error("PFM_PREC_BF16 needs feats <= 16 (got %d)", c.feats); return PFM_ERR_UNSUPPORTED; }
+  if (c.feats > TC_KXMAX) { set_error("PFM_PREC_BF16 needs feats <= %d (got %d)", TC_KXMAX, c.feats); return PFM_ERR_UNSUPPORTED; }
   if (c.layers < 1) { set_error("PFM_PREC_BF16 needs at least one EPiC layer"); return PFM_ERR_UNSUPPORTED; }
   if (N > TC_ROWS) { set_error("PFM_PREC_BF16: a jet of %d particles exceeds the %d-row group; use PFM_PREC_FP32", N, TC_ROWS); return PFM_ERR_UNSUPPORTED; }
-  if ((int)(sizeof(TcSmem) + 1024) > h->max_smem_optin) { set_error("PFM_PREC_BF16: not enough shared memory per block"); return PFM_ERR_UNSUPPORTED; }
+  if ((int)(sizeof(TcSmem<8>) + 1024) > h->max_smem_optin) { set_error("PFM_PREC_BF16: not enough shared memory per block"); return PFM_ERR_UNSUPPORTED; }
   return PFM_OK;
 }
 
@@ -571,17 +634,42 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
     src[it++] = mk(LIN_LAYER0 + 4 * l + 0, TCH);
     src[it++] = mk(LIN_LAYER0 + 4 * l + 3, 0);       // fc_local2
   }
-  const size_t bytes = (size_t)n_items * TC_MAT;
-  if (h->tc_bytes < bytes + sizeof(ImgSrc) * n_items) {
+  std::vector<SpkSrc> spk(c.layers + 1);
+  for (int u = 0; u <= c.layers; ++u) {
+    SpkSrc q;
+    memset(&q, 0, sizeof(q));
+    q.Z = c.latent;
+    if (u == 0) {
+      const Lin& G2 = h->lin_host[LIN_G2];
+      q.g2 = G2.Wt + (size_t)G2.m_off * G2.ldo; q.g2_ldo = G2.ldo;
+    } else {
+      const Lin& Ga = h->lin_host[LIN_LAYER0 + 4 * (u - 1) + 0];
+      const Lin& Gb = h->lin_host[LIN_LAYER0 + 4 * (u - 1) + 1];
+      const Lin& La = h->lin_host[LIN_LAYER0 + 4 * (u - 1) + 2];
+      q.gg = Ga.Wt + (size_t)(Ga.m_off + 2 * TCH) * Ga.ldo; q.gg_ldo = Ga.ldo;
+      q.gl = La.Wt + (size_t)La.g_off * La.ldo; q.gl_ldo = La.ldo;
+      q.g2 = Gb.Wt + (size_t)Gb.m_off * Gb.ldo; q.g2_ldo = Gb.ldo;
+    }
+    spk[u] = q;
+  }
+  const size_t img_bytes = (size_t)n_items * TC_MAT;
+  const size_t spk_bytes = (size_t)(c.layers + 1) * TC_SPK;
+  const size_t bytes = img_bytes + spk_bytes;
+  const size_t aux = sizeof(ImgSrc) * n_items + sizeof(SpkSrc) * spk.size();
+  if (h->tc_bytes < bytes + aux) {
     if (h->tc_store) cudaFree(h->tc_store);
     h->tc_store = nullptr; h->tc_bytes = 0;
-    PFM_CUDA_CHECK(cudaMalloc(&h->tc_store, bytes + sizeof(ImgSrc) * n_items));
-    h->tc_bytes = bytes + sizeof(ImgSrc) * n_items;
+    PFM_CUDA_CHECK(cudaMalloc(&h->tc_store, bytes + aux));
+    h->tc_bytes = bytes + aux;
   }
-  ImgSrc* dsrc = reinterpret_cast<ImgSrc*>(reinterpret_cast<uint8_t*>(h->tc_store) + bytes);
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->tc_store);
+  ImgSrc* dsrc = reinterpret_cast<ImgSrc*>(base + bytes);
+  SpkSrc* dspk = reinterpret_cast<SpkSrc*>(base + bytes + sizeof(ImgSrc) * n_items);
   PFM_CUDA_CHECK(cudaMemcpyAsync(dsrc, src.data(), sizeof(ImgSrc) * n_items, cudaMemcpyHostToDevice, st));
-  PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src is a host temporary
-  pack_images_kernel<<<n_items, 256, 0, st>>>(dsrc, reinterpret_cast<uint8_t*>(h->tc_store));
+  PFM_CUDA_CHECK(cudaMemcpyAsync(dspk, spk.data(), sizeof(SpkSrc) * spk.size(), cudaMemcpyHostToDevice, st));
+  PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src / spk are host temporaries
+  pack_images_kernel<<<n_items, 256, 0, st>>>(dsrc, base);
+  pack_spk_kernel<<<c.layers + 1, 256, 0, st>>>(dspk, reinterpret_cast<__nv_bfloat16*>(base + img_bytes));
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
@@ -589,7 +677,7 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
 template <int FP>
 static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
   auto kern = epic_tc_kernel<FP>;
-  const int smem = (int)sizeof(TcSmem) + 1024;
+  const int smem = (int)sizeof(TcSmem<FP>) + 1024;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, TC_THREADS, smem, st>>>(p);
   PFM_CUDA_CHECK(cudaGetLastError());
@@ -610,6 +698,14 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.n_items = 3 + 4 * c.layers;
   p.sum_scale = c.sum_scale; p.slope = c.neg_slope;
   p.lin = h->lin_dev; p.wimg = reinterpret_cast<const uint8_t*>(h->tc_store);
+  p.spk = p.wimg + (size_t)p.n_items * TC_MAT;
+  {
+    const int ZP = (c.latent + 3) & ~3;
+    p.boff_stem = h->lin_host[LIN_L1].bias_off;
+    p.boff_layer0 = h->lin_host[LIN_LAYER0].bias_off;
+    p.boff_layer_stride = 3 * TCH + ZP;
+    p.bias_chunk_floats = 3 * TCH + ZP;
+  }
   p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride; p.tbias_per_jet = a.tbias_per_jet;
   p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
   p.counter = h->plan.counter;
@@ -618,8 +714,7 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;
   const int kmax = a.Kx > c.feats ? a.Kx : c.feats;
   if (kmax <= 4) return launch_tc<4>(p, grid, st);
-  if (kmax <= 8) return launch_tc<8>(p, grid, st);
-  return launch_tc<16>(p, grid, st);
+  return launch_tc<8>(p, grid, st);
 }
 
 }  // namespace pfm
