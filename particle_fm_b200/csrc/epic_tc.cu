@@ -16,6 +16,8 @@
 // per-jet path costs ~5% extra tensor time instead of a CUDA-core GEMV.
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one lane), warps 4-7 / 8-11 = epilogue
 // warpgroups of tile A / tile B (TMEM lane quadrant = warp % 4).
+#include <cstdlib>
+
 #include "pfm_internal.cuh"
 #include "tc_ptx.cuh"
 
@@ -49,6 +51,7 @@ struct TcSmem {
   alignas(16) __nv_bfloat16 spk[3][16][TCH];   // [0] W_gg[z][o]  [1] W_glob[z][o]  [2] W_g2[z][o]   (current unit)
   alignas(16) float sbias[TC_SBIAS];           // time-bias slice of the current unit (4 consecutive linears)
   float inv_n[TC_J];
+  int boff[128];                               // bias-table offset of every linear (copied once: no global descriptor loads in the loop)
   int jrow0[TC_J + 1];
   int group;
   uint32_t tmem_base;
@@ -69,6 +72,7 @@ struct TcParams {
   const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
   const float* x_in; float* x_out; int B, N;
   int n_evals, solver, n_steps; const float* dt;
+  long long* prof;          // [3][20] debug phase timers (PFM_TC_PROF)
 };
 
 __device__ __forceinline__ float lrelu_tc(float v, float s) { return fmaxf(v, v * s); }   // 0 < s < 1
@@ -80,24 +84,59 @@ __device__ __forceinline__ float tc_bias_of(const TcParams& p, const Lin& L, int
   return b;
 }
 
-__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
-
-// 16 MMAs: D[128 x 128] (+)= A[128 x 128] . B[128 x 128]^T, A and B K-major SW128 images in shared memory
-__device__ __forceinline__ void issue_ss_128(uint32_t d, uint32_t a_base, uint32_t b_base, uint32_t idesc, bool acc_first) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t off = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
-    mma_ss(d, desc_kmajor(a_base + off), desc_kmajor(b_base + off), idesc, (acc_first || k > 0) ? 1u : 0u);
-  }
+// packed fp32x2 math (FADD2 / FMUL2 on sm_100): leaky_relu(v + b) for two neighbouring columns
+__device__ __forceinline__ void bias_lrelu2(uint32_t& v0, uint32_t& v1, float b0, float b1, unsigned long long slope2, bool valid) {
+  unsigned long long v = ((unsigned long long)v1 << 32) | v0;
+  const unsigned long long b = ((unsigned long long)__float_as_uint(b1) << 32) | __float_as_uint(b0);
+  unsigned long long a, t;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(v), "l"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(a), "l"(slope2));
+  const float r0 = fmaxf(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)t));
+  const float r1 = fmaxf(__uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)(t >> 32)));
+  v0 = valid ? __float_as_uint(r0) : 0u;
+  v1 = valid ? __float_as_uint(r1) : 0u;
 }
 
-template <int FP>
+__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// descriptor advance (units of 16 bytes) of K-step k inside a 128-wide K-major SW128 image: 64-column blocks are
+// 16 KB apart, a K=16 step is 32 bytes inside the swizzled 128-byte row
+__device__ __forceinline__ constexpr uint32_t kstep16(int k) { return (uint32_t)(k >> 2) * 1024u + (uint32_t)(k & 3) * 2u; }
+
+// 8 MMAs: D[128 x 128] (+)= A[128 x 128] . B[128 x 128]^T, descriptors of the two K-major SW128 images precomputed
+// (called by the whole, converged MMA warp; one elected lane issues -- operands stay in uniform registers)
+__device__ __forceinline__ void issue_ss_128(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc_first) {
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ss(d, a_desc + kstep16(k), b_desc + kstep16(k), idesc, (acc_first || k > 0) ? 1u : 0u);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
+  __syncwarp();
+}
+
+// Phase profiler (debug, PFM_TC_PROF=1): block 0 accumulates clock64() deltas per phase for one thread of each role.
+#define PROF_T(slot) do { if (PROF && prof_on) { const long long _n = clock64(); prof[slot] += _n - prof_t; prof_t = _n; } } while (0)
+
+template <int FP, bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  TcSmem<FP>& s = *reinterpret_cast<TcSmem<FP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte aligned view of the dynamic shared memory, derived by pointer arithmetic on the __shared__ array so
+  // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  TcSmem<FP>& s = *reinterpret_cast<TcSmem<FP>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Lin* lin = p.lin;
   const int L = p.L, Z = p.Z, F = p.F;
+  long long prof[20];
+  long long prof_t = 0;
+  const bool prof_on = PROF && blockIdx.x == 0 && (tid == 32 || tid == 128 || tid == 256);   // lane 0 of the MMA warp, of epilogue A, of epilogue B
+  if (PROF) {
+#pragma unroll
+    for (int i = 0; i < 20; ++i) prof[i] = 0;
+    prof_t = clock64();
+  }
 
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -119,6 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int c = i / FP, f = i - c * FP;
       s.w3s[c][f] = f < L3.ldo ? L3.Wt[(size_t)(L3.m_off + c) * L3.ldo + f] : 0.f;
     }
+    for (int i = tid; i < p.n_lin && i < 128; i += TC_THREADS) s.boff[i] = lin[i].bias_off;
   }
   tc_fence_before();
   __syncthreads();
@@ -142,8 +182,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     const int j0 = grp.x, nj = grp.y;
 
     if (warp == 0) {
-      // ================================ weight producer ================================
-      if (lane == 0) {
+      // ================================ weight producer (whole warp, elected lane issues) ================================
+      {
         const bool stage_bias = !p.tbias_per_jet;
         const uint32_t bias_bytes = stage_bias ? (uint32_t)p.bias_chunk_floats * 4u : 0u;
         for (int ev = 0; ev < p.n_evals; ++ev) {
@@ -153,101 +193,128 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             if (u >= 0) {
               mbar_wait(&s.spk_empty, (spk_it & 1) ^ 1);
               ++spk_it;
-              mbar_arrive_expect_tx(&s.spk_full, TC_SPK + bias_bytes);
-              bulk_copy_g2s(s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
-              if (stage_bias)
-                bulk_copy_g2s(s.sbias, p.tbias + (size_t)ev * p.bstride + (u == 0 ? p.boff_stem : p.boff_layer0 + (u - 1) * p.boff_layer_stride),
-                              bias_bytes, &s.spk_full);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&s.spk_full, TC_SPK + bias_bytes);
+                bulk_copy_g2s(s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
+                if (stage_bias)
+                  bulk_copy_g2s(s.sbias, p.tbias + (size_t)ev * p.bstride + (u == 0 ? p.boff_stem : p.boff_layer0 + (u - 1) * p.boff_layer_stride),
+                                bias_bytes, &s.spk_full);
+              }
+              __syncwarp();
             }
             const uint32_t slot = ring_it % TC_NSLOT, round = ring_it / TC_NSLOT;
             mbar_wait(&s.empty[slot], (round & 1) ^ 1);
-            mbar_arrive_expect_tx(&s.full[slot], TC_MAT);
-            bulk_copy_g2s(s.w[slot], p.wimg + (size_t)it * TC_MAT, TC_MAT, &s.full[slot]);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s.full[slot], TC_MAT);
+              bulk_copy_g2s(s.w[slot], p.wimg + (size_t)it * TC_MAT, TC_MAT, &s.full[slot]);
+            }
+            __syncwarp();
           }
         }
       }
     } else if (warp == 1) {
-      // ================================ MMA issuer ================================
-      if (lane == 0) {
+      // ================================ MMA issuer (whole warp, elected lane issues) ================================
+      {
         const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
         const uint32_t idesc_pool = make_idesc_bf16(128, 16, 1, 0);
         const uint32_t idesc_glob = make_idesc_bf16(128, 16, 0, 0);
-        const uint32_t hA = smem_u32(s.h[0]), hB = smem_u32(s.h[1]);
+        const uint64_t hA = desc_kmajor(smem_u32(s.h[0])), hB = desc_kmajor(smem_u32(s.h[1]));
+        const uint64_t hAt = desc_mnmajor(smem_u32(s.h[0]), 16384u, 1024u), hBt = desc_mnmajor(smem_u32(s.h[1]), 16384u, 1024u);
+        const uint64_t pdesc = desc_kmajor(smem_u32(s.P)), sdesc = desc_kmajor(smem_u32(s.St));
+        const uint64_t wdesc0 = desc_kmajor(smem_u32(s.w[0]));
         const uint32_t accH0 = tm, accH1 = tm + 128, accU0 = tm + 256, accU1 = tm + 384;
         const uint32_t dpool = tm + 384 + 64, dglob = tm + 384 + 80;
         auto wait_full = [&](uint32_t it) { mbar_wait(&s.full[it % TC_NSLOT], (it / TC_NSLOT) & 1); };
-        auto wslot = [&](uint32_t it) { return smem_u32(s.w[it % TC_NSLOT]); };
+        auto wslot = [&](uint32_t it) { return wdesc0 + (uint64_t)((it % TC_NSLOT) * (TC_MAT >> 4)); };
         for (int ev = 0; ev < p.n_evals; ++ev) {
           // ---- stem fc_l2: accH[t] (holds h1) += h1 . W_l2^T
           const uint32_t it_l2 = ring_it++;
           for (int t = 0; t < 2; ++t) {
+            PROF_T(0);
             mbar_wait(&s.hready[t], c_hready[t]++ & 1);
             tc_fence_after();
+            PROF_T(1);
             if (t == 0) wait_full(it_l2);
+            PROF_T(2);
             issue_ss_128(t ? accH1 : accH0, t ? hB : hA, wslot(it_l2), idesc, true);
-            mma_commit(&s.accH_full[t]);
+            commit_to(&s.accH_full[t]);
           }
-          mma_commit(&s.empty[it_l2 % TC_NSLOT]);
+          commit_to(&s.empty[it_l2 % TC_NSLOT]);
           for (int gi = 0; gi <= L; ++gi) {
             uint32_t it_w1 = 0;
             if (gi != 1) {   // a new version of h is complete: pool it   S[c][jet] = sum_rows h[row][c] P[jet][row]
+              PROF_T(0);
               mbar_wait(&s.hready[0], c_hready[0]++ & 1);
               mbar_wait(&s.hready[1], c_hready[1]++ & 1);
               tc_fence_after();
-              const uint32_t pb = smem_u32(s.P);
+              PROF_T(3);
+              if (elect_one()) {
 #pragma unroll
-              for (int t = 0; t < 2; ++t)
+                for (int t = 0; t < 2; ++t)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const uint64_t da = desc_mnmajor((t ? hB : hA) + (uint32_t)k * 2048u, 16384u, 1024u);
-                  const uint64_t db = desc_kmajor(pb + (uint32_t)(t * 2 + (k >> 2)) * 2048u + (uint32_t)(k & 3) * 32u);
-                  mma_ss(dpool, da, db, idesc_pool, (t | k) ? 1u : 0u);
-                }
-              mma_commit(&s.pool_full);
+                  for (int k = 0; k < 8; ++k) {      // 16 rows of h per step: +2 KB in the MN-major view; P: 2 KB per 64 rows
+                    const uint64_t da = (t ? hBt : hAt) + (uint64_t)(k * 128);
+                    const uint64_t db = pdesc + (uint64_t)((t * 2 + (k >> 2)) * 128 + (k & 3) * 2);
+                    mma_ss(dpool, da, db, idesc_pool, (t | k) ? 1u : 0u);
+                  }
+              }
+              __syncwarp();
+              commit_to(&s.pool_full);
             }
             if (gi >= 1) {   // fc_local1 of tile A does not need the global vector: issue it right away
               it_w1 = ring_it++;
+              PROF_T(0);
               wait_full(it_w1);
+              PROF_T(4);
               issue_ss_128(accU0, hA, wslot(it_w1), idesc, false);
-              mma_commit(&s.accU_full[0]);
+              commit_to(&s.accU_full[0]);
             }
             // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . S[:, jet],  W_sum likewise
             const uint32_t it_gm = ring_it++, it_gs = ring_it++;
+            PROF_T(0);
             mbar_wait(&s.glob_go, c_globgo++ & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(s.St);
+            PROF_T(5);
             for (int m = 0; m < 2; ++m) {
               const uint32_t itw = m ? it_gs : it_gm;
               wait_full(itw);
+              PROF_T(6);
+              const uint64_t wd = wslot(itw);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint32_t offa = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
-                const uint32_t offb = (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u;
-                mma_ss(dglob + m * 16, desc_kmajor(wslot(itw) + offa), desc_kmajor(sb + offb), idesc_glob, k ? 1u : 0u);
+                for (int k = 0; k < 8; ++k)
+                  mma_ss(dglob + m * 16, wd + kstep16(k), sdesc + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), idesc_glob, k ? 1u : 0u);
               }
+              __syncwarp();
             }
-            mma_commit(&s.glob_full);
-            mma_commit(&s.empty[it_gm % TC_NSLOT]);
-            mma_commit(&s.empty[it_gs % TC_NSLOT]);
+            commit_to(&s.glob_full);
+            commit_to(&s.empty[it_gm % TC_NSLOT]);
+            commit_to(&s.empty[it_gs % TC_NSLOT]);
+            PROF_T(0);
             mbar_wait(&s.d_free, c_dfree++ & 1);      // pooling / global accumulators (aliasing accU of tile B) consumed
             tc_fence_after();
+            PROF_T(7);
             if (gi >= 1) {
               issue_ss_128(accU1, hB, wslot(it_w1), idesc, false);
-              mma_commit(&s.accU_full[1]);
-              mma_commit(&s.empty[it_w1 % TC_NSLOT]);
+              commit_to(&s.accU_full[1]);
+              commit_to(&s.empty[it_w1 % TC_NSLOT]);
               const uint32_t it_w2 = ring_it++;
               for (int t = 0; t < 2; ++t) {          // fc_local2: accH[t] += u[t] (bf16 in TMEM) . W2^T
+                PROF_T(0);
                 mbar_wait(&s.u_ready[t], c_uready[t]++ & 1);
                 tc_fence_after();
+                PROF_T(8 + t);
                 if (t == 0) wait_full(it_w2);
+                PROF_T(10);
+                const uint64_t wd = wslot(it_w2);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const uint32_t off = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
-                  mma_ts(t ? accH1 : accH0, (t ? accU1 : accU0) + (uint32_t)k * 8u, desc_kmajor(wslot(it_w2) + off), idesc, 1u);
+                  for (int k = 0; k < 8; ++k) mma_ts(t ? accH1 : accH0, (t ? accU1 : accU0) + (uint32_t)k * 8u, wd + kstep16(k), idesc, 1u);
                 }
-                mma_commit(&s.accH_full[t]);
+                __syncwarp();
+                commit_to(&s.accH_full[t]);
               }
-              mma_commit(&s.empty[it_w2 % TC_NSLOT]);
+              commit_to(&s.empty[it_w2 % TC_NSLOT]);
             }
           }
         }
@@ -286,9 +353,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int jg = j0 + myjet;
       // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
       // slow direct path when every jet has its own time (training-style forward)
-      auto unit_bias = [&](const Lin& Lx, int voff, int ev_, int jet_global, int o) -> float {
-        float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + Lx.bias_off + o] : s.sbias[voff + o];
-        if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + Lx.bias_off + o];
+      auto unit_bias = [&](int lin_idx, int voff, int ev_, int jet_global, int o) -> float {
+        float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o] : s.sbias[voff + o];
+        if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o];
         (void)ev_;
         return b;
       };
@@ -306,20 +373,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 
       for (int ev = 0; ev < p.n_evals; ++ev) {
         // ---------------- unit 0 pack (stem biases + fc_g2) has landed; per-jet stem biases ----------------
+        PROF_T(0);
         mbar_wait(&s.spk_full, c_spk++ & 1);
+        PROF_T(1);
         float b3[FP];                              // head bias and step size: loaded now, used at the end of the evaluation
         {
-          const Lin L3 = lin[p.n_lin - 1];
 #pragma unroll
-          for (int f = 0; f < FP; ++f) b3[f] = f < F ? tc_bias_of(p, L3, ev, jg, f) : 0.f;
+          for (int f = 0; f < FP; ++f) {
+            b3[f] = 0.f;
+            if (f < F) {
+              b3[f] = p.tbias[(size_t)(p.tbias_per_jet ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
+              if (p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
+            }
+          }
         }
         const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
         {
-          const Lin L1 = lin[LIN_L1], L2 = lin[LIN_L2];
           for (int i = et; i < nj * TCH; i += 256) {
             const int j = i >> 7, o = i & 127;
-            s.bl1[j][o] = unit_bias(L1, 0, ev, j0 + j, o);
-            s.bl2[j][o] = unit_bias(L2, 128, ev, j0 + j, o);
+            s.bl1[j][o] = unit_bias(LIN_L1, 0, ev, j0 + j, o);
+            s.bl2[j][o] = unit_bias(LIN_L2, 128, ev, j0 + j, o);
           }
         }
         ebar();
@@ -352,70 +425,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&s.hready[wg]);
+        PROF_T(2);
 
         // residual update epilogue shared by the stem's fc_l2 and every fc_local2:
         //   h = lrelu(acc + bias) -> TMEM fp32 (in place) and shared bf16; on the last layer also the head
-        auto epi_h = [&](bool write_back, bool head) {
-          mbar_wait(&s.accH_full[wg], c_accH++ & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(accH + c * 32, v);
-            tmem_wait_ld();
-            const float4* bj = reinterpret_cast<const float4*>(&s.bl2[myjet][c * 32]);
+        const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
+        // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16 (+ head)
+        auto epi_h_chunk = [&](uint32_t (&v)[32], int c, bool write_back, bool head) {
+          const float4* bj = reinterpret_cast<const float4*>(&s.bl2[myjet][c * 32]);
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 b = bj[i4];
-              float a0 = __uint_as_float(v[i4 * 4 + 0]) + b.x, a1 = __uint_as_float(v[i4 * 4 + 1]) + b.y;
-              float a2 = __uint_as_float(v[i4 * 4 + 2]) + b.z, a3 = __uint_as_float(v[i4 * 4 + 3]) + b.w;
-              a0 = valid ? lrelu_tc(a0, p.slope) : 0.f; a1 = valid ? lrelu_tc(a1, p.slope) : 0.f;
-              a2 = valid ? lrelu_tc(a2, p.slope) : 0.f; a3 = valid ? lrelu_tc(a3, p.slope) : 0.f;
-              v[i4 * 4 + 0] = __float_as_uint(a0); v[i4 * 4 + 1] = __float_as_uint(a1);
-              v[i4 * 4 + 2] = __float_as_uint(a2); v[i4 * 4 + 3] = __float_as_uint(a3);
-            }
-            if (head) {
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 b = bj[i4];
+            bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2, valid);
+            bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2, valid);
+          }
+          if (head) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float a = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) {
+              const float a = __uint_as_float(v[i]);
 #pragma unroll
-                for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
-              }
-            }
-            if (write_back) {
-              tmem_st32(accH + c * 32, v);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-                pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-                pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-                pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-                const int c16 = c * 4 + q;
-                *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
-              }
+              for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
             }
           }
+          if (write_back) {
+            tmem_st32(accH + c * 32, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+              pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+              pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+              pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+              const int c16 = c * 4 + q;
+              *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
+            }
+          }
+        };
+        // residual update epilogue shared by the stem's fc_l2 and every fc_local2; the TMEM load of chunk c+1 is in
+        // flight while chunk c is processed (tcgen05.wait::ld covers all outstanding loads, so issue after the wait)
+        auto epi_h = [&](bool write_back, bool head) {
+          PROF_T(0);
+          mbar_wait(&s.accH_full[wg], c_accH++ & 1);
+          tc_fence_after();
+          PROF_T(3);
+          uint32_t va[32], vb[32];
+          tmem_ld32(accH, va);
+          tmem_wait_ld();
+          tmem_ld32(accH + 32, vb);
+          epi_h_chunk(va, 0, write_back, head);
+          tmem_wait_ld();
+          tmem_ld32(accH + 64, va);
+          epi_h_chunk(vb, 1, write_back, head);
+          tmem_wait_ld();
+          tmem_ld32(accH + 96, vb);
+          epi_h_chunk(va, 2, write_back, head);
+          tmem_wait_ld();
+          epi_h_chunk(vb, 3, write_back, head);
           if (write_back) {
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&s.hready[wg]);
           }
+          PROF_T(4);
         };
         epi_h(true, false);                        // stem fc_l2 (+ residual h1)
 
         for (int gi = 0; gi <= L; ++gi) {
           // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
-          const Lin Ga = gi == 0 ? lin[LIN_G1] : lin[LIN_LAYER0 + 4 * (gi - 1) + 0];
-          const Lin Gb = gi == 0 ? lin[LIN_G2] : lin[LIN_LAYER0 + 4 * (gi - 1) + 1];
+          const int Ga = gi == 0 ? LIN_G1 : LIN_LAYER0 + 4 * (gi - 1) + 0;
+          const int Gb = gi == 0 ? LIN_G2 : LIN_LAYER0 + 4 * (gi - 1) + 1;
           const int ZP = (Z + 3) & ~3;
           const int off_ga = gi == 0 ? 256 : 0, off_gb = gi == 0 ? 384 : 128;     // slice offsets inside sbias
+          PROF_T(0);
           if (gi >= 1) mbar_wait(&s.spk_full, c_spk++ & 1);                        // unit gi's pack (unit 0: waited at eval start)
+          PROF_T(5);
+          if (wg == 1) {
+            // tile B's warps are idle during the (narrow) global chain: they compute bias + W_gg . g (previous global
+            // vector) for every (jet, o = r) into the g1 buffer and hand over through named barrier 2
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = j < nj ? unit_bias(Ga, off_ga, ev, j0 + j, r) : 0.f;
+            if (gi >= 1) {
+#pragma unroll
+              for (int z = 0; z < TC_ZMAX; ++z) {
+                if (z < Z) {
+                  const float w = __bfloat162float(s.spk[0][z][r]);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) a[j] = fmaf(w, s.gv[j][z], a[j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s.g1[j][r] = a[j];
+            asm volatile("bar.arrive 2, 256;" ::: "memory");
+            PROF_T(8);
+          }
           if (wg == 0) {
+            PROF_T(8);
             if (gi != 1) {                         // new pooled sums: TMEM -> bf16 B operand in shared memory
               mbar_wait(&s.pool_full, c_pool++ & 1);
               tc_fence_after();
+              PROF_T(6);
               uint32_t v[16];
               tmem_ld16(dpool, v);
               tmem_wait_ld();
@@ -426,19 +537,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             }
             tc_fence_before();
             mbar_arrive(&s.glob_go);
-            // while the two N=16 MMAs run: bias + W_gg . g (previous global vector), all operands in shared memory
-            float a[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = j < nj ? unit_bias(Ga, off_ga, ev, j0 + j, r) : 0.f;
-            if (gi >= 1) {
-              for (int z = 0; z < Z; ++z) {
-                const float w = __bfloat162float(s.spk[0][z][r]);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a[j] = fmaf(w, s.gv[j][z], a[j]);
-              }
-            }
+            PROF_T(7);
             mbar_wait(&s.glob_full, c_glob++ & 1);
             tc_fence_after();
+            PROF_T(9);
             uint32_t dm[16], ds[16];
             tmem_ld16(dglob, dm);
             tmem_ld16(dglob + 16, ds);
@@ -446,27 +548,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             tc_fence_before();
             mbar_arrive(&s.d_free);
             // g1[j][o = r] = lrelu(W_mean.S / n + s * W_sum.S (+ W_g . g) + bias)     (epic.py:180-182, :375-377)
+            asm volatile("bar.sync 2, 256;" ::: "memory");      // tile B's warps have written bias + W_gg . g
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float v = fmaf(__uint_as_float(dm[j]), s.inv_n[j], a[j]);
+              float v = fmaf(__uint_as_float(dm[j]), s.inv_n[j], s.g1[j][r]);
               v = fmaf(__uint_as_float(ds[j]), p.sum_scale, v);
               s.g1[j][r] = lrelu_tc(v, p.slope);
             }
+            PROF_T(10);
           }
           ebar();
-          {   // fc_g2 / fc_global2 (+ residual for the layers): one warp per (jet, latent) output
-            const int ew = et >> 5;
-            for (int item = ew; item < nj * Z; item += 8) {
-              const int j = item / Z, z = item - j * Z;
+          PROF_T(11);
+          {   // fc_g2 / fc_global2 (+ residual for the layers): 8 threads per (jet, latent) output, 16 inputs each
+            const int sub = et & 7, pi = et >> 3;
+            const int n_out = nj * Z;
+            for (int base = 0; base < n_out; base += 32) {
+              const int item = base + pi;
+              const bool on = item < n_out;
+              const int j = on ? item / Z : 0, z = on ? item - (item / Z) * Z : 0;
+              const uint4* wp = reinterpret_cast<const uint4*>(&s.spk[2][z][sub * 16]);
+              const float4* gp = reinterpret_cast<const float4*>(&s.g1[j][sub * 16]);
+              const uint4 w0 = wp[0], w1 = wp[1];
+              const float4 g0 = gp[0], g1v = gp[1], g2v = gp[2], g3 = gp[3];
+              const __nv_bfloat162* wh0 = reinterpret_cast<const __nv_bfloat162*>(&w0);
+              const __nv_bfloat162* wh1 = reinterpret_cast<const __nv_bfloat162*>(&w1);
               float acc = 0.f;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int o = lane + 32 * q;
-                acc = fmaf(__bfloat162float(s.spk[2][z][o]), s.g1[j][o], acc);
-              }
-#pragma unroll
-              for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
-              if (lane == 0) {
+              float2 f;
+              f = __bfloat1622float2(wh0[0]); acc = fmaf(f.x, g0.x, acc); acc = fmaf(f.y, g0.y, acc);
+              f = __bfloat1622float2(wh0[1]); acc = fmaf(f.x, g0.z, acc); acc = fmaf(f.y, g0.w, acc);
+              f = __bfloat1622float2(wh0[2]); acc = fmaf(f.x, g1v.x, acc); acc = fmaf(f.y, g1v.y, acc);
+              f = __bfloat1622float2(wh0[3]); acc = fmaf(f.x, g1v.z, acc); acc = fmaf(f.y, g1v.w, acc);
+              f = __bfloat1622float2(wh1[0]); acc = fmaf(f.x, g2v.x, acc); acc = fmaf(f.y, g2v.y, acc);
+              f = __bfloat1622float2(wh1[1]); acc = fmaf(f.x, g2v.z, acc); acc = fmaf(f.y, g2v.w, acc);
+              f = __bfloat1622float2(wh1[2]); acc = fmaf(f.x, g3.x, acc); acc = fmaf(f.y, g3.y, acc);
+              f = __bfloat1622float2(wh1[3]); acc = fmaf(f.x, g3.z, acc); acc = fmaf(f.y, g3.w, acc);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+              if (on && sub == 0) {
                 acc += unit_bias(Gb, off_gb, ev, j0 + j, z);
                 if (gi >= 1) acc += s.gv[j][z];
                 s.gv[j][z] = lrelu_tc(acc, p.slope);
@@ -476,47 +595,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           if (gi == 0) {                           // the stem has no per-particle linears of its own after the pooling
             mbar_arrive(&s.spk_empty);
             ebar();
+            PROF_T(12);
             continue;
           }
           ebar();
+          PROF_T(12);
           const int l = gi - 1;
           {   // per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
-            const Lin La = lin[LIN_LAYER0 + 4 * l + 2], Lb = lin[LIN_LAYER0 + 4 * l + 3];
+            const int La = LIN_LAYER0 + 4 * l + 2, Lb = LIN_LAYER0 + 4 * l + 3;
             const int o = et & 127;
+            float wgl[TC_ZMAX];
+#pragma unroll
+            for (int z = 0; z < TC_ZMAX; ++z) wgl[z] = z < Z ? __bfloat162float(s.spk[1][z][o]) : 0.f;
             for (int j = et >> 7; j < nj; j += 2) {
               float acc = unit_bias(La, 128 + ZP, ev, j0 + j, o);
-              for (int z = 0; z < Z; ++z) acc = fmaf(__bfloat162float(s.spk[1][z][o]), s.gv[j][z], acc);
+#pragma unroll
+              for (int z = 0; z < TC_ZMAX; ++z) acc = fmaf(wgl[z], s.gv[j][z], acc);
               s.bl1[j][o] = acc;
               s.bl2[j][o] = unit_bias(Lb, 256 + ZP, ev, j0 + j, o);
             }
           }
           mbar_arrive(&s.spk_empty);               // pack + bias slice of this unit are dead: the producer may refill
           ebar();
+          PROF_T(13);
           // ======== fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM ========
           mbar_wait(&s.accU_full[wg], c_accU++ & 1);
           tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(accU + c * 32, v);
-            tmem_wait_ld();
-            const float4* bj = reinterpret_cast<const float4*>(&s.bl1[myjet][c * 32]);
-            uint32_t u16[16];
+          PROF_T(14);
+          {
+            auto epi1_chunk = [&](uint32_t (&v)[32], int c) {
+              const float4* bj = reinterpret_cast<const float4*>(&s.bl1[myjet][c * 32]);
+              uint32_t u16[16];
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 b = bj[i4];
-              float a0 = __uint_as_float(v[i4 * 4 + 0]) + b.x, a1 = __uint_as_float(v[i4 * 4 + 1]) + b.y;
-              float a2 = __uint_as_float(v[i4 * 4 + 2]) + b.z, a3 = __uint_as_float(v[i4 * 4 + 3]) + b.w;
-              a0 = valid ? lrelu_tc(a0, p.slope) : 0.f; a1 = valid ? lrelu_tc(a1, p.slope) : 0.f;
-              a2 = valid ? lrelu_tc(a2, p.slope) : 0.f; a3 = valid ? lrelu_tc(a3, p.slope) : 0.f;
-              u16[i4 * 2 + 0] = pack_bf16x2(a0, a1);
-              u16[i4 * 2 + 1] = pack_bf16x2(a2, a3);
-            }
-            tmem_st16(accU + c * 16, u16);          // columns [16c, 16c+16) were already read (c <= 2c+1)
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 b = bj[i4];
+                bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2, valid);
+                bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2, valid);
+                u16[i4 * 2 + 0] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]));
+                u16[i4 * 2 + 1] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 2]), __uint_as_float(v[i4 * 4 + 3]));
+              }
+              tmem_st16(accU + c * 16, u16);        // columns [16c, 16c+16) were already read (16c+16 <= 32c+32)
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(accU, va);
+            tmem_wait_ld();
+            tmem_ld32(accU + 32, vb);
+            epi1_chunk(va, 0);
+            tmem_wait_ld();
+            tmem_ld32(accU + 64, va);
+            epi1_chunk(vb, 1);
+            tmem_wait_ld();
+            tmem_ld32(accU + 96, vb);
+            epi1_chunk(va, 2);
+            tmem_wait_ld();
+            epi1_chunk(vb, 3);
           }
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&s.u_ready[wg]);
+          PROF_T(15);
           // ======== fc_local2 epilogue (+ head after the last layer) ========
           const bool last = (l == L - 1);
           if (last) {
@@ -545,7 +682,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             }
           }
         }
+        PROF_T(16);
         ebar();      // bl1/bl2 of this evaluation are dead before the next one rewrites them
+        PROF_T(17);
       }
       // ---------------- write back ----------------
       for (int j = 0; j < nj; ++j) {
@@ -562,6 +701,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           if (f < F) dst[f] = p.solver >= 0 ? x0[f] : vout[f];
       }
     }
+  }
+  if (PROF && prof_on && p.prof) {
+    const int role = tid == 32 ? 0 : (tid == 128 ? 1 : 2);
+    for (int i = 0; i < 20; ++i) p.prof[role * 20 + i] = prof[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -604,7 +747,7 @@ int tc_supported(const pfm_epic* h, int N) {
   if (c.hid != TCH) { set_error("PFM_PREC_BF16 needs hid == 128 (got %d); use PFM_PREC_FP32", c.hid); return PFM_ERR_UNSUPPORTED; }
   if (c.latent > TC_ZMAX) { set_error("PFM_PREC_BF16 needs latent <= %d (got %d)", TC_ZMAX, c.latent); return PFM_ERR_UNSUPPORTED; }
   if (c.feats > TC_KXMAX) { set_error("PFM_PREC_BF16 needs feats <= %d (got %d)", TC_KXMAX, c.feats); return PFM_ERR_UNSUPPORTED; }
-  if (c.layers < 1) { set_error("PFM_PREC_BF16 needs at least one EPiC layer"); return PFM_ERR_UNSUPPORTED; }
+  if (c.layers < 1 || c.layers > 30) { set_error("PFM_PREC_BF16 needs 1..30 EPiC layers (got %d)", c.layers); return PFM_ERR_UNSUPPORTED; }
   if (N > TC_ROWS) { set_error("PFM_PREC_BF16: a jet of %d particles exceeds the %d-row group; use PFM_PREC_FP32", N, TC_ROWS); return PFM_ERR_UNSUPPORTED; }
   if ((int)(sizeof(TcSmem<8>) + 1024) > h->max_smem_optin) { set_error("PFM_PREC_BF16: not enough shared memory per block"); return PFM_ERR_UNSUPPORTED; }
   return PFM_OK;
@@ -674,9 +817,9 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
   return PFM_OK;
 }
 
-template <int FP>
+template <int FP, bool PROF>
 static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
-  auto kern = epic_tc_kernel<FP>;
+  auto kern = epic_tc_kernel<FP, PROF>;
   const int smem = (int)sizeof(TcSmem<FP>) + 1024;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, TC_THREADS, smem, st>>>(p);
@@ -713,8 +856,28 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;
   const int kmax = a.Kx > c.feats ? a.Kx : c.feats;
-  if (kmax <= 4) return launch_tc<4>(p, grid, st);
-  return launch_tc<8>(p, grid, st);
+  if (getenv("PFM_TC_PROF")) {        // debug: phase timers of block 0, printed after the kernel
+    static long long* dprof = nullptr;
+    if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, sizeof(long long) * 60));
+    PFM_CUDA_CHECK(cudaMemsetAsync(dprof, 0, sizeof(long long) * 60, st));
+    p.prof = dprof;
+    int rc = kmax <= 4 ? launch_tc<4, true>(p, grid, st) : launch_tc<8, true>(p, grid, st);
+    if (rc != PFM_OK) return rc;
+    long long hp[60];
+    PFM_CUDA_CHECK(cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st));
+    PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+    const char* roles[3] = {"mma", "epiA", "epiB"};
+    for (int r = 0; r < 3; ++r) {
+      long long tot = 0;
+      for (int i = 0; i < 20; ++i) tot += hp[r * 20 + i];
+      fprintf(stderr, "[pfm tc prof] %-4s total %lld cyc:", roles[r], tot);
+      for (int i = 0; i < 20; ++i) fprintf(stderr, " %d:%.1f%%", i, tot ? 100.0 * hp[r * 20 + i] / tot : 0.0);
+      fprintf(stderr, "\n");
+    }
+    return PFM_OK;
+  }
+  if (kmax <= 4) return launch_tc<4, false>(p, grid, st);
+  return launch_tc<8, false>(p, grid, st);
 }
 
 }  // namespace pfm
