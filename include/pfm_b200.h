@@ -119,6 +119,38 @@ int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float*
                     const float* t_codes, const float* t_codes_in, const float* dt, int solver,
                     int n_steps, int B, int N, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training (fp32 path).  Gradients are returned w.r.t. the FOLDED weights and the biases in one
+ * flat buffer  [W_0 (out_0 x in_0, row-major) | b_0 | W_1 | b_1 | ...]  of pfm_epic_grad_size()
+ * floats, linears in the order of pfm_epic_set_weights; the host maps dW onto weight_g / weight_v
+ * (W = g*v/||v||).  A flat buffer is what a data-parallel all-reduce wants.
+ * --------------------------------------------------------------------------------------------- */
+long long pfm_epic_grad_size(const pfm_epic* h);
+
+/* Fused flow-matching training step:  losses.py:38-77 (FM-OT), :101-136 (CFM), :308-342 (droid)
+ * + the autograd backward of the network.  The random draws are the caller's (the reference draws
+ * t on the CPU generator and the noise on the device):
+ *   x1      [B, N, feats]   data            t       [B]          per-jet time
+ *   t_code  [B, t_dim]      time code of t  t_code_in [B, input_dim-feats]  (add_time_to_input) or NULL
+ *   noise0  [B, N, feats]   z / x0          noise1  [B, N, feats] (CFM's extra epsilon) or NULL
+ *   mask    [B, N] or NULL  cond [B, cond_dim] or NULL
+ * Computes  y, u_t  by the loss kind's interpolation, v = net(t, y),
+ *   loss_out[0] = sum((v - u_t)^2) / sum(mask)            (device scalar)
+ * and, if grad_flat != NULL, d loss / d(folded weights, biases) into grad_flat (overwritten). */
+int pfm_epic_loss_fwd_bwd(pfm_epic* h, const float* x1, const float* t, const float* t_code,
+                          const float* t_code_in, const float* noise0, const float* noise1,
+                          const float* mask, const float* cond, int loss_kind, float sigma,
+                          float* loss_out, float* grad_flat, int B, int N, void* stream);
+
+/* Generic differentiable evaluation (autograd of CNF.forward / EPiC_encoder.forward for any loss):
+ * pfm_epic_forward_train = pfm_epic_forward that also keeps the activations in the handle;
+ * pfm_epic_backward consumes them once: given grad_out = dL/d out [B,N,feats] it writes
+ * dL/dx into grad_x [B,N,input_dim] (optional) and dL/d(weights) into grad_flat (optional). */
+int pfm_epic_forward_train(pfm_epic* h, const float* t_code, int t_rows, const float* x,
+                           const float* mask, const float* cond, float* out, int B, int N, void* stream);
+int pfm_epic_backward(pfm_epic* h, const float* t_code, int t_rows, const float* cond,
+                      const float* grad_out, float* grad_x, float* grad_flat, int B, int N, void* stream);
+
 /* Introspection for tests / bench: kernels launched by the last call on this handle and the
  * number of CTA work groups the last plan produced. */
 int pfm_epic_last_launches(const pfm_epic* h);

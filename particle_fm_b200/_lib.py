@@ -36,6 +36,11 @@ _SIGNATURES = {
     "pfm_epic_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "pfm_epic_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_epic_grad_size": (C.c_longlong, [C.c_void_p]),
+    "pfm_epic_loss_fwd_bwd": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, _F, _F, C.c_int, C.c_float, _F, _F, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    "pfm_epic_forward_train": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_epic_backward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),
     "pfm_epic_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -12,11 +12,9 @@
 //   (+ W_glob . g  per jet, for fc_local1),
 // which is the same sum in a different association order (fp32 rounding only).
 #include "pfm_internal.cuh"
+#include "simt_common.cuh"
 
 namespace pfm {
-
-static constexpr int kThreads = 256;
-static constexpr int kWarps = kThreads / 32;
 
 struct SimtParams {
   int F, Kx, Kxp, x_ld, xin_off, H, Hp, LDH, Z, L, n_lin;
@@ -27,83 +25,16 @@ struct SimtParams {
   const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
   const float* x_in; float* x_out; int B, N;
   int n_evals, solver, n_steps; const float* dt;
+  // training forward (TRAIN instantiation): interpolation inputs, saved activations, loss
+  const float* x1; const float* tjet; const float* noise0; const float* noise1; int loss_kind; float sigma;
+  float* act; size_t act_stage_stride; int Hp_act;          // act[stage][row][Hp_act]
+  float* yact;                                              // yact[row][Kx]   network input of every real particle
+  float* jact; int junit; int jstride; int LDP_act;         // jact[jet][unit][pool input (LDP) | g1 (Hp) | g]
+  float* dpre3; float* loss_acc; const int* rowoff; const int* n_total;
   // shared-memory carve-up (float offsets)
   int o_xs, o_x0, o_hs, o_tmp, o_wbuf, o_pool, o_g, o_g1, o_bl1, o_bl2, o_v, o_int, total_floats;
   int wbuf_floats, LDB, LDP;
 };
-
-__device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// ---------------------------------------------------------------------------------------------
-// Row-block GEMM on CUDA cores.  Every warp owns RB consecutive rows of the current chunk and all
-// `out` columns (lane l holds columns l, l+32, ...: TC per lane).  The k-major weight block
-// Wt[K, ldo] streams through a double-buffered shared-memory stage shared by the 8 warps.
-//   acc[r][i] = sum_k A[row0 + r][k] * Wt[k][lane + 32 i]
-// A rows are zero in their padding columns [K, round_up(K,4)), so the k loop runs on multiples of 4.
-// ---------------------------------------------------------------------------------------------
-template <int TC, int RB>
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int K,
-                                          int ldo, float* wbuf, int wbuf_half, int KC, float (&acc)[RB][TC]) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
-#pragma unroll
-    for (int i = 0; i < TC; ++i) acc[r][i] = 0.f;
-  const int Kp = (K + 3) & ~3;
-  const int n_chunks = (Kp + KC - 1) / KC;
-  const float* Arow = A + (size_t)(warp * RB) * lda;
-  // prologue: chunk 0
-  {
-    int kc = Kp < KC ? Kp : KC;
-    int n16 = kc * ldo / 4;
-    for (int i = tid; i < n16; i += kThreads) cp_async16(wbuf + i * 4, Wt + i * 4);
-    cp_async_commit();
-  }
-  for (int c = 0; c < n_chunks; ++c) {
-    const int k0 = c * KC;
-    if (c + 1 < n_chunks) {
-      int k1 = k0 + KC;
-      int kc = (Kp - k1) < KC ? (Kp - k1) : KC;
-      int n16 = kc * ldo / 4;
-      float* dst = wbuf + ((c + 1) & 1) * wbuf_half;
-      const float* src = Wt + (size_t)k1 * ldo;
-      for (int i = tid; i < n16; i += kThreads) cp_async16(dst + i * 4, src + i * 4);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const float* wb = wbuf + (c & 1) * wbuf_half;
-    const int kc = (Kp - k0) < KC ? (Kp - k0) : KC;
-    for (int kk = 0; kk < kc; kk += 4) {
-      float4 a[RB];
-#pragma unroll
-      for (int r = 0; r < RB; ++r) a[r] = *reinterpret_cast<const float4*>(Arow + (size_t)r * lda + k0 + kk);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float w[TC];
-#pragma unroll
-        for (int i = 0; i < TC; ++i) w[i] = wb[(kk + q) * ldo + lane + 32 * i];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          const float av = q == 0 ? a[r].x : (q == 1 ? a[r].y : (q == 2 ? a[r].z : a[r].w));
-#pragma unroll
-          for (int i = 0; i < TC; ++i) acc[r][i] = fmaf(av, w[i], acc[r][i]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
 
 // per-jet effective bias of one linear: time table row + cond table row (+ W_glob . g)
 __device__ __forceinline__ float bias_of(const SimtParams& p, const Lin& L, int eval, int jet_global, int o) {
@@ -113,7 +44,7 @@ __device__ __forceinline__ float bias_of(const SimtParams& p, const Lin& L, int 
   return b;
 }
 
-template <int TC, int RB>
+template <int TC, int RB, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams p) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem + p.o_xs;      // [R_cap, LDX]   current network input (state or midpoint state)
@@ -153,6 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
     }
     __syncthreads();
     const int R = jrow0[nj];
+    const int row_g0 = TRAIN ? p.rowoff[j0] : 0;     // first packed row of this group in the saved-activation arrays
     // zero everything that later relies on zero padding, then load the group's particles
     for (int i = tid; i < p.R_cap * LDX; i += kThreads) xs[i] = 0.f;
     for (int i = tid; i < p.R_cap * LDH; i += kThreads) hs[i] = 0.f;
@@ -164,9 +96,30 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
       for (int i = tid; i < n * p.Kx; i += kThreads) {
         const int r = i / p.Kx, c = i - r * p.Kx;
         const int part = p.ridx[(size_t)(j0 + j) * p.N + r];
-        const float v = p.x_in[((size_t)(j0 + j) * p.N + part) * p.x_ld + c];
+        const size_t gi = ((size_t)(j0 + j) * p.N + part) * p.x_ld + c;
+        float v;
+        if (TRAIN && p.loss_kind >= 0) {
+          // flow-matching interpolation y(x1, t, noise) and target u_t (losses.py:56-62, :115-119, :320-326);
+          // the target is parked in x0 until the loss is evaluated
+          const float x = p.x1[gi], t = p.tjet[j0 + j], z = p.noise0[gi];
+          float u;
+          if (p.loss_kind == PFM_LOSS_FM_OT) {
+            v = (1.f - t) * x + (p.sigma + (1.f - p.sigma) * t) * z;
+            u = (1.f - p.sigma) * z - x;
+          } else if (p.loss_kind == PFM_LOSS_CFM) {
+            v = ((1.f - t) * x + t * z) + p.sigma * p.noise1[gi];
+            u = z - x;
+          } else {
+            v = x + t * z;
+            u = z;
+          }
+          x0[(r0 + r) * F + c] = u;
+        } else {
+          v = p.x_in[gi];
+          if (p.solver >= 0) x0[(r0 + r) * F + c] = v;
+        }
         xs[(r0 + r) * LDX + c] = v;
-        if (p.solver >= 0) x0[(r0 + r) * F + c] = v;
+        if (TRAIN) p.yact[(size_t)(row_g0 + r0 + r) * p.Kx + c] = v;
       }
     }
     __syncthreads();
@@ -193,7 +146,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll
               for (int i = 0; i < TC; ++i) {
                 const int o = lane + 32 * i;
-                if (o < H) tmp[(warp * RB + r) * LDH + o] = lrelu(acc[r][i] + bj[o], p.slope);
+                if (o < H) {
+                  const float hv = lrelu(acc[r][i] + bj[o], p.slope);
+                  tmp[(warp * RB + r) * LDH + o] = hv;
+                  if (TRAIN) p.act[(size_t)(row_g0 + row) * p.Hp_act + o] = hv;                       // stage 0: h1
+                }
               }
             }
           }
@@ -207,7 +164,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll
               for (int i = 0; i < TC; ++i) {
                 const int o = lane + 32 * i;
-                if (o < H) hs[(size_t)row * LDH + o] = lrelu(acc[r][i] + bj[o] + tmp[(warp * RB + r) * LDH + o], p.slope);
+                if (o < H) {
+                  const float hv = lrelu(acc[r][i] + bj[o] + tmp[(warp * RB + r) * LDH + o], p.slope);
+                  hs[(size_t)row * LDH + o] = hv;
+                  if (TRAIN) p.act[p.act_stage_stride + (size_t)(row_g0 + row) * p.Hp_act + o] = hv;  // stage 1: h0
+                }
               }
             }
           }
@@ -224,6 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           for (int r = r0; r < r1; ++r) s += hs[(size_t)r * LDH + o];
           pool[j * LDP + o] = s * p.sum_scale;                    // (sum, mean) order in the stem, :373
           pool[j * LDP + H + o] = s / (float)(r1 - r0);
+          if (TRAIN) {                                                                                 // unit 0: pool input
+            p.jact[(size_t)(j0 + j) * p.jstride + o] = pool[j * LDP + o];
+            p.jact[(size_t)(j0 + j) * p.jstride + H + o] = pool[j * LDP + H + o];
+          }
         }
         __syncthreads();
         const Lin G1 = lin[LIN_G1], G2 = lin[LIN_G2];
@@ -235,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll 4
           for (int k = 0; k < 2 * H; ++k) a = fmaf(__ldg(w + (size_t)k * G1.ldo), in[k], a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
+          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + p.LDP_act + o] = g1[j * p.Hp + o];        // unit 0: g1
         }
         __syncthreads();
         for (int i = tid; i < nj * Z; i += kThreads) {
@@ -245,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll 4
           for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * G2.ldo), in[k], a);
           gv[j * Z + o] = lrelu(a, p.slope);                       // no residual in the stem, :378-380
+          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + p.LDP_act + p.Hp_act + o] = gv[j * Z + o]; // unit 0: g
         }
         __syncthreads();
       }
@@ -259,10 +226,16 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           for (int r = r0; r < r1; ++r) s += hs[(size_t)r * LDH + o];
           pool[j * LDP + o] = s / (float)(r1 - r0);                // (mean, sum, global) order, :164-171
           pool[j * LDP + H + o] = s * p.sum_scale;
+          if (TRAIN) {                                                                                // unit l+1: pool input
+            float* ja = p.jact + (size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit;
+            ja[o] = pool[j * LDP + o];
+            ja[H + o] = pool[j * LDP + H + o];
+          }
         }
         for (int i = tid; i < nj * Z; i += kThreads) {
           const int j = i / Z, o = i - j * Z;
           pool[j * LDP + 2 * H + o] = gv[j * Z + o];
+          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + 2 * H + o] = gv[j * Z + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * H; i += kThreads) {            // fc_global1, :180-182
@@ -274,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll 4
           for (int k = 0; k < K; ++k) a = fmaf(__ldg(w + (size_t)k * Ga.ldo), in[k], a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
+          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + o] = g1[j * p.Hp + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * Z; i += kThreads) {            // fc_global2 + residual, :184-186
@@ -286,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           // the new global vector is written to the pool row first (gv is still being read as the residual
           // by other threads only through gv[j*Z+o] of the SAME (j,o) -> safe in place)
           gv[j * Z + o] = lrelu(a + gv[j * Z + o], p.slope);
+          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + p.Hp_act + o] = gv[j * Z + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * H; i += kThreads) {            // per-jet bias of fc_local1 / fc_local2
@@ -310,7 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 #pragma unroll
               for (int i = 0; i < TC; ++i) {
                 const int o = lane + 32 * i;
-                if (o < H) tmp[(warp * RB + r) * LDH + o] = lrelu(acc[r][i] + bj[o], p.slope);
+                if (o < H) {
+                  const float uv = lrelu(acc[r][i] + bj[o], p.slope);
+                  tmp[(warp * RB + r) * LDH + o] = uv;
+                  if (TRAIN) p.act[(size_t)(2 + 2 * l) * p.act_stage_stride + (size_t)(row_g0 + row) * p.Hp_act + o] = uv;
+                }
               }
             }
           }
@@ -327,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
                 if (o < H) {
                   float* hp = hs + (size_t)row * LDH + o;
                   *hp = lrelu(acc[r][i] + bj[o] + *hp, p.slope);
+                  if (TRAIN) p.act[(size_t)(3 + 2 * l) * p.act_stage_stride + (size_t)(row_g0 + row) * p.Hp_act + o] = *hp;
                 }
               }
             }
@@ -369,6 +349,26 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
         __syncthreads();
       }
     }
+    if (TRAIN && p.loss_kind < 0) {
+      // plain forward with saved activations: park leaky_relu'(pre3) (sign(v) == sign(pre3)); the backward
+      // entry point multiplies it with the incoming gradient
+      for (int i = tid; i < R * F; i += kThreads) p.dpre3[(size_t)row_g0 * F + i] = vbuf[i] > 0.f ? 1.f : p.slope;
+    }
+    if (TRAIN && p.loss_kind >= 0) {
+      // masked squared error sum((v - u)^2) (losses.py:75-76) and the gradient seed at the head pre-activation:
+      // d loss / d pre3 = 2 (v - u) / sum(mask) * leaky_relu'(pre3)   (sign(v) == sign(pre3))
+      const float inv_n = 1.f / (float)(*p.n_total);
+      float part = 0.f;
+      for (int i = tid; i < R * F; i += kThreads) {
+        const float v = vbuf[i], d = v - x0[i];
+        part += d * d;
+        p.dpre3[(size_t)row_g0 * F + i] = 2.f * d * inv_n * (v > 0.f ? 1.f : p.slope);
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sft);
+      if (lane == 0) atomicAdd(p.loss_acc, part);
+      continue;
+    }
     // ---------------- write back: real particles from the resident buffers, padding = 0 ----------------
     {
       const float* src = p.solver >= 0 ? x0 : vbuf;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 // ---------------------------------------------------------------------------------------------
 struct SimtShape { int TC, RB, KC, R_cap, J_cap; SimtParams p; size_t smem; };
 
-static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s) {
+static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_force = 0, int J_cap_force = 0) {
   const pfm_epic_cfg& c = h->cfg;
   const int H = c.hid, Z = c.latent, F = c.feats;
   if (H > 320) { set_error("fp32 path supports hid <= 320 (got %d)", H); return PFM_ERR_UNSUPPORTED; }
@@ -432,6 +432,10 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s) {
     return PFM_ERR_UNSUPPORTED;
   }
   if (R_cap > 1024) R_cap = 1024;
+  if (R_cap_force > 0) {          // training: forward and backward kernels share one plan
+    if (R_cap_force > R_cap || J_cap_force > J_cap) { set_error("internal: forced group capacity exceeds the forward plan"); return PFM_ERR_INVALID; }
+    R_cap = R_cap_force; J_cap = J_cap_force;
+  }
   s->R_cap = R_cap; s->J_cap = J_cap;
   SimtParams& p = s->p;
   memset(&p, 0, sizeof(p));
@@ -472,9 +476,9 @@ int simt_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap) {
   return PFM_OK;
 }
 
-template <int TC, int RB>
+template <int TC, int RB, bool TRAIN>
 static int launch_simt(const pfm_epic* h, const SimtShape& s, int grid, cudaStream_t st) {
-  auto kern = epic_simt_kernel<TC, RB>;
+  auto kern = epic_simt_kernel<TC, RB, TRAIN>;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
   kern<<<grid, kThreads, s.smem, st>>>(s.p);
   PFM_CUDA_CHECK(cudaGetLastError());
@@ -496,9 +500,43 @@ int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   // persistent CTAs: one per SM, but never more than there can be groups (every group has >= 1 jet)
   int grid = h->sm_count < a.B ? h->sm_count : a.B;
-  if (s.TC == 4) return launch_simt<4, 8>(h, s, grid, st);
-  if (s.TC == 5) return launch_simt<5, 8>(h, s, grid, st);
-  return launch_simt<10, 4>(h, s, grid, st);
+  if (s.TC == 4) return launch_simt<4, 8, false>(h, s, grid, st);
+  if (s.TC == 5) return launch_simt<5, 8, false>(h, s, grid, st);
+  return launch_simt<10, 4, false>(h, s, grid, st);
+}
+
+// training forward: same kernel with the interpolation prologue (loss_kind >= 0), the activation saves and the
+// loss / gradient-seed epilogue
+int simt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
+  SimtShape s;
+  int rc = simt_shape(h, a.N, a.Kx, &s, a.lay.R_cap, a.lay.J_cap);
+  if (rc != PFM_OK) return rc;
+  SimtParams& p = s.p;
+  p.Kx = a.Kx; p.Kxp = (p.Kx + 3) & ~3; p.x_ld = p.Kx; p.xin_off = a.xin_off;
+  p.lin = h->lin_dev;
+  p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride; p.tbias_per_jet = a.tbias_per_jet;
+  p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
+  p.counter = h->plan.counter;
+  p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
+  p.n_evals = 1; p.solver = -1; p.n_steps = 0; p.dt = nullptr;
+  p.x1 = a.x_in; p.tjet = a.t; p.noise0 = a.noise0; p.noise1 = a.noise1; p.loss_kind = a.loss_kind; p.sigma = a.sigma;
+  p.act = h->act; p.act_stage_stride = a.lay.stage_stride; p.Hp_act = a.lay.Hp;
+  p.yact = h->yact;
+  p.jact = h->jact; p.junit = a.lay.junit; p.jstride = a.lay.jstride; p.LDP_act = a.lay.LDP;
+  p.dpre3 = h->dpre3; p.loss_acc = h->loss_acc; p.rowoff = h->plan.rowoff; p.n_total = h->plan.n_total;
+  int grid = h->sm_count < a.B ? h->sm_count : a.B;
+  if (s.TC == 4) return launch_simt<4, 8, true>(h, s, grid, st);
+  if (s.TC == 5) return launch_simt<5, 8, true>(h, s, grid, st);
+  return launch_simt<10, 4, true>(h, s, grid, st);
+}
+
+// group capacity of the forward kernel (the training plan takes the minimum with the backward kernel's)
+int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC) {
+  SimtShape s;
+  int rc = simt_shape(h, N, 0, &s);
+  if (rc != PFM_OK) return rc;
+  *R_cap = s.R_cap; *J_cap = s.J_cap; *TC = s.TC; *RB = s.RB; *KC = s.KC;
+  return PFM_OK;
 }
 
 }  // namespace pfm

@@ -88,14 +88,17 @@ __global__ void plan_count_kernel(const float* __restrict__ mask, int B, int N, 
 }
 
 __global__ void plan_group_kernel(const int* __restrict__ n_real, int B, int R_cap, int J_cap,
-                                  int2* __restrict__ groups, int* __restrict__ n_groups, int* __restrict__ counter) {
+                                  int2* __restrict__ groups, int* __restrict__ n_groups, int* __restrict__ counter,
+                                  int* __restrict__ rowoff, int* __restrict__ n_total) {
   extern __shared__ int s_n[];
   for (int i = threadIdx.x; i < B; i += blockDim.x) s_n[i] = n_real[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    int g = 0, first = 0, rows = 0, cnt = 0;
+    int g = 0, first = 0, rows = 0, cnt = 0, total = 0;
     for (int j = 0; j < B; ++j) {
       int n = s_n[j];
+      rowoff[j] = total;
+      total += n;
       if (cnt > 0 && (rows + n > R_cap || cnt >= J_cap)) {
         groups[g++] = make_int2(first, cnt);
         first = j; rows = 0; cnt = 0;
@@ -105,7 +108,16 @@ __global__ void plan_group_kernel(const int* __restrict__ n_real, int B, int R_c
     if (cnt > 0) groups[g++] = make_int2(first, cnt);
     *n_groups = g;
     *counter = 0;
+    *n_total = total;
   }
+}
+
+__global__ void rowmajor_main_kernel(const float* __restrict__ W, float* __restrict__ Wr, int out, int in, int m_off,
+                                     int m_len, int ldr) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= out * ldr) return;
+  int o = idx / ldr, k = idx - o * ldr;
+  Wr[idx] = k < m_len ? W[(size_t)o * in + m_off + k] : 0.f;
 }
 
 static int ensure_plan(pfm_epic* h, int B, int N) {
@@ -113,8 +125,10 @@ static int ensure_plan(pfm_epic* h, int B, int N) {
   if (B > p.capB) {
     if (p.n_real) cudaFree(p.n_real);
     if (p.groups) cudaFree(p.groups);
+    if (p.rowoff) cudaFree(p.rowoff);
     PFM_CUDA_CHECK(cudaMalloc(&p.n_real, sizeof(int) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.groups, sizeof(int2) * B));
+    PFM_CUDA_CHECK(cudaMalloc(&p.rowoff, sizeof(int) * B));
     p.capB = B;
   }
   if ((long long)B * N > p.capBN) {
@@ -125,6 +139,7 @@ static int ensure_plan(pfm_epic* h, int B, int N) {
   if (!p.n_groups) {
     PFM_CUDA_CHECK(cudaMalloc(&p.n_groups, sizeof(int)));
     PFM_CUDA_CHECK(cudaMalloc(&p.counter, sizeof(int)));
+    PFM_CUDA_CHECK(cudaMalloc(&p.n_total, sizeof(int)));
   }
   return PFM_OK;
 }
@@ -194,7 +209,8 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
     const float* mk = mask ? mask + (size_t)b0 * N : nullptr;
     plan_count_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mk, nb, N, h->plan.n_real, h->plan.ridx);
     plan_group_kernel<<<1, 1024, sizeof(int) * nb, st>>>(h->plan.n_real, nb, R_cap, J_cap, h->plan.groups,
-                                                         h->plan.n_groups, h->plan.counter);
+                                                         h->plan.n_groups, h->plan.counter, h->plan.rowoff,
+                                                         h->plan.n_total);
     h->last_launches += 2;
     PFM_CUDA_CHECK(cudaGetLastError());
     RunArgs a;
@@ -226,6 +242,110 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
     h->last_launches++;
   }
   PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training: forward with saved activations (+ fused flow-matching loss), backward, weight gradients
+// ---------------------------------------------------------------------------------------------
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, const int* __restrict__ n_total, float* __restrict__ loss) {
+  *loss = *acc / (float)(*n_total);          // sum((v-u)^2) / sum(mask)   (losses.py:76,130,341)
+}
+
+// dpre3[row][f] (holds leaky_relu'(pre3)) *= grad_out[jet][particle][f]; one warp per jet
+__global__ void seed_kernel(float* __restrict__ dpre3, const float* __restrict__ grad_out, const int* __restrict__ n_real,
+                            const uint16_t* __restrict__ ridx, const int* __restrict__ rowoff, int B, int N, int F) {
+  const int jet = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (jet >= B) return;
+  const int n = n_real[jet], r0 = rowoff[jet];
+  for (int i = lane; i < n * F; i += 32) {
+    const int r = i / F, f = i - r * F;
+    const int part = ridx[(size_t)jet * N + r];
+    dpre3[(size_t)(r0 + r) * F + f] *= grad_out[((size_t)jet * N + part) * F + f];
+  }
+}
+
+// grad_x[jet][particle][:] = dxs[row][:] for real particles, 0 for padding
+__global__ void scatter_dx_kernel(const float* __restrict__ dxs, float* __restrict__ grad_x, const int* __restrict__ n_real,
+                                  const uint16_t* __restrict__ ridx, const int* __restrict__ rowoff, int B, int N, int Kx) {
+  const int jet = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (jet >= B) return;
+  const int n = n_real[jet], r0 = rowoff[jet];
+  float* dst = grad_x + (size_t)jet * N * Kx;
+  for (int i = lane; i < N * Kx; i += 32) dst[i] = 0.f;
+  __syncwarp();
+  for (int i = lane; i < n * Kx; i += 32) {
+    const int r = i / Kx, c = i - r * Kx;
+    dst[(size_t)ridx[(size_t)jet * N + r] * Kx + c] = dxs[(size_t)(r0 + r) * Kx + c];
+  }
+}
+
+static size_t grad_floats(const pfm_epic* h) {
+  size_t n = 0;
+  for (const Lin& L : h->lin_host) n += (size_t)L.out * L.in + L.out;
+  return n;
+}
+
+// forward half shared by pfm_epic_loss_fwd_bwd and pfm_epic_forward_train
+static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, const float* t_code_in, int t_in,
+                                const float* x, float* out, const float* t_jet, const float* noise0, const float* noise1,
+                                int loss_kind, float sigma, const float* mask, const float* cond, int B, int N, int Kx,
+                                int xin_off, TrainLayout* lay, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  if (!h->weights_set) { set_error("weights not set (call pfm_epic_set_weights first)"); return PFM_ERR_STATE; }
+  if (B <= 0 || N <= 0 || N > 65535) { set_error("bad batch shape B=%d N=%d", B, N); return PFM_ERR_INVALID; }
+  if (B > kMaxJetsPerCall) { set_error("training batch of %d jets exceeds %d per call", B, kMaxJetsPerCall); return PFM_ERR_INVALID; }
+  const int cond_dim = c.global_cond_dim > c.local_cond_dim ? c.global_cond_dim : c.local_cond_dim;
+  if (cond_dim > 0 && cond == nullptr) { set_error("cond is NULL but the net is conditioned"); return PFM_ERR_INVALID; }
+  const bool any_t = (c.t_local_cat || c.t_global_cat) && c.t_dim > 0;
+  if ((any_t && !t_code) || (t_in > 0 && !t_code_in)) { set_error("time code is NULL but the net takes a time code"); return PFM_ERR_INVALID; }
+  PFM_CUDA_CHECK(cudaSetDevice(h->device));
+  h->last_launches = 0; h->ev_used = 0; h->train_B = 0;
+  int rc = train_layout(h, B, N, lay);
+  if (rc != PFM_OK) return rc;
+  const bool per_jet = t_rows == B && B > 1;
+  const int trows = per_jet ? B : 1;
+  rc = ensure_floats(&h->tbias, &h->tbias_cap, (size_t)trows * h->bstride);
+  if (rc != PFM_OK) return rc;
+  tbias_kernel<<<dim3(trows, h->n_lin), 128, 0, st>>>(h->lin_dev, t_code, c.t_dim, t_code_in, t_in, h->tbias, h->bstride);
+  h->last_launches++;
+  if (cond_dim > 0) {
+    rc = ensure_floats(&h->cbias, &h->cbias_cap, (size_t)B * h->bstride);
+    if (rc != PFM_OK) return rc;
+    cbias_kernel<<<dim3(B, h->n_lin), 128, 0, st>>>(h->lin_dev, cond, cond_dim, h->cbias, h->bstride);
+    h->last_launches++;
+  }
+  rc = ensure_plan(h, B, N);
+  if (rc != PFM_OK) return rc;
+  plan_count_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, B, N, h->plan.n_real, h->plan.ridx);
+  plan_group_kernel<<<1, 1024, sizeof(int) * B, st>>>(h->plan.n_real, B, lay->R_cap, lay->J_cap, h->plan.groups, h->plan.n_groups,
+                                                     h->plan.counter, h->plan.rowoff, h->plan.n_total);
+  h->last_launches += 2;
+  PFM_CUDA_CHECK(cudaGetLastError());
+  const size_t rows = (size_t)B * N;
+  const size_t stages = 2 + 2 * (size_t)c.layers;
+  if ((rc = ensure_floats(&h->act, &h->act_cap, stages * lay->stage_stride)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->dact, &h->dact_cap, stages * lay->stage_stride)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->yact, &h->yact_cap, rows * Kx)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->jact, &h->jact_cap, (size_t)B * lay->jstride)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->dpre3, &h->dpre3_cap, rows * c.feats)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->dbeff, &h->dbeff_cap, (size_t)B * h->bstride)) != PFM_OK) return rc;
+  if ((rc = ensure_floats(&h->dxs, &h->dxs_cap, rows * Kx)) != PFM_OK) return rc;
+  if (!h->loss_acc) {
+    PFM_CUDA_CHECK(cudaMalloc(&h->loss_acc, sizeof(float)));
+    PFM_CUDA_CHECK(cudaMalloc(&h->ones, sizeof(float)));
+    const float one = 1.f;
+    PFM_CUDA_CHECK(cudaMemcpy(h->ones, &one, sizeof(float), cudaMemcpyHostToDevice));
+  }
+  PFM_CUDA_CHECK(cudaMemsetAsync(h->loss_acc, 0, sizeof(float), st));
+  TrainFwdArgs a;
+  a.x_in = x; a.x_out = out; a.t = t_jet; a.noise0 = noise0; a.noise1 = noise1; a.loss_kind = loss_kind; a.sigma = sigma;
+  a.B = B; a.N = N; a.Kx = Kx; a.xin_off = xin_off; a.has_cbias = cond_dim > 0; a.tbias_per_jet = per_jet ? 1 : 0;
+  a.lay = *lay;
+  rc = simt_train_forward(h, a, st);
+  if (rc != PFM_OK) return rc;
+  h->last_launches++;
+  h->train_B = B; h->train_N = N; h->train_Kx = Kx; h->train_xin_off = xin_off;
   return PFM_OK;
 }
 
@@ -300,6 +420,11 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->precision = PFM_PREC_FP32;
   h->weights_set = false;
   h->lin_dev = nullptr; h->wt_store = nullptr; h->b_store = nullptr; h->tc_store = nullptr; h->tc_bytes = 0;
+  h->wr_store = nullptr; h->wr_floats = 0;
+  h->act = nullptr; h->act_cap = 0; h->dact = nullptr; h->dact_cap = 0; h->yact = nullptr; h->yact_cap = 0;
+  h->jact = nullptr; h->jact_cap = 0; h->dpre3 = nullptr; h->dpre3_cap = 0;
+  h->dbeff = nullptr; h->dbeff_cap = 0; h->dxs = nullptr; h->dxs_cap = 0; h->loss_acc = nullptr; h->ones = nullptr;
+  h->jobs_dev = nullptr; h->jobs_cap = 0; h->train_B = 0; h->train_N = 0; h->train_Kx = 0; h->train_xin_off = 0;
   h->tbias = nullptr; h->tbias_cap = 0; h->cbias = nullptr; h->cbias_cap = 0;
   memset(&h->plan, 0, sizeof(h->plan));
   h->last_launches = 0; h->last_groups_host = 0;
@@ -307,7 +432,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   h->lin_host.resize(h->n_lin);
-  size_t wt = 0, bf = 0;
+  size_t wt = 0, bf = 0, wr = 0;
   int boff = 0;
   for (int i = 0; i < h->n_lin; ++i) {
     Lin& L = h->lin_host[i];
@@ -316,27 +441,34 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
     boff += L.ldo;
     wt += (size_t)(L.in + 8) * L.ldo;   // +8 slack rows: kernels may read (never use) up to 3 rows past a block
     bf += L.ldo;
+    L.ldr = round_up(L.m_len, 4);
+    wr += (size_t)(L.out + 8) * L.ldr;
   }
+  h->wr_floats = wr + 1024;
   h->bstride = boff;
   h->wt_floats = wt + 1024;
   h->b_floats = bf;
   cudaError_t e1 = cudaMalloc(&h->wt_store, sizeof(float) * h->wt_floats);
   cudaError_t e2 = cudaMalloc(&h->b_store, sizeof(float) * h->b_floats);
   cudaError_t e3 = cudaMalloc(&h->lin_dev, sizeof(Lin) * h->n_lin);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+  cudaError_t e4 = cudaMalloc(&h->wr_store, sizeof(float) * h->wr_floats);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
     set_error("cudaMalloc failed for packed weights");
     pfm_epic_destroy(h);
     return PFM_ERR_CUDA;
   }
   cudaMemset(h->wt_store, 0, sizeof(float) * h->wt_floats);
   cudaMemset(h->b_store, 0, sizeof(float) * h->b_floats);
-  size_t wo = 0, bo = 0;
+  cudaMemset(h->wr_store, 0, sizeof(float) * h->wr_floats);
+  size_t wo = 0, bo = 0, ro = 0;
   for (int i = 0; i < h->n_lin; ++i) {
     Lin& L = h->lin_host[i];
     L.Wt = h->wt_store + wo;
     L.b = h->b_store + bo;
+    L.Wr = h->wr_store + ro;
     wo += (size_t)(L.in + 8) * L.ldo;
     bo += L.ldo;
+    ro += (size_t)(L.out + 8) * L.ldr;
   }
   cudaMemcpy(h->lin_dev, h->lin_host.data(), sizeof(Lin) * h->n_lin, cudaMemcpyHostToDevice);
   *out = h;
@@ -350,6 +482,17 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->wt_store) cudaFree(h->wt_store);
   if (h->b_store) cudaFree(h->b_store);
   if (h->tc_store) cudaFree(h->tc_store);
+  if (h->wr_store) cudaFree(h->wr_store);
+  if (h->act) cudaFree(h->act);
+  if (h->dact) cudaFree(h->dact);
+  if (h->yact) cudaFree(h->yact);
+  if (h->dxs) cudaFree(h->dxs);
+  if (h->ones) cudaFree(h->ones);
+  if (h->jobs_dev) cudaFree(h->jobs_dev);
+  if (h->jact) cudaFree(h->jact);
+  if (h->dpre3) cudaFree(h->dpre3);
+  if (h->dbeff) cudaFree(h->dbeff);
+  if (h->loss_acc) cudaFree(h->loss_acc);
   if (h->tbias) cudaFree(h->tbias);
   if (h->cbias) cudaFree(h->cbias);
   if (h->plan.n_real) cudaFree(h->plan.n_real);
@@ -357,6 +500,8 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->plan.groups) cudaFree(h->plan.groups);
   if (h->plan.n_groups) cudaFree(h->plan.n_groups);
   if (h->plan.counter) cudaFree(h->plan.counter);
+  if (h->plan.rowoff) cudaFree(h->plan.rowoff);
+  if (h->plan.n_total) cudaFree(h->plan.n_total);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -382,6 +527,8 @@ int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* 
     int total = L.in * L.ldo;
     transpose_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(weights[i], const_cast<float*>(L.Wt), L.out, L.in,
                                                                  L.ldo);
+    rowmajor_main_kernel<<<(L.out * L.ldr + 255) / 256, 256, 0, st>>>(weights[i], const_cast<float*>(L.Wr), L.out, L.in,
+                                                                      L.m_off, L.m_len, L.ldr);
     PFM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(L.b), biases[i], sizeof(float) * L.out,
                                    cudaMemcpyDeviceToDevice, st));
   }
@@ -459,6 +606,78 @@ float pfm_epic_last_kernel_ms(pfm_epic* h) {
     total += ms;
   }
   return total;
+}
+
+long long pfm_epic_grad_size(const pfm_epic* h) { return h ? (long long)grad_floats(h) : (long long)PFM_ERR_INVALID; }
+
+int pfm_epic_loss_fwd_bwd(pfm_epic* h, const float* x1, const float* t, const float* t_code, const float* t_code_in,
+                          const float* noise0, const float* noise1, const float* mask, const float* cond, int loss_kind,
+                          float sigma, float* loss_out, float* grad_flat, int B, int N, void* stream) {
+  if (!h || !x1 || !t || !noise0 || !loss_out) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (loss_kind != PFM_LOSS_FM_OT && loss_kind != PFM_LOSS_CFM && loss_kind != PFM_LOSS_DROID) {
+    set_error("unknown loss kind %d", loss_kind); return PFM_ERR_INVALID;
+  }
+  if (loss_kind == PFM_LOSS_CFM && !noise1) { set_error("the CFM loss needs noise1"); return PFM_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const pfm_epic_cfg& c = h->cfg;
+  const int t_in = c.input_dim - c.feats;
+  if (t_in < 0) { set_error("input_dim < feats"); return PFM_ERR_INVALID; }
+  TrainLayout lay;
+  int rc = train_forward_common(h, t_code, B, t_code_in, t_in, x1, nullptr, t, noise0, noise1, loss_kind, sigma, mask, cond, B, N,
+                                c.feats, t_in, &lay, st);
+  if (rc != PFM_OK) return rc;
+  loss_finalize_kernel<<<1, 1, 0, st>>>(h->loss_acc, h->plan.n_total, loss_out);
+  h->last_launches++;
+  if (!grad_flat) return PFM_OK;
+  PFM_CUDA_CHECK(cudaMemsetAsync(grad_flat, 0, sizeof(float) * grad_floats(h), st));
+  TrainBwdArgs b;
+  b.B = B; b.N = N; b.Kx = c.feats; b.xin_off = t_in;
+  b.t_code = t_code; b.t_ld = (B > 1) ? c.t_dim : 0; b.t_code_in = t_code_in; b.t_in = t_in;
+  b.cond = cond; b.cond_dim = c.global_cond_dim > c.local_cond_dim ? c.global_cond_dim : c.local_cond_dim;
+  b.grad_flat = grad_flat; b.want_dx = false; b.lay = lay;
+  return train_backward(h, b, st);
+}
+
+int pfm_epic_forward_train(pfm_epic* h, const float* t_code, int t_rows, const float* x, const float* mask,
+                           const float* cond, float* out, int B, int N, void* stream) {
+  if (!h || !x || !out) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (t_rows != 1 && t_rows != B) { set_error("t_rows must be 1 or B (got %d, B=%d)", t_rows, B); return PFM_ERR_INVALID; }
+  TrainLayout lay;
+  return train_forward_common(h, t_code, t_rows, nullptr, 0, x, out, nullptr, nullptr, nullptr, -1, 0.f, mask, cond, B, N,
+                              h->cfg.input_dim, 0, &lay, (cudaStream_t)stream);
+}
+
+int pfm_epic_backward(pfm_epic* h, const float* t_code, int t_rows, const float* cond, const float* grad_out, float* grad_x,
+                      float* grad_flat, int B, int N, void* stream) {
+  if (!h || !grad_out) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (h->train_B != B || h->train_N != N || h->train_Kx != h->cfg.input_dim) {
+    set_error("pfm_epic_backward: no matching pfm_epic_forward_train (saved B=%d N=%d, asked B=%d N=%d)", h->train_B,
+              h->train_N, B, N);
+    return PFM_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const pfm_epic_cfg& c = h->cfg;
+  PFM_CUDA_CHECK(cudaSetDevice(h->device));
+  TrainLayout lay;
+  int rc = train_layout(h, B, N, &lay);
+  if (rc != PFM_OK) return rc;
+  seed_kernel<<<(B + 7) / 8, 256, 0, st>>>(h->dpre3, grad_out, h->plan.n_real, h->plan.ridx, h->plan.rowoff, B, N, c.feats);
+  h->last_launches++;
+  if (grad_flat) PFM_CUDA_CHECK(cudaMemsetAsync(grad_flat, 0, sizeof(float) * grad_floats(h), st));
+  TrainBwdArgs b;
+  b.B = B; b.N = N; b.Kx = c.input_dim; b.xin_off = 0;
+  b.t_code = t_code; b.t_ld = (t_rows == B && B > 1) ? c.t_dim : 0; b.t_code_in = nullptr; b.t_in = 0;
+  b.cond = cond; b.cond_dim = c.global_cond_dim > c.local_cond_dim ? c.global_cond_dim : c.local_cond_dim;
+  b.grad_flat = grad_flat; b.want_dx = grad_x != nullptr; b.lay = lay;
+  rc = train_backward(h, b, st);
+  if (rc != PFM_OK) return rc;
+  if (grad_x) {
+    scatter_dx_kernel<<<(B + 7) / 8, 256, 0, st>>>(h->dxs, grad_x, h->plan.n_real, h->plan.ridx, h->plan.rowoff, B, N, c.input_dim);
+    h->last_launches++;
+  }
+  h->train_B = 0;            // the saved dpre3 has been consumed
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
 }
 
 }  // extern "C"

@@ -22,6 +22,8 @@ struct Lin {
   int ldo;            // leading dimension of the k-major (transposed) fp32 copy, round_up(out, 4)
   const float* Wt;    // k-major fp32 copy  Wt[k*ldo + o] = W[o][k],  k in [0, in)  (+ slack rows)
   const float* b;     // [out]
+  const float* Wr;    // row-major copy of the main block  Wr[o*ldr + k] = W[o][m_off + k]  (backward: dX = dY . W)
+  int ldr;            // round_up(m_len, 4)
 };
 
 enum LinIdx { LIN_L1 = 0, LIN_L2 = 1, LIN_G1 = 2, LIN_G2 = 3, LIN_LAYER0 = 4 };
@@ -33,6 +35,8 @@ struct Plan {          // device buffers describing how jets are packed into CTA
   int2* groups;        // [B]     (first jet, number of jets) of every group
   int* n_groups;       // [1]
   int* counter;        // [1]     dynamic work counter for persistent CTAs
+  int* rowoff;         // [B]     first packed row of every jet (exclusive prefix sum of n_real)
+  int* n_total;        // [1]     total number of real particles (= sum(mask), the loss denominator)
   int capB, capBN;
 };
 
@@ -50,7 +54,8 @@ struct pfm_epic {
   pfm::Lin* lin_dev;                // device copy of the descriptors
   float* wt_store;                  // all k-major fp32 copies
   float* b_store;                   // all biases
-  size_t wt_floats, b_floats;
+  float* wr_store;                  // row-major main blocks (training backward)
+  size_t wt_floats, b_floats, wr_floats;
   int bstride;                      // floats per bias-table row
   // bf16 tensor-core path: pre-swizzled shared-memory images of the H x H per-particle weights
   void* tc_store;
@@ -60,6 +65,18 @@ struct pfm_epic {
   float* cbias; size_t cbias_cap;   // [B, bstride]     W_c . cond
   pfm::Plan plan;
   int last_launches, last_groups_host;
+  // training workspaces (grown on demand; see epic_train.cu for the layouts)
+  float* act; size_t act_cap;       // saved per-particle activations      [(2+2L) stages, rows, Hp]
+  float* dact; size_t dact_cap;     // per-particle pre-activation grads   [(2+2L) stages, rows, Hp]
+  float* yact; size_t yact_cap;     // per-particle network input          [rows, Kx]
+  float* jact; size_t jact_cap;     // saved per-jet vectors               [B, L+1 units, LDP + Hp + Zp]
+  float* dpre3; size_t dpre3_cap;   // gradient at the head pre-activation [rows, F]
+  float* dbeff; size_t dbeff_cap;   // gradient of the per-jet effective biases [B, bstride]
+  float* dxs; size_t dxs_cap;       // gradient w.r.t. the per-particle input   [rows, Kx]
+  float* loss_acc;                  // [1] sum of squared errors
+  float* ones;                      // [1] = 1.0f (the "input" of a bias in the weight-gradient jobs)
+  void* jobs_dev; size_t jobs_cap;  // device copy of the weight-gradient job table
+  int train_B, train_N, train_Kx, train_xin_off;   // shape of the saved forward (0 = none)
   bool timing;
   std::vector<cudaEvent_t> ev_pool;   // start/stop pairs of the main kernel, one pair per chunk of a call
   int ev_used;
@@ -94,6 +111,34 @@ struct RunArgs {
 // fp32 CUDA-core path (epic_simt.cu)
 int simt_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap);
 int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st);
+// training, fp32 CUDA cores (forward with saved activations: epic_simt.cu; backward: epic_train.cu)
+struct TrainLayout {       // strides of the saved-activation arrays, shared by forward and backward
+  size_t stage_stride;     // floats between two stages of act / dact  (= rows_cap * Hp)
+  int Hp;                  // row stride of act / dact
+  int LDP, Zp;             // per-jet unit = [pool input (LDP) | g1 (Hp) | g (Zp)]
+  int junit, jstride;      // floats per unit / per jet
+  int R_cap, J_cap;        // group capacity both kernels are planned for
+};
+int train_layout(const pfm_epic* h, int B, int N, TrainLayout* lay);
+struct TrainFwdArgs {
+  const float* x_in;       // loss_kind < 0: network input [B,N,Kx];  else the data x1 [B,N,F]
+  float* x_out;            // loss_kind < 0: network output [B,N,F]
+  const float* t; const float* noise0; const float* noise1; int loss_kind; float sigma;
+  int B, N, Kx, xin_off; bool has_cbias; int tbias_per_jet;
+  TrainLayout lay;
+};
+int simt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st);
+struct TrainBwdArgs {
+  int B, N, Kx, xin_off;
+  const float* t_code; int t_ld;        // [B or 1, t_dim]; t_ld = 0 when one row serves every jet
+  const float* t_code_in; int t_in;     // hoisted add_time_to_input columns (loss path) or NULL
+  const float* cond; int cond_dim;
+  float* grad_flat;                     // [sum_i out_i*in_i + out_i]  (W_0 | b_0 | W_1 | b_1 ...)
+  bool want_dx;
+  TrainLayout lay;
+};
+int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st);
+int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);
 // bf16 tcgen05 path (epic_tc.cu)
 int tc_supported(const pfm_epic* h, int N);
 int tc_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap);

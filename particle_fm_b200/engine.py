@@ -160,6 +160,87 @@ class EpicEngine:
                        "pfm_epic_sample")
         return x
 
+    # -- training --------------------------------------------------------------------------------
+    def grad_size(self) -> int:
+        return int(self.lib.pfm_epic_grad_size(self._h))
+
+    def grad_views(self, flat: Tensor):
+        """Per-linear (dW [out,in], db [out]) views of the flat gradient buffer (layout of pfm_b200.h)."""
+        views, off = [], 0
+        for o, i in self.linear_shapes():
+            views.append((flat[off:off + o * i].view(o, i), flat[off + o * i:off + o * i + o]))
+            off += o * i + o
+        return views
+
+    def loss_fwd_bwd(self, kind: str, x: Tensor, mask: Optional[Tensor], cond: Optional[Tensor], t: Tensor,
+                     t_code: Optional[Tensor], t_code_in: Optional[Tensor], n0: Tensor, n1: Optional[Tensor],
+                     sigma: float, want_grad: bool = True):
+        """Fused flow-matching loss (+ backward).  Returns (loss [1] on the device, flat gradient or None)."""
+        d = self.dims
+        B, N = int(x.shape[0]), int(x.shape[1])
+        code = {"FM-OT": _lib.PFM_LOSS_FM_OT, "CFM": _lib.PFM_LOSS_CFM, "droid": _lib.PFM_LOSS_DROID}[kind]
+        x = _f32c(x, self.device)
+        if x.shape[2] != d.feats:
+            raise ValueError(f"x has {x.shape[2]} features, the net expects {d.feats}")
+        mask = None if mask is None else _f32c(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        t = _f32c(t, self.device).reshape(B)
+        n0 = _f32c(n0, self.device)
+        n1 = None if n1 is None else _f32c(n1, self.device)
+        t_code = _f32c(t_code, self.device).reshape(B, d.t_dim) if (d.takes_time and t_code is not None) else None
+        if d.takes_time and t_code is None:
+            raise ValueError("the net takes a time code but none was given")
+        t_in = d.input_dim - d.feats
+        t_code_in = _f32c(t_code_in, self.device).reshape(B, t_in) if t_in > 0 else None
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        flat = torch.empty(self.grad_size(), device=self.device, dtype=torch.float32) if want_grad else None
+        self._ticket = getattr(self, "_ticket", 0) + 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_loss_fwd_bwd(self._h, _ptr(x), _ptr(t), _ptr(t_code), _ptr(t_code_in), _ptr(n0),
+                                                      _ptr(n1), _ptr(mask), _ptr(cond), code, float(sigma), _ptr(loss),
+                                                      _ptr(flat), B, N, self._stream()), "pfm_epic_loss_fwd_bwd")
+        return loss, flat
+
+    def forward_train(self, t_code: Optional[Tensor], x: Tensor, mask: Optional[Tensor], cond: Optional[Tensor]):
+        """forward() that keeps the activations for ONE later backward(); returns (out, ticket)."""
+        d = self.dims
+        B, N = int(x.shape[0]), int(x.shape[1])
+        x = _f32c(x, self.device)
+        if x.shape[2] != d.input_dim:
+            raise ValueError(f"x has {x.shape[2]} columns, the net expects input_dim={d.input_dim}")
+        mask = None if mask is None else _f32c(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        t_rows = 1
+        if d.takes_time:
+            if t_code is None:
+                raise ValueError("t_local_cat/t_global_cat is set but no time code was given (epic.py:317-321)")
+            t_code = _f32c(t_code, self.device).reshape(-1, d.t_dim)
+            t_rows = int(t_code.shape[0])
+            if t_rows not in (1, B):
+                raise ValueError(f"time code must have 1 or B={B} rows, got {t_rows}")
+        else:
+            t_code = None
+        out = torch.empty(B, N, d.feats, device=self.device, dtype=torch.float32)
+        self._ticket = getattr(self, "_ticket", 0) + 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_forward_train(self._h, _ptr(t_code), t_rows, _ptr(x), _ptr(mask), _ptr(cond),
+                                                       _ptr(out), B, N, self._stream()), "pfm_epic_forward_train")
+        return out, self._ticket, (t_code, t_rows, cond, B, N)
+
+    def backward(self, ticket: int, saved, grad_out: Tensor, want_gx: bool, want_gw: bool):
+        if ticket != getattr(self, "_ticket", 0):
+            raise RuntimeError("the saved activations of this forward were overwritten by a later training forward on "
+                               "the same network: libpfm_b200 keeps ONE in-flight forward per handle")
+        t_code, t_rows, cond, B, N = saved
+        d = self.dims
+        grad_out = _f32c(grad_out, self.device)
+        gx = torch.empty(B, N, d.input_dim, device=self.device, dtype=torch.float32) if want_gx else None
+        flat = torch.empty(self.grad_size(), device=self.device, dtype=torch.float32) if want_gw else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_backward(self._h, _ptr(t_code), t_rows, _ptr(cond), _ptr(grad_out), _ptr(gx),
+                                                  _ptr(flat), B, N, self._stream()), "pfm_epic_backward")
+        return gx, flat
+
     def _cond(self, cond: Optional[Tensor], B: int) -> Optional[Tensor]:
         d = self.dims
         if d.cond_dim == 0:

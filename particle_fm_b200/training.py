@@ -1,0 +1,102 @@
+"""Autograd glue of the fused training kernels.
+
+The reference obtains gradients from torch autograd over the eager network; here the
+whole loss forward + backward is libpfm_b200 (``pfm_epic_loss_fwd_bwd``), and a ``torch.autograd.Function``
+hands the result to autograd as the gradient of the FOLDED weights ``W = g*v/||v||`` -- the fold itself
+(``torch._weight_norm``) stays a differentiable torch op, so ``weight_g`` / ``weight_v`` / ``bias``
+receive their gradients, and optimizers, gradient clipping, DDP hooks and the EMA callback keep working.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def _folded_and_engine(net, device):
+    """Folded (W, b) of every linear WITH autograd history, and the engine holding the same values.
+    The training kernels are fp32 whatever precision the module uses for sampling."""
+    eng = net.engine(device, sync_weights=False)
+    folded = [lin.folded() for lin in net.linears()]
+    key = net._weights_key()
+    if eng.weights_key != key:
+        eng.set_weights([w.detach() for w, _ in folded], [b.detach() for _, b in folded], key=key)
+    flat: List[Tensor] = []
+    for w, b in folded:
+        flat += [w, b]
+    return eng, flat
+
+
+class _FMLossFn(torch.autograd.Function):
+    """loss = sum((net(t, y) - u)^2) / sum(mask), forward and backward in one fused call."""
+
+    @staticmethod
+    def forward(ctx, net, eng, kind, sigma, x, mask, cond, t, t_code, t_code_in, n0, n1, *wb):
+        want = any(ctx.needs_input_grad[12:])
+        loss, flat = eng.loss_fwd_bwd(kind, x, mask, cond, t, t_code, t_code_in, n0, n1, sigma, want_grad=want)
+        hook = getattr(net, "flat_grad_hook", None)
+        if want and hook is not None:
+            flat = hook(flat)                     # e.g. the data-parallel all-reduce of the flat gradient
+        ctx.eng, ctx.flat = eng, flat
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = [None] * 12
+        if ctx.flat is None:
+            return tuple(grads) + (None,) * (2 * ctx.eng.n_lin)
+        for (gw, gb), need_w, need_b in zip(ctx.eng.grad_views(ctx.flat), ctx.needs_input_grad[12::2],
+                                            ctx.needs_input_grad[13::2]):
+            grads.append(gw * g if need_w else None)
+            grads.append(gb * g if need_b else None)
+        return tuple(grads)
+
+
+def fm_loss_autograd(cnf, kind: str, x: Tensor, mask: Tensor, cond: Optional[Tensor], t: Tensor, n0: Tensor,
+                     n1: Optional[Tensor], sigma: float) -> Tensor:
+    """Scalar loss with an autograd graph to ``cnf.net``'s parameters (x: (B,N,F), t: (B,) per jet)."""
+    net = cnf.net
+    if x.device.type != "cuda":
+        raise RuntimeError(f"the flow-matching loss got a batch on {x.device}: the B200 path needs a CUDA device "
+                           "(no CPU fallback; use oracle/ for CPU reference numbers)")
+    eng, wb = _folded_and_engine(net, x.device)
+    takes = net.t_local_cat or net.t_global_cat
+    with torch.no_grad():
+        code = cnf.time_code(t.to(x.device)) if (takes or cnf.add_time_to_input) else None     # [B, 2*frequencies]
+    return _FMLossFn.apply(net, eng, kind, sigma, x, mask, cond, t, code if takes else None,
+                           code if cnf.add_time_to_input else None, n0, n1, *wb)
+
+
+class _EpicFn(torch.autograd.Function):
+    """Differentiable EPiC_encoder.forward: out = net(t_code, x); gradients w.r.t. x and the folded weights."""
+
+    @staticmethod
+    def forward(ctx, net, eng, t_code, x, mask, cond, *wb):
+        out, ticket, saved = eng.forward_train(t_code, x, mask, cond)
+        ctx.eng, ctx.ticket, ctx.saved = eng, ticket, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        want_gx = ctx.needs_input_grad[3]
+        want_gw = any(ctx.needs_input_grad[6:])
+        gx, flat = ctx.eng.backward(ctx.ticket, ctx.saved, gout, want_gx, want_gw)
+        grads = [None, None, None, gx, None, None]
+        if flat is None:
+            return tuple(grads) + (None,) * (2 * ctx.eng.n_lin)
+        for (gw, gb), need_w, need_b in zip(ctx.eng.grad_views(flat), ctx.needs_input_grad[6::2],
+                                            ctx.needs_input_grad[7::2]):
+            grads.append(gw if need_w else None)
+            grads.append(gb if need_b else None)
+        return tuple(grads)
+
+
+def epic_forward_autograd(net, t_code: Optional[Tensor], x_local: Tensor, cond: Optional[Tensor],
+                          mask: Optional[Tensor]) -> Tensor:
+    if x_local.device.type != "cuda":
+        raise RuntimeError(f"EPiC_encoder got an input on {x_local.device}: the B200 path needs a CUDA device "
+                           "(no CPU fallback)")
+    eng, wb = _folded_and_engine(net, x_local.device)
+    return _EpicFn.apply(net, eng, t_code, x_local, mask, cond, *wb)

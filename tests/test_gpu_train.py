@@ -1,0 +1,134 @@
+"""GPU: the fused training step (loss forward + backward through the C ABI) against torch autograd over the
+CPU oracle.  fp32 path: loss relative error <= 1e-5, every parameter gradient relative L2 <= 1e-4."""
+import pytest
+import torch
+
+from oracle import epic_oracle as eo
+from oracle import loss_oracle as lo
+
+from helpers import GOLDEN_CASES, Golden, build_module, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOSS_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    return lib_built
+
+
+def oracle_loss_and_grads(g, kind, x, mask, cond, t, n0, n1, sigma):
+    sd = {k: v.clone().requires_grad_(True) for k, v in g.sd.items()}
+    kw = g.oracle_kwargs()
+    vf = lambda tt, y: eo.cnf_forward(sd, g.cfg, tt, y, cond, mask, **kw)
+    loss = lo.fm_loss(vf, kind, x, mask, t, n0, n1, sigma)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in sd.items()}
+
+
+def module_grads(m):
+    return {k[len("flows.0.net."):]: p.grad.detach().cpu() for k, p in m.named_parameters() if k.startswith("flows.0.net.")}
+
+
+def run_fused(m, kind, x, mask, cond, t, n0, n1, sigma):
+    from particle_fm_b200.training import fm_loss_autograd
+    m.zero_grad(set_to_none=True)
+    c = None if cond is None else cond.to(DEV)
+    loss = fm_loss_autograd(m.flows[0], kind, x.to(DEV), mask.to(DEV), c, t.to(DEV), n0.to(DEV),
+                            None if n1 is None else n1.to(DEV), sigma)
+    loss.backward()
+    return loss.detach().cpu(), module_grads(m)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("kind", ["FM-OT", "CFM", "droid"])
+def test_loss_and_gradients_vs_oracle_autograd(name, kind):
+    g = Golden(name)
+    m = build_module(g.ctor, g.sd, loss_type=kind, device=DEV)
+    gen = torch.Generator().manual_seed(31)
+    x = g.x * 5.0 * g.mask
+    B = x.shape[0]
+    t = torch.rand(B, generator=gen)
+    n0 = torch.randn(x.shape, generator=gen)
+    n1 = torch.randn(x.shape, generator=gen) if kind == "CFM" else None
+    sigma = 1e-4
+    ref_loss, ref_g = oracle_loss_and_grads(g, kind, x, g.mask, g.cond, t, n0, n1, sigma)
+    loss, got = run_fused(m, kind, x, g.mask, g.cond, t, n0, n1, sigma)
+    assert abs(float(loss) - float(ref_loss)) <= LOSS_TOL * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    assert set(got) == set(ref_g)
+    worst = max((rel_l2(got[k], ref_g[k]), k) for k in ref_g if ref_g[k] is not None and float(ref_g[k].norm()) > 0)
+    assert worst[0] < GRAD_TOL, worst
+    # gradient of a parameter the loss does not depend on is exactly zero on both sides
+    for k, v in ref_g.items():
+        if v is not None and float(v.norm()) == 0:
+            assert float(got[k].norm()) == 0, k
+
+
+def test_loss_module_api_and_rng_order():
+    """SetFlowMatchingLitModule.training_step: t from the CPU generator, noise on the device;
+    the same draws fed to the oracle give the same loss; validation (no_grad) gives the same value, no grads."""
+    g = Golden("c1_jetnet30")
+    m = build_module(g.ctor, g.sd, loss_type="FM-OT", device=DEV)
+    x = (g.x * 5.0 * g.mask).to(DEV)
+    mask = g.mask.to(DEV)
+    torch.manual_seed(5)
+    out = m.training_step((x, mask, torch.zeros(x.shape[0], device=DEV)), 0)
+    loss = out["loss"]
+    assert loss.requires_grad and loss.dim() == 0
+    loss.backward()
+    assert all(p.grad is not None for p in m.flows[0].net.parameters())
+    torch.manual_seed(5)
+    t = torch.rand_like(torch.ones(x.shape[0]))
+    n0 = torch.randn_like(x)
+    vf = g.oracle_vf()
+    ref = lo.fm_loss(vf, "FM-OT", x.cpu(), g.mask, t, n0.cpu(), None, 1e-4)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    torch.manual_seed(5)
+    val = m.validation_step((x, mask, torch.zeros(x.shape[0], device=DEV)), 0)["loss"]
+    assert not val.requires_grad and abs(float(val) - float(loss)) <= 1e-6 * abs(float(loss))
+
+
+def test_generic_autograd_of_the_vector_field():
+    """CNF.forward under autograd with an arbitrary downstream loss: gradients w.r.t. x and the parameters."""
+    g = Golden("cond_lhco_like")
+    m = build_module(g.ctor, g.sd, device=DEV)
+    gen = torch.Generator().manual_seed(3)
+    x = g.x.clone()
+    w = torch.randn(x.shape, generator=gen)
+    B, N = x.shape[:2]
+    t = torch.rand(B, generator=gen).unsqueeze(-1).repeat_interleave(N, dim=1)
+    sd = {k: v.clone().requires_grad_(True) for k, v in g.sd.items()}
+    xr = x.clone().requires_grad_(True)
+    v_ref = eo.cnf_forward(sd, g.cfg, t, xr, g.cond, g.mask, **g.oracle_kwargs())
+    (v_ref * w).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    m.zero_grad(set_to_none=True)
+    v = m.flows[0](t.to(DEV), xd, cond=g.cond.to(DEV), mask=g.mask.to(DEV))
+    assert rel_l2(v.detach().cpu(), v_ref.detach()) < 1e-5
+    (v * w.to(DEV)).sum().backward()
+    assert rel_l2(xd.grad.cpu() * g.mask, xr.grad * g.mask) < GRAD_TOL
+    assert float((xd.grad.cpu() * (1 - g.mask)).abs().max()) == 0
+    got = module_grads(m)
+    worst = max((rel_l2(got[k], sd[k].grad), k) for k in sd if float(sd[k].grad.norm()) > 0)
+    assert worst[0] < GRAD_TOL, worst
+
+
+def test_optimizer_step_changes_the_packed_weights():
+    """AdamW step -> parameters change in place -> the packed copy is refreshed; loss goes down on a fixed batch."""
+    g = Golden("c1_jetnet30")
+    m = build_module(g.ctor, g.sd, loss_type="FM-OT", device=DEV)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=5e-5)
+    x = (g.x * 5.0 * g.mask).to(DEV)
+    mask = g.mask.to(DEV)
+    losses = []
+    for _ in range(8):
+        torch.manual_seed(11)
+        opt.zero_grad()
+        loss = m.loss(x, mask=mask, cond=None)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
