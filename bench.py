@@ -131,6 +131,50 @@ def time_cpu(run, n_jets, seed, reps=1):
     return n_jets / dt, dt, float(n_real.float().mean())
 
 
+def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
+    """Secondary metric (BASELINE.json: "train jets/s"): full training steps of the default JetNet-150 net --
+    fused FM-OT loss forward+backward (fp32 kernels), flat-gradient all-reduce over the ranks, global-norm clip 0.5,
+    AdamW(1e-3, wd 5e-5) (configs/model/flow_matching.yaml:3-7, experiment gradient_clip_val 0.5).  Weak scaling:
+    B jets per GPU per step (jetnet_tops_30_jedi.yaml:3 batch 1024)."""
+    import torch.distributed as dist
+    from particle_fm_b200.launch import attach_flat_grad_allreduce
+    if world > 1:
+        attach_flat_grad_allreduce(model)
+    mask_h, n_real = synth_masks(B, 777 + rank)
+    g = torch.Generator().manual_seed(888 + rank)
+    x = (5.0 * torch.randn(B, N_PART, FEATS, generator=g) * mask_h).to(dev)
+    mask = mask_h.to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-5)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(x, mask=mask, cond=None)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"value": world * B * steps / (ms / 1e3), "unit": "jets/s", "batch_per_gpu": B, "steps": steps,
+            "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss),
+            "step": "fused loss fwd+bwd (fp32 CUDA cores) + flat-grad all-reduce + clip 0.5 + AdamW",
+            "mean_real_particles": float(n_real.float().mean())}
+
+
 def reference_arm(args, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port; torchdyn/Lightning are
     not installable here), all host threads, bounded sample per step."""
@@ -169,6 +213,7 @@ def main():
     ap.add_argument("--ref-jets", type=int, default=8, help="jets per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-jets", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,6 +304,10 @@ def main():
     h2d = B * N_PART * FEATS * 4 + B * N_PART * 4 + NFE * 32 * 4 + (ODE_STEPS - 1) * 4
     d2h = B * N_PART * FEATS * 4
 
+    train = None
+    if not args.no_train:
+        train = train_bench(model, dev, world, rank)
+
     if rank == 0:
         peaks = measured_peaks()
         flops = (float(n_real.sum()) * FLOP_PER_PARTICLE + B * FLOP_PER_JET) * NFE          # per launch, this rank
@@ -282,6 +331,8 @@ def main():
                              "kernel": "epic_tc_kernel" if args.precision == "bf16" else "epic_simt_kernel",
                              "kernel_ms": k_ms, "algorithmic_flop_per_launch": flops,
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)"}}
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)

@@ -1,0 +1,36 @@
+"""Data-parallel training of the fused flow-matching step.
+
+The reference trains with Lightning DDP (`configs/trainer/ddp.yaml:4-9`): DistributedDataParallel all-reduces the
+per-parameter gradients (87 tensors for the default net) in buckets while autograd runs.  Here the fused backward
+produces ONE flat fp32 buffer with the gradient of the folded weights (2.25 MB for the default net), so data
+parallelism is a single all-reduce (mean) of that buffer over NCCL/NVLink before `torch._weight_norm`'s backward
+maps it onto weight_g / weight_v.  The map is linear, so averaging folded-weight gradients equals averaging
+parameter gradients -- every rank then takes the identical optimizer step, like DDP.  The loss normaliser stays
+per rank (sum(mask) of the local batch), which is DDP's semantics over the reference loss.
+
+Lightning's own DDP keeps working too (the parameters receive ordinary autograd gradients); this hook is the
+lighter path for the repo's own launcher and bench.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def attach_flat_grad_allreduce(model, group=None):
+    """Average the flat gradient over `group` inside the fused training step of every flow of `model`."""
+    world = dist.get_world_size(group)
+
+    def hook(flat: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return flat.div_(world)
+
+    for f in model.flows:
+        f.net.flat_grad_hook = hook
+    return model
+
+
+def detach_flat_grad_allreduce(model):
+    for f in model.flows:
+        f.net.flat_grad_hook = None
+    return model
