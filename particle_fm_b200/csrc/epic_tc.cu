@@ -30,7 +30,15 @@ static constexpr int TC_ROWS = 256;      // 2 tiles of 128 particles
 static constexpr int TC_J = 16;          // jets per group (N of the pooling MMA)
 static constexpr int TC_ZMAX = 16;        // latent width (10 / 16 in the configs); the small-weight pack is laid out for 16
 static constexpr int TC_KXMAX = 8;          // per-particle input columns / features (3 JetNet, 8 JetClass)
-static constexpr uint32_t TC_SPK = 3 * 16 * 128 * 2;   // per-unit small-weight pack (bf16): W_gg | W_glob | W_g2, 12 KB
+// per-unit small-weight pack, one bulk copy:  W_gg | W_glob (bf16, [z][o])  and  W_g2 (fp32, [z][k], rows padded to
+// 132 floats so that 8 lanes reading 8 different rows with LDS.128 hit 8 different bank groups)
+struct SpkPack {
+  __nv_bfloat16 gg[16][128];     // W_gg[z][o]   = fc_global1[o][2H + z]        (layers)
+  __nv_bfloat16 gl[16][128];     // W_glob[z][o] = fc_local1[o][H + z]          (layers)
+  float g2[16][128 + 4];         // W_g2[z][k]   = fc_global2[z][k]  (fc_g2 for the stem)
+};
+static constexpr uint32_t TC_SPK = sizeof(SpkPack);
+static_assert(sizeof(SpkPack) % 16 == 0, "bulk copies move multiples of 16 bytes");
 static constexpr int TC_SBIAS = 384 + 16;               // one unit's slice of the time-bias table
 static constexpr int TC_THREADS = 384;
 static constexpr int TC_NSLOT = 3;
@@ -41,14 +49,16 @@ struct TcSmem {
   alignas(1024) uint8_t h[2][TC_MAT];          // bf16 h tiles
   alignas(1024) uint8_t w[TC_NSLOT][TC_MAT];   // weight ring
   alignas(1024) uint8_t P[8192];               // [16 jets x 256 rows] bf16, K-major SW128, 4 blocks of 2 KB
-  alignas(1024) uint8_t St[4096];              // [16 jets x 128 c]    bf16, K-major SW128, 2 blocks of 2 KB
+  union alignas(1024) {
+    uint8_t St[8192];                          // [16 jets x 256 k] bf16, K-major SW128, 4 blocks of 2 KB: k < 128 mean, k >= 128 sum.
+    float g1[TC_J][TCH];                       // B operand of the fc_global1 MMAs; dead once they complete -> reused for g1
+  } sg;
   float bl1[TC_J][TCH];
   float bl2[TC_J][TCH];
-  float g1[TC_J][TCH];
-  float gv[TC_J][TC_ZMAX];
-  float w1s[FP][TCH];                          // fc_l1 rows used for the particle features (k-major)
-  float w3s[TCH][FP];                          // fc_l3 (k-major)
-  alignas(16) __nv_bfloat16 spk[3][16][TCH];   // [0] W_gg[z][o]  [1] W_glob[z][o]  [2] W_g2[z][o]   (current unit)
+  alignas(16) float gv[TC_J][TC_ZMAX];
+  alignas(16) float w1s[TCH][FP];              // fc_l1 weights of the particle features, [column][feature]
+  alignas(16) float w3s[TCH][FP];              // fc_l3 (k-major)
+  alignas(16) SpkPack spk;                     // small weights of the current unit
   alignas(16) float sbias[TC_SBIAS];           // time-bias slice of the current unit (4 consecutive linears)
   float inv_n[TC_J];
   int boff[128];                               // bias-table offset of every linear (copied once: no global descriptor loads in the loop)
@@ -61,6 +71,8 @@ struct TcSmem {
   uint64_t spk_full, spk_empty;
 };
 
+static_assert(sizeof(TcSmem<8>) + 1024 <= 232448, "TcSmem exceeds the 227 KB per-block shared-memory limit of sm_100");
+template <int N> struct PrintSize;
 struct TcParams {
   int F, Kx, x_ld, xin_off, Z, L, n_lin, n_items;
   float sum_scale, slope;
@@ -85,16 +97,14 @@ __device__ __forceinline__ float tc_bias_of(const TcParams& p, const Lin& L, int
 }
 
 // packed fp32x2 math (FADD2 / FMUL2 on sm_100): leaky_relu(v + b) for two neighbouring columns
-__device__ __forceinline__ void bias_lrelu2(uint32_t& v0, uint32_t& v1, float b0, float b1, unsigned long long slope2, bool valid) {
+__device__ __forceinline__ void bias_lrelu2(uint32_t& v0, uint32_t& v1, float b0, float b1, unsigned long long slope2) {
   unsigned long long v = ((unsigned long long)v1 << 32) | v0;
   const unsigned long long b = ((unsigned long long)__float_as_uint(b1) << 32) | __float_as_uint(b0);
   unsigned long long a, t;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(v), "l"(b));
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(a), "l"(slope2));
-  const float r0 = fmaxf(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)t));
-  const float r1 = fmaxf(__uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)(t >> 32)));
-  v0 = valid ? __float_as_uint(r0) : 0u;
-  v1 = valid ? __float_as_uint(r1) : 0u;
+  v0 = __float_as_uint(fmaxf(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)t)));
+  v1 = __float_as_uint(fmaxf(__uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)(t >> 32))));
 }
 
 __device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
@@ -118,7 +128,11 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {
 }
 
 // Phase profiler (debug, PFM_TC_PROF=1): block 0 accumulates clock64() deltas per phase for one thread of each role.
-#define PROF_T(slot) do { if (PROF && prof_on) { const long long _n = clock64(); prof[slot] += _n - prof_t; prof_t = _n; } } while (0)
+// It also records an event trace (slot, clock) of evaluation TRACE_EV of the block's first group.
+#define PROF_T(slot) do { if (PROF && prof_on) { const long long _n = clock64(); prof[slot] += _n - prof_t; prof_t = _n; \
+    if (trace_on && ev == TRACE_EV && trace_n < TRACE_MAX) { p.prof[60 + (prof_role * TRACE_MAX + trace_n) * 2] = slot; \
+      p.prof[61 + (prof_role * TRACE_MAX + trace_n) * 2] = _n; ++trace_n; } } } while (0)
+static constexpr int TRACE_EV = 6, TRACE_MAX = 160;
 
 template <int FP, bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p) {
@@ -132,6 +146,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
   long long prof[20];
   long long prof_t = 0;
   const bool prof_on = PROF && blockIdx.x == 0 && (tid == 32 || tid == 128 || tid == 256);   // lane 0 of the MMA warp, of epilogue A, of epilogue B
+  const int prof_role = tid == 32 ? 0 : (tid == 128 ? 1 : 2);
+  int trace_n = 0;
+  bool trace_on = PROF;
   if (PROF) {
 #pragma unroll
     for (int i = 0; i < 20; ++i) prof[i] = 0;
@@ -143,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
     }
-    mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 128); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 128);
+    mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 256); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 256);
     mbar_init(&s.spk_full, 1); mbar_init(&s.spk_empty, 256);
     fence_barrier_init();
   }
@@ -152,8 +169,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     const Lin L1 = lin[LIN_L1], L3 = lin[p.n_lin - 1];
     for (int i = tid; i < p.Kx * TCH; i += TC_THREADS) {
       const int k = i / TCH, o = i - k * TCH;
-      s.w1s[k][o] = L1.Wt[(size_t)(L1.m_off + p.xin_off + k) * L1.ldo + o];
+      s.w1s[o][k] = L1.Wt[(size_t)(L1.m_off + p.xin_off + k) * L1.ldo + o];
     }
+    for (int i = tid; i < TCH * FP; i += TC_THREADS)
+      if ((i % FP) >= p.Kx) (&s.w1s[0][0])[i] = 0.f;
     for (int i = tid; i < TCH * FP; i += TC_THREADS) {
       const int c = i / FP, f = i - c * FP;
       s.w3s[c][f] = f < L3.ldo ? L3.Wt[(size_t)(L3.m_off + c) * L3.ldo + f] : 0.f;
@@ -173,6 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
   uint32_t spk_it = 0;                                      // producer: small-weight packs issued so far
 
   for (;;) {
+    if (PROF && trace_n > 0) trace_on = false;     // trace the block's first group only
     __syncthreads();
     if (tid == 0) s.group = atomicAdd(p.counter, 1);
     __syncthreads();
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               ++spk_it;
               if (elect_one()) {
                 mbar_arrive_expect_tx(&s.spk_full, TC_SPK + bias_bytes);
-                bulk_copy_g2s(s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
+                bulk_copy_g2s(&s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
                 if (stage_bias)
                   bulk_copy_g2s(s.sbias, p.tbias + (size_t)ev * p.bstride + (u == 0 ? p.boff_stem : p.boff_layer0 + (u - 1) * p.boff_layer_stride),
                                 bias_bytes, &s.spk_full);
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         const uint32_t idesc_glob = make_idesc_bf16(128, 16, 0, 0);
         const uint64_t hA = desc_kmajor(smem_u32(s.h[0])), hB = desc_kmajor(smem_u32(s.h[1]));
         const uint64_t hAt = desc_mnmajor(smem_u32(s.h[0]), 16384u, 1024u), hBt = desc_mnmajor(smem_u32(s.h[1]), 16384u, 1024u);
-        const uint64_t pdesc = desc_kmajor(smem_u32(s.P)), sdesc = desc_kmajor(smem_u32(s.St));
+        const uint64_t pdesc = desc_kmajor(smem_u32(s.P)), sdesc = desc_kmajor(smem_u32(s.sg.St));
         const uint64_t wdesc0 = desc_kmajor(smem_u32(s.w[0]));
         const uint32_t accH0 = tm, accH1 = tm + 128, accU0 = tm + 256, accU1 = tm + 384;
         const uint32_t dpool = tm + 384 + 64, dglob = tm + 384 + 80;
@@ -243,33 +263,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           for (int gi = 0; gi <= L; ++gi) {
             uint32_t it_w1 = 0;
             if (gi != 1) {   // a new version of h is complete: pool it   S[c][jet] = sum_rows h[row][c] P[jet][row]
-              PROF_T(0);
-              mbar_wait(&s.hready[0], c_hready[0]++ & 1);
-              mbar_wait(&s.hready[1], c_hready[1]++ & 1);
-              tc_fence_after();
-              PROF_T(3);
-              if (elect_one()) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t)
+              for (int t = 0; t < 2; ++t) {          // tile A's half is issued as soon as tile A is ready
+                PROF_T(0);
+                mbar_wait(&s.hready[t], c_hready[t]++ & 1);
+                tc_fence_after();
+                PROF_T(3);
+                if (elect_one()) {
 #pragma unroll
                   for (int k = 0; k < 8; ++k) {      // 16 rows of h per step: +2 KB in the MN-major view; P: 2 KB per 64 rows
                     const uint64_t da = (t ? hBt : hAt) + (uint64_t)(k * 128);
                     const uint64_t db = pdesc + (uint64_t)((t * 2 + (k >> 2)) * 128 + (k & 3) * 2);
                     mma_ss(dpool, da, db, idesc_pool, (t | k) ? 1u : 0u);
                   }
+                }
+                __syncwarp();
               }
-              __syncwarp();
               commit_to(&s.pool_full);
             }
-            if (gi >= 1) {   // fc_local1 of tile A does not need the global vector: issue it right away
-              it_w1 = ring_it++;
-              PROF_T(0);
-              wait_full(it_w1);
-              PROF_T(4);
-              issue_ss_128(accU0, hA, wslot(it_w1), idesc, false);
-              commit_to(&s.accU_full[0]);
-            }
-            // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . S[:, jet],  W_sum likewise
+            if (gi >= 1) it_w1 = ring_it++;          // ring order: fc_local1 | fc_global1 mean | sum | fc_local2
+            // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . mean[jet][:] + W_sum[o][:] . sum[jet][:]
+            // (issued before fc_local1: it is on the serial per-jet chain, fc_local1's result is not needed before the chain ends)
             const uint32_t it_gm = ring_it++, it_gs = ring_it++;
             PROF_T(0);
             mbar_wait(&s.glob_go, c_globgo++ & 1);
@@ -283,13 +297,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                  mma_ss(dglob + m * 16, wd + kstep16(k), sdesc + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), idesc_glob, k ? 1u : 0u);
+                  mma_ss(dglob, wd + kstep16(k), sdesc + (uint64_t)((m * 2 + (k >> 2)) * 128 + (k & 3) * 2), idesc_glob, (m | k) ? 1u : 0u);
               }
               __syncwarp();
             }
             commit_to(&s.glob_full);
             commit_to(&s.empty[it_gm % TC_NSLOT]);
             commit_to(&s.empty[it_gs % TC_NSLOT]);
+            if (gi >= 1) {   // fc_local1 of tile A
+              PROF_T(0);
+              wait_full(it_w1);
+              PROF_T(4);
+              issue_ss_128(accU0, hA, wslot(it_w1), idesc, false);
+              commit_to(&s.accU_full[0]);
+            }
             PROF_T(0);
             mbar_wait(&s.d_free, c_dfree++ & 1);      // pooling / global accumulators (aliasing accU of tile B) consumed
             tc_fence_after();
@@ -341,7 +362,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int j = nj; j <= TC_J; ++j) s.jrow0[j] = acc;
         for (int j = nj; j < TC_J; ++j) s.inv_n[j] = 0.f;
       }
+      // P = 0, h = 0: rows without a particle are never written afterwards, so they stay finite (0) in every
+      // operand the pooling MMA reads; their TMEM lanes hold finite junk that no real row ever sees
       for (int i = et; i < 8192 / 16; i += 256) reinterpret_cast<uint4*>(s.P)[i] = make_uint4(0, 0, 0, 0);
+      for (int i = et; i < 2 * (int)TC_MAT / 16; i += 256) reinterpret_cast<uint4*>(&s.h[0][0])[i] = make_uint4(0, 0, 0, 0);
       for (int i = et; i < TC_J * TC_ZMAX; i += 256) (&s.gv[0][0])[i] = 0.f;
       ebar();
       const int R = s.jrow0[nj];
@@ -353,10 +377,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int jg = j0 + myjet;
       // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
       // slow direct path when every jet has its own time (training-style forward)
-      auto unit_bias = [&](int lin_idx, int voff, int ev_, int jet_global, int o) -> float {
+      auto unit_bias = [&](int lin_idx, int voff, int jet_global, int o) -> float {
         float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o] : s.sbias[voff + o];
         if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o];
-        (void)ev_;
         return b;
       };
       float x0[FP], xc[FP], vout[FP];
@@ -370,6 +393,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int f = 0; f < FP; ++f)
           if (f < p.Kx) { xc[f] = src[f]; x0[f] = xc[f]; }
       }
+      const uint32_t hrow_addr = smem_u32(hrow), rx16 = (uint32_t)(r & 7) << 4, vpred = valid ? 1u : 0u;
+      const uint32_t bl1_addr = smem_u32(&s.bl1[myjet][0]), bl2_addr = smem_u32(&s.bl2[myjet][0]);
+      const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
+      const int ZP = (Z + 3) & ~3;
+
+      // store 32 fp32 columns [32c, 32c+32) of this particle's row as bf16 into the swizzled h tile
+      auto store_h_bf16 = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+          const int c16 = c * 4 + q;
+          sts128_if(hrow_addr + (uint32_t)((c16 >> 3) * 16384) + ((uint32_t)((c16 & 7) << 4) ^ rx16), pk.x, pk.y, pk.z, pk.w, vpred);
+        }
+      };
 
       for (int ev = 0; ev < p.n_evals; ++ev) {
         // ---------------- unit 0 pack (stem biases + fc_g2) has landed; per-jet stem biases ----------------
@@ -377,23 +418,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         mbar_wait(&s.spk_full, c_spk++ & 1);
         PROF_T(1);
         float b3[FP];                              // head bias and step size: loaded now, used at the end of the evaluation
-        {
 #pragma unroll
-          for (int f = 0; f < FP; ++f) {
-            b3[f] = 0.f;
-            if (f < F) {
-              b3[f] = p.tbias[(size_t)(p.tbias_per_jet ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
-              if (p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
-            }
+        for (int f = 0; f < FP; ++f) {
+          b3[f] = 0.f;
+          if (f < F) {
+            b3[f] = p.tbias[(size_t)(p.tbias_per_jet ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
+            if (p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
           }
         }
         const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
-        {
-          for (int i = et; i < nj * TCH; i += 256) {
-            const int j = i >> 7, o = i & 127;
-            s.bl1[j][o] = unit_bias(LIN_L1, 0, ev, j0 + j, o);
-            s.bl2[j][o] = unit_bias(LIN_L2, 128, ev, j0 + j, o);
-          }
+        for (int i = et; i < nj * TCH; i += 256) {
+          const int j = i >> 7, o = i & 127;
+          s.bl1[j][o] = unit_bias(LIN_L1, 0, j0 + j, o);
+          s.bl2[j][o] = unit_bias(LIN_L2, 128, j0 + j, o);
         }
         ebar();
         // ---------------- fc_l1 on CUDA cores (K = a few features): h1 -> TMEM (fp32) + shared (bf16) ----------------
@@ -401,25 +438,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = s.bl1[myjet][c * 32 + i];
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 b = lds128(bl1_addr + (uint32_t)(c * 128 + i4 * 16));
+            float a[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int f = 0; f < FP; ++f)
-              if (f < p.Kx) a = fmaf(s.w1s[f][c * 32 + i], xc[f], a);
-            a = valid ? lrelu_tc(a, p.slope) : 0.f;
-            v[i] = __float_as_uint(a);
+            for (int q = 0; q < 4; ++q) {
+              const float* w = &s.w1s[c * 32 + i4 * 4 + q][0];
+              if (FP == 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w);
+                a[q] = fmaf(w4.x, xc[0], a[q]); a[q] = fmaf(w4.y, xc[1], a[q]); a[q] = fmaf(w4.z, xc[2], a[q]);
+                a[q] = fmaf(w4.w, xc[3], a[q]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < FP; ++f) a[q] = fmaf(w[f], xc[f], a[q]);
+              }
+              v[i4 * 4 + q] = __float_as_uint(lrelu_tc(a[q], p.slope));
+            }
           }
           tmem_st32(accH + c * 32, v);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-            pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-            pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-            const int c16 = c * 4 + q;
-            *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
-          }
+          store_h_bf16(v, c);
         }
         tmem_wait_st();
         fence_proxy_async();
@@ -427,38 +464,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         mbar_arrive(&s.hready[wg]);
         PROF_T(2);
 
-        // residual update epilogue shared by the stem's fc_l2 and every fc_local2:
-        //   h = lrelu(acc + bias) -> TMEM fp32 (in place) and shared bf16; on the last layer also the head
-        const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
         // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16 (+ head)
         auto epi_h_chunk = [&](uint32_t (&v)[32], int c, bool write_back, bool head) {
-          const float4* bj = reinterpret_cast<const float4*>(&s.bl2[myjet][c * 32]);
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 b = bj[i4];
-            bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2, valid);
-            bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2, valid);
+            const float4 b = lds128(bl2_addr + (uint32_t)(c * 128 + i4 * 16));
+            bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
+            bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
           }
           if (head) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float a = __uint_as_float(v[i]);
+              if (FP == 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&s.w3s[c * 32 + i][0]);
+                vout[0] = fmaf(w4.x, a, vout[0]); vout[1] = fmaf(w4.y, a, vout[1]); vout[2] = fmaf(w4.z, a, vout[2]);
+                vout[3] = fmaf(w4.w, a, vout[3]);
+              } else {
 #pragma unroll
-              for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
+                for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
+              }
             }
           }
           if (write_back) {
             tmem_st32(accH + c * 32, v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-              const int c16 = c * 4 + q;
-              *reinterpret_cast<uint4*>(hrow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
-            }
+            store_h_bf16(v, c);
           }
         };
         // residual update epilogue shared by the stem's fc_l2 and every fc_local2; the TMEM load of chunk c+1 is in
@@ -481,138 +511,180 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           epi_h_chunk(va, 2, write_back, head);
           tmem_wait_ld();
           epi_h_chunk(vb, 3, write_back, head);
+          PROF_T(4);
           if (write_back) {
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&s.hready[wg]);
           }
-          PROF_T(4);
+          PROF_T(18);
         };
         epi_h(true, false);                        // stem fc_l2 (+ residual h1)
 
-        for (int gi = 0; gi <= L; ++gi) {
-          // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
+        // [A] (off the critical path) pre[j] = bias_g1[o] + W_gg[o] . g_prev[j] of unit gi, for this thread's jets;
+        // waits for the unit's small-weight pack first
+        float pre[2][4];
+        auto compute_pre = [&](int gi) {
           const int Ga = gi == 0 ? LIN_G1 : LIN_LAYER0 + 4 * (gi - 1) + 0;
-          const int Gb = gi == 0 ? LIN_G2 : LIN_LAYER0 + 4 * (gi - 1) + 1;
-          const int ZP = (Z + 3) & ~3;
-          const int off_ga = gi == 0 ? 256 : 0, off_gb = gi == 0 ? 384 : 128;     // slice offsets inside sbias
+          const int off_ga = gi == 0 ? 256 : 0;
           PROF_T(0);
           if (gi >= 1) mbar_wait(&s.spk_full, c_spk++ & 1);                        // unit gi's pack (unit 0: waited at eval start)
           PROF_T(5);
-          if (wg == 1) {
-            // tile B's warps are idle during the (narrow) global chain: they compute bias + W_gg . g (previous global
-            // vector) for every (jet, o = r) into the g1 buffer and hand over through named barrier 2
-            float a[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = j < nj ? unit_bias(Ga, off_ga, ev, j0 + j, r) : 0.f;
-            if (gi >= 1) {
+          for (int bb = 0; bb < 2; ++bb) {
+            const int jb = (wg + 2 * bb) * 4;
 #pragma unroll
-              for (int z = 0; z < TC_ZMAX; ++z) {
-                if (z < Z) {
-                  const float w = __bfloat162float(s.spk[0][z][r]);
+            for (int q = 0; q < 4; ++q) pre[bb][q] = 0.f;
+            if (jb < nj) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) a[j] = fmaf(w, s.gv[j][z], a[j]);
+              for (int q = 0; q < 4; ++q) pre[bb][q] = (jb + q < nj) ? unit_bias(Ga, off_ga, j0 + jb + q, r) : 0.f;
+              if (gi >= 1) {
+#pragma unroll
+                for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {
+                  if (z4 * 4 < Z) {
+                    float w[4];
+#pragma unroll
+                    for (int zz = 0; zz < 4; ++zz) w[zz] = __bfloat162float(s.spk.gg[z4 * 4 + zz][r]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float4 g = *reinterpret_cast<const float4*>(&s.gv[jb + q][z4 * 4]);
+                      pre[bb][q] = fmaf(w[0], g.x, pre[bb][q]); pre[bb][q] = fmaf(w[1], g.y, pre[bb][q]);
+                      pre[bb][q] = fmaf(w[2], g.z, pre[bb][q]); pre[bb][q] = fmaf(w[3], g.w, pre[bb][q]);
+                    }
+                  }
                 }
               }
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s.g1[j][r] = a[j];
-            asm volatile("bar.arrive 2, 256;" ::: "memory");
-            PROF_T(8);
           }
-          if (wg == 0) {
-            PROF_T(8);
-            if (gi != 1) {                         // new pooled sums: TMEM -> bf16 B operand in shared memory
-              mbar_wait(&s.pool_full, c_pool++ & 1);
-              tc_fence_after();
-              PROF_T(6);
-              uint32_t v[16];
-              tmem_ld16(dpool, v);
-              tmem_wait_ld();
+          PROF_T(8);
+        };
+
+        float sreg[2][4];                          // this thread's pooled sums S[c = r][its jets] (reused by layer 0)
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                *reinterpret_cast<__nv_bfloat16*>(s.St + sw128_offset(j, r, 2048)) = __float2bfloat16(__uint_as_float(v[j]));
-              fence_proxy_async();
-            }
-            tc_fence_before();
-            mbar_arrive(&s.glob_go);
-            PROF_T(7);
-            mbar_wait(&s.glob_full, c_glob++ & 1);
+        for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sreg[bb][q] = 0.f;
+
+        for (int gi = 0; gi <= L; ++gi) {
+          // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
+          // Per-jet work is split over the 256 threads as (o = r) x (batches of 4 jets: wg, wg + 2).
+          const int Gb = gi == 0 ? LIN_G2 : LIN_LAYER0 + 4 * (gi - 1) + 1;
+          const int off_gb = gi == 0 ? 384 : 128;                                 // slice offset inside sbias
+          if (gi <= 1) compute_pre(gi);            // later units: computed while fc_local2 of the previous layer runs
+          // ---- [B] pooled sums -> pre-scaled bf16 B operand  St[j][0:128) = S/n (mean), St[j][128:256) = S*s (sum)
+          if (gi != 1) {
+            mbar_wait(&s.pool_full, c_pool++ & 1);
             tc_fence_after();
-            PROF_T(9);
-            uint32_t dm[16], ds[16];
-            tmem_ld16(dglob, dm);
-            tmem_ld16(dglob + 16, ds);
-            tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive(&s.d_free);
-            // g1[j][o = r] = lrelu(W_mean.S / n + s * W_sum.S (+ W_g . g) + bias)     (epic.py:180-182, :375-377)
-            asm volatile("bar.sync 2, 256;" ::: "memory");      // tile B's warps have written bias + W_gg . g
+            PROF_T(6);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = fmaf(__uint_as_float(dm[j]), s.inv_n[j], s.g1[j][r]);
-              v = fmaf(__uint_as_float(ds[j]), p.sum_scale, v);
-              s.g1[j][r] = lrelu_tc(v, p.slope);
-            }
-            PROF_T(10);
-          }
-          ebar();
-          PROF_T(11);
-          {   // fc_g2 / fc_global2 (+ residual for the layers): 8 threads per (jet, latent) output, 16 inputs each
-            const int sub = et & 7, pi = et >> 3;
-            const int n_out = nj * Z;
-            for (int base = 0; base < n_out; base += 32) {
-              const int item = base + pi;
-              const bool on = item < n_out;
-              const int j = on ? item / Z : 0, z = on ? item - (item / Z) * Z : 0;
-              const uint4* wp = reinterpret_cast<const uint4*>(&s.spk[2][z][sub * 16]);
-              const float4* gp = reinterpret_cast<const float4*>(&s.g1[j][sub * 16]);
-              const uint4 w0 = wp[0], w1 = wp[1];
-              const float4 g0 = gp[0], g1v = gp[1], g2v = gp[2], g3 = gp[3];
-              const __nv_bfloat162* wh0 = reinterpret_cast<const __nv_bfloat162*>(&w0);
-              const __nv_bfloat162* wh1 = reinterpret_cast<const __nv_bfloat162*>(&w1);
-              float acc = 0.f;
-              float2 f;
-              f = __bfloat1622float2(wh0[0]); acc = fmaf(f.x, g0.x, acc); acc = fmaf(f.y, g0.y, acc);
-              f = __bfloat1622float2(wh0[1]); acc = fmaf(f.x, g0.z, acc); acc = fmaf(f.y, g0.w, acc);
-              f = __bfloat1622float2(wh0[2]); acc = fmaf(f.x, g1v.x, acc); acc = fmaf(f.y, g1v.y, acc);
-              f = __bfloat1622float2(wh0[3]); acc = fmaf(f.x, g1v.z, acc); acc = fmaf(f.y, g1v.w, acc);
-              f = __bfloat1622float2(wh1[0]); acc = fmaf(f.x, g2v.x, acc); acc = fmaf(f.y, g2v.y, acc);
-              f = __bfloat1622float2(wh1[1]); acc = fmaf(f.x, g2v.z, acc); acc = fmaf(f.y, g2v.w, acc);
-              f = __bfloat1622float2(wh1[2]); acc = fmaf(f.x, g3.x, acc); acc = fmaf(f.y, g3.y, acc);
-              f = __bfloat1622float2(wh1[3]); acc = fmaf(f.x, g3.z, acc); acc = fmaf(f.y, g3.w, acc);
-              acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-              acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-              acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-              if (on && sub == 0) {
-                acc += unit_bias(Gb, off_gb, ev, j0 + j, z);
-                if (gi >= 1) acc += s.gv[j][z];
-                s.gv[j][z] = lrelu_tc(acc, p.slope);
+            for (int bb = 0; bb < 2; ++bb) {
+              const int jb = (wg + 2 * bb) * 4;
+              if (jb < nj) {
+                uint32_t v[4];
+                tmem_ld4(dpool + jb, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sreg[bb][q] = __uint_as_float(v[q]);
               }
             }
           }
-          if (gi == 0) {                           // the stem has no per-particle linears of its own after the pooling
-            mbar_arrive(&s.spk_empty);
-            ebar();
-            PROF_T(12);
-            continue;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            const int jb = (wg + 2 * bb) * 4;
+            if (jb < nj) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int j = jb + q;
+                *reinterpret_cast<__nv_bfloat16*>(s.sg.St + sw128_offset(j, r, 2048)) = __float2bfloat16(sreg[bb][q] * s.inv_n[j]);
+                *reinterpret_cast<__nv_bfloat16*>(s.sg.St + sw128_offset(j, 128 + r, 2048)) = __float2bfloat16(sreg[bb][q] * p.sum_scale);
+              }
+            }
+          }
+          PROF_T(7);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&s.glob_go);
+          PROF_T(19);
+          // ---- [C] g1[j][o] = lrelu(W_mean . mean + W_sum . sum (+ W_gg . g) + bias)     (epic.py:180-182, :375-377)
+          mbar_wait(&s.glob_full, c_glob++ & 1);
+          tc_fence_after();
+          PROF_T(9);
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            const int jb = (wg + 2 * bb) * 4;
+            if (jb < nj) {
+              uint32_t v[4];
+              tmem_ld4(dglob + jb, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) s.sg.g1[jb + q][r] = lrelu_tc(__uint_as_float(v[q]) + pre[bb][q], p.slope);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&s.d_free);
+          ebar();
+          PROF_T(10);
+          // ---- [D] fc_g2 / fc_global2 (+ residual for the layers): warp = jet, lane = (k half, z); K = 2 x 64
+          for (int j = (et >> 5); j < nj; j += 8) {
+            const int lane_ = et & 31, z = lane_ & 15, kh = lane_ >> 4;
+            const int zc = z < Z ? z : 0;
+            const uint32_t wa = smem_u32(&s.spk.g2[zc][kh * 64]), ga = smem_u32(&s.sg.g1[j][kh * 64]);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float4 w = lds128(wa + k * 16), g = lds128(ga + k * 16);
+              a0 = fmaf(w.x, g.x, a0); a1 = fmaf(w.y, g.y, a1); a2 = fmaf(w.z, g.z, a2); a3 = fmaf(w.w, g.w, a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (kh == 0 && z < Z) {
+              acc += unit_bias(Gb, off_gb, j0 + j, z);
+              if (gi >= 1) acc += s.gv[j][z];
+              s.gv[j][z] = lrelu_tc(acc, p.slope);
+            }
           }
           ebar();
           PROF_T(12);
+          if (gi == 0) {                           // the stem has no per-particle linears of its own after the pooling
+            mbar_arrive(&s.spk_empty);
+            continue;
+          }
           const int l = gi - 1;
-          {   // per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
+          // ---- [E] per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
+          {
             const int La = LIN_LAYER0 + 4 * l + 2, Lb = LIN_LAYER0 + 4 * l + 3;
-            const int o = et & 127;
             float wgl[TC_ZMAX];
 #pragma unroll
-            for (int z = 0; z < TC_ZMAX; ++z) wgl[z] = z < Z ? __bfloat162float(s.spk[1][z][o]) : 0.f;
-            for (int j = et >> 7; j < nj; j += 2) {
-              float acc = unit_bias(La, 128 + ZP, ev, j0 + j, o);
+            for (int z = 0; z < TC_ZMAX; ++z) wgl[z] = z < Z ? __bfloat162float(s.spk.gl[z][r]) : 0.f;
 #pragma unroll
-              for (int z = 0; z < TC_ZMAX; ++z) acc = fmaf(wgl[z], s.gv[j][z], acc);
-              s.bl1[j][o] = acc;
-              s.bl2[j][o] = unit_bias(Lb, 256 + ZP, ev, j0 + j, o);
+            for (int bb = 0; bb < 2; ++bb) {
+              const int jb = (wg + 2 * bb) * 4;
+              if (jb < nj) {          // 4 jets at once: independent accumulator chains (rows >= nj hold zeros / stale finite values)
+                float acc[4], b2v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int jq = (jb + q < nj) ? jb + q : nj - 1;
+                  acc[q] = unit_bias(La, 128 + ZP, j0 + jq, r);
+                  b2v[q] = unit_bias(Lb, 256 + ZP, j0 + jq, r);
+                }
+#pragma unroll
+                for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {
+                  if (z4 * 4 < Z) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float4 g = *reinterpret_cast<const float4*>(&s.gv[jb + q][z4 * 4]);
+                      acc[q] = fmaf(wgl[z4 * 4 + 0], g.x, acc[q]); acc[q] = fmaf(wgl[z4 * 4 + 1], g.y, acc[q]);
+                      acc[q] = fmaf(wgl[z4 * 4 + 2], g.z, acc[q]); acc[q] = fmaf(wgl[z4 * 4 + 3], g.w, acc[q]);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  s.bl1[jb + q][r] = acc[q];
+                  s.bl2[jb + q][r] = b2v[q];
+                }
+              }
             }
           }
           mbar_arrive(&s.spk_empty);               // pack + bias slice of this unit are dead: the producer may refill
@@ -624,13 +696,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           PROF_T(14);
           {
             auto epi1_chunk = [&](uint32_t (&v)[32], int c) {
-              const float4* bj = reinterpret_cast<const float4*>(&s.bl1[myjet][c * 32]);
               uint32_t u16[16];
 #pragma unroll
               for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 b = bj[i4];
-                bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2, valid);
-                bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2, valid);
+                const float4 b = lds128(bl1_addr + (uint32_t)(c * 128 + i4 * 16));
+                bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
+                bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
                 u16[i4 * 2 + 0] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]));
                 u16[i4 * 2 + 1] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 2]), __uint_as_float(v[i4 * 4 + 3]));
               }
@@ -654,6 +725,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           tc_fence_before();
           mbar_arrive(&s.u_ready[wg]);
           PROF_T(15);
+          if (gi < L) compute_pre(gi + 1);         // next unit's [A] while the tensor pipe runs fc_local2
           // ======== fc_local2 epilogue (+ head after the last layer) ========
           const bool last = (l == L - 1);
           if (last) {
@@ -703,7 +775,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     }
   }
   if (PROF && prof_on && p.prof) {
-    const int role = tid == 32 ? 0 : (tid == 128 ? 1 : 2);
+    const int role = prof_role;
     for (int i = 0; i < 20; ++i) p.prof[role * 20 + i] = prof[i];
   }
   tc_fence_before();
@@ -727,18 +799,19 @@ __global__ void pack_images_kernel(const ImgSrc* __restrict__ src, uint8_t* __re
   }
 }
 
-// small-weight pack of unit u (bf16): [0] W_gg[z][o] = fc_global1[o][2H + z]   [1] W_glob[z][o] = fc_local1[o][H + z]
-//                                      [2] W_g2[z][o] = fc_global2[z][o] (fc_g2 for the stem); zero padding to 16 rows
+// small-weight pack of unit u (SpkPack): W_gg[z][o] = fc_global1[o][2H + z], W_glob[z][o] = fc_local1[o][H + z] (bf16),
+// W_g2[z][k] = fc_global2[z][k] (fc_g2 for the stem; fp32); zero padding to 16 rows
 struct SpkSrc { const float* gg; int gg_ldo; const float* gl; int gl_ldo; const float* g2; int g2_ldo; int Z; };
 
-__global__ void pack_spk_kernel(const SpkSrc* __restrict__ src, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_spk_kernel(const SpkSrc* __restrict__ src, SpkPack* __restrict__ out) {
   const SpkSrc S = src[blockIdx.x];
-  __nv_bfloat16* o = out + (size_t)blockIdx.x * (TC_SPK / 2);
+  SpkPack& o = out[blockIdx.x];
   for (int i = threadIdx.x; i < 16 * TCH; i += blockDim.x) {
     const int z = i >> 7, c = i & 127;
-    o[i] = __float2bfloat16((S.gg && z < S.Z) ? S.gg[(size_t)z * S.gg_ldo + c] : 0.f);
-    o[16 * TCH + i] = __float2bfloat16((S.gl && z < S.Z) ? S.gl[(size_t)z * S.gl_ldo + c] : 0.f);
-    o[32 * TCH + i] = __float2bfloat16(z < S.Z ? S.g2[(size_t)c * S.g2_ldo + z] : 0.f);
+    o.gg[z][c] = __float2bfloat16((S.gg && z < S.Z) ? S.gg[(size_t)z * S.gg_ldo + c] : 0.f);
+    o.gl[z][c] = __float2bfloat16((S.gl && z < S.Z) ? S.gl[(size_t)z * S.gl_ldo + c] : 0.f);
+    o.g2[z][c] = z < S.Z ? S.g2[(size_t)c * S.g2_ldo + z] : 0.f;
+    if (c < 4) o.g2[z][TCH + c] = 0.f;
   }
 }
 
@@ -812,7 +885,7 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
   PFM_CUDA_CHECK(cudaMemcpyAsync(dspk, spk.data(), sizeof(SpkSrc) * spk.size(), cudaMemcpyHostToDevice, st));
   PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src / spk are host temporaries
   pack_images_kernel<<<n_items, 256, 0, st>>>(dsrc, base);
-  pack_spk_kernel<<<c.layers + 1, 256, 0, st>>>(dspk, reinterpret_cast<__nv_bfloat16*>(base + img_bytes));
+  pack_spk_kernel<<<c.layers + 1, 256, 0, st>>>(dspk, reinterpret_cast<SpkPack*>(base + img_bytes));
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
@@ -858,14 +931,24 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   const int kmax = a.Kx > c.feats ? a.Kx : c.feats;
   if (getenv("PFM_TC_PROF")) {        // debug: phase timers of block 0, printed after the kernel
     static long long* dprof = nullptr;
-    if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, sizeof(long long) * 60));
-    PFM_CUDA_CHECK(cudaMemsetAsync(dprof, 0, sizeof(long long) * 60, st));
+    const int n_ll = 60 + 3 * TRACE_MAX * 2;
+    if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, sizeof(long long) * n_ll));
+    PFM_CUDA_CHECK(cudaMemsetAsync(dprof, 0, sizeof(long long) * n_ll, st));
     p.prof = dprof;
     int rc = kmax <= 4 ? launch_tc<4, true>(p, grid, st) : launch_tc<8, true>(p, grid, st);
     if (rc != PFM_OK) return rc;
-    long long hp[60];
+    static long long hp[60 + 3 * TRACE_MAX * 2];
     PFM_CUDA_CHECK(cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st));
     PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (getenv("PFM_TC_TRACE")) {
+      long long t0 = 0;
+      for (int r = 0; r < 3; ++r) { const long long t = hp[61 + r * TRACE_MAX * 2]; if (t && (!t0 || t < t0)) t0 = t; }
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < TRACE_MAX; ++i) {
+          const long long slot = hp[60 + (r * TRACE_MAX + i) * 2], t = hp[61 + (r * TRACE_MAX + i) * 2];
+          if (t) fprintf(stderr, "[pfm tc trace] %lld %d %lld\n", t - t0, r, slot);
+        }
+    }
     const char* roles[3] = {"mma", "epiA", "epiB"};
     for (int r = 0; r < 3; ++r) {
       long long tot = 0;
