@@ -134,7 +134,11 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {
       p.prof[61 + (prof_role * TRACE_MAX + trace_n) * 2] = _n; ++trace_n; } } } while (0)
 static constexpr int TRACE_EV = 6, TRACE_MAX = 160;
 
-template <int FP, bool PROF>
+// SIMPLE: one time code for the whole batch and no conditioning (the sampling configuration of the headline
+// workload): every bias comes from the staged slice of the time-bias table, which removes all data-dependent
+// branches from the serial per-jet phases (a uniform branch costs ~30-40 cycles of fetch bubble, and those phases
+// are latency-bound).
+template <int FP, bool PROF, bool SIMPLE>
 __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned view of the dynamic shared memory, derived by pointer arithmetic on the __shared__ array so
@@ -243,7 +247,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         const uint64_t pdesc = desc_kmajor(smem_u32(s.P)), sdesc = desc_kmajor(smem_u32(s.sg.St));
         const uint64_t wdesc0 = desc_kmajor(smem_u32(s.w[0]));
         const uint32_t accH0 = tm, accH1 = tm + 128, accU0 = tm + 256, accU1 = tm + 384;
-        const uint32_t dpool = tm + 384 + 64, dglob = tm + 384 + 80;
+        // pooling / global accumulators: 4 independent 16-column accumulators each (a dependent chain of N=16 MMAs on
+        // ONE accumulator is latency-bound, ~70 cycles per MMA); the readers add the 4 partial results
+        const uint32_t dpool = tm + 384, dglob = tm + 384 + 64;
         auto wait_full = [&](uint32_t it) { mbar_wait(&s.full[it % TC_NSLOT], (it / TC_NSLOT) & 1); };
         auto wslot = [&](uint32_t it) { return wdesc0 + (uint64_t)((it % TC_NSLOT) * (TC_MAT >> 4)); };
         for (int ev = 0; ev < p.n_evals; ++ev) {
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
                   for (int k = 0; k < 8; ++k) {      // 16 rows of h per step: +2 KB in the MN-major view; P: 2 KB per 64 rows
                     const uint64_t da = (t ? hBt : hAt) + (uint64_t)(k * 128);
                     const uint64_t db = pdesc + (uint64_t)((t * 2 + (k >> 2)) * 128 + (k & 3) * 2);
-                    mma_ss(dpool, da, db, idesc_pool, (t | k) ? 1u : 0u);
+                    mma_ss(dpool + (uint32_t)((k & 3) * 16), da, db, idesc_pool, (t | (k >> 2)) ? 1u : 0u);
                   }
                 }
                 __syncwarp();
@@ -297,7 +303,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                  mma_ss(dglob, wd + kstep16(k), sdesc + (uint64_t)((m * 2 + (k >> 2)) * 128 + (k & 3) * 2), idesc_glob, (m | k) ? 1u : 0u);
+                  mma_ss(dglob + (uint32_t)((k & 3) * 16), wd + kstep16(k), sdesc + (uint64_t)((m * 2 + (k >> 2)) * 128 + (k & 3) * 2), idesc_glob,
+                         (m | (k >> 2)) ? 1u : 0u);
               }
               __syncwarp();
             }
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int row = wg * 128 + r;
       const uint32_t lane_base = tm + ((uint32_t)((warp & 3) * 32) << 16);
       const uint32_t accH = lane_base + wg * 128, accU = lane_base + 256 + wg * 128;
-      const uint32_t dpool = lane_base + 384 + 64, dglob = lane_base + 384 + 80;
+      const uint32_t dpool = lane_base + 384, dglob = lane_base + 384 + 64;
       uint8_t* hrow = s.h[wg] + (r >> 3) * 1024 + (r & 7) * 128;       // this particle's 128-byte swizzled row (per 64-col block)
 
       if (et == 0) {
@@ -378,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
       // slow direct path when every jet has its own time (training-style forward)
       auto unit_bias = [&](int lin_idx, int voff, int jet_global, int o) -> float {
+        if (SIMPLE) return s.sbias[voff + o];
         float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o] : s.sbias[voff + o];
         if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o];
         return b;
@@ -398,8 +406,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
       const int ZP = (Z + 3) & ~3;
 
+      const uint32_t w3_addr = smem_u32(&s.w3s[0][0]), st_addr = smem_u32(s.sg.St);
+
       // store 32 fp32 columns [32c, 32c+32) of this particle's row as bf16 into the swizzled h tile
-      auto store_h_bf16 = [&](const uint32_t (&v)[32], int c) {
+      auto store_h_bf16 = [&](const uint32_t (&v)[32], int c, uint32_t pred) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 pk;
@@ -408,10 +418,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           pk.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
           pk.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
           const int c16 = c * 4 + q;
-          sts128_if(hrow_addr + (uint32_t)((c16 >> 3) * 16384) + ((uint32_t)((c16 & 7) << 4) ^ rx16), pk.x, pk.y, pk.z, pk.w, vpred);
+          sts128_if(hrow_addr + (uint32_t)((c16 >> 3) * 16384) + ((uint32_t)((c16 & 7) << 4) ^ rx16), pk.x, pk.y, pk.z, pk.w, pred);
         }
       };
+      // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16
+      auto epi_h_chunk = [&](uint32_t (&v)[32], int c, uint32_t spred) {
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b = lds128(bl2_addr + (uint32_t)(c * 128 + i4 * 16));
+          bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
+          bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
+        }
+        tmem_st32(accH + c * 32, v);
+        store_h_bf16(v, c, spred);
+      };
+      // one 32-column chunk of the fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM
+      auto epi1_chunk = [&](uint32_t (&v)[32], int c) {
+        uint32_t u16[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b = lds128(bl1_addr + (uint32_t)(c * 128 + i4 * 16));
+          bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
+          bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
+          u16[i4 * 2 + 0] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]));
+          u16[i4 * 2 + 1] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 2]), __uint_as_float(v[i4 * 4 + 3]));
+        }
+        tmem_st16(accU + c * 16, u16);        // columns [16c, 16c+16) were already read (16c+16 <= 32c+32)
+      };
 
+      // NOTE on code size: the layer loop below is deliberately kept compact (chunk loops rolled, one call site per
+      // epilogue, head outside the loop).  With 12 warps at different program counters the instruction cache is a
+      // first-order resource: the fully unrolled version of this loop body (~50 KB of SASS) ran ~4x slower per
+      // instruction than this one in the serial per-jet phases.
       for (int ev = 0; ev < p.n_evals; ++ev) {
         // ---------------- unit 0 pack (stem biases + fc_g2) has landed; per-jet stem biases ----------------
         PROF_T(0);
@@ -422,8 +460,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int f = 0; f < FP; ++f) {
           b3[f] = 0.f;
           if (f < F) {
-            b3[f] = p.tbias[(size_t)(p.tbias_per_jet ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
-            if (p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
+            b3[f] = p.tbias[(size_t)((!SIMPLE && p.tbias_per_jet) ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
+            if (!SIMPLE && p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
           }
         }
         const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
@@ -456,71 +494,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             }
           }
           tmem_st32(accH + c * 32, v);
-          store_h_bf16(v, c);
+          store_h_bf16(v, c, vpred);
         }
         tmem_wait_st();
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&s.hready[wg]);
         PROF_T(2);
-
-        // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16 (+ head)
-        auto epi_h_chunk = [&](uint32_t (&v)[32], int c, bool write_back, bool head) {
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 b = lds128(bl2_addr + (uint32_t)(c * 128 + i4 * 16));
-            bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
-            bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
-          }
-          if (head) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float a = __uint_as_float(v[i]);
-              if (FP == 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(&s.w3s[c * 32 + i][0]);
-                vout[0] = fmaf(w4.x, a, vout[0]); vout[1] = fmaf(w4.y, a, vout[1]); vout[2] = fmaf(w4.z, a, vout[2]);
-                vout[3] = fmaf(w4.w, a, vout[3]);
-              } else {
-#pragma unroll
-                for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
-              }
-            }
-          }
-          if (write_back) {
-            tmem_st32(accH + c * 32, v);
-            store_h_bf16(v, c);
-          }
-        };
-        // residual update epilogue shared by the stem's fc_l2 and every fc_local2; the TMEM load of chunk c+1 is in
-        // flight while chunk c is processed (tcgen05.wait::ld covers all outstanding loads, so issue after the wait)
-        auto epi_h = [&](bool write_back, bool head) {
-          PROF_T(0);
-          mbar_wait(&s.accH_full[wg], c_accH++ & 1);
-          tc_fence_after();
-          PROF_T(3);
-          uint32_t va[32], vb[32];
-          tmem_ld32(accH, va);
-          tmem_wait_ld();
-          tmem_ld32(accH + 32, vb);
-          epi_h_chunk(va, 0, write_back, head);
-          tmem_wait_ld();
-          tmem_ld32(accH + 64, va);
-          epi_h_chunk(vb, 1, write_back, head);
-          tmem_wait_ld();
-          tmem_ld32(accH + 96, vb);
-          epi_h_chunk(va, 2, write_back, head);
-          tmem_wait_ld();
-          epi_h_chunk(vb, 3, write_back, head);
-          PROF_T(4);
-          if (write_back) {
-            tmem_wait_st();
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&s.hready[wg]);
-          }
-          PROF_T(18);
-        };
-        epi_h(true, false);                        // stem fc_l2 (+ residual h1)
 
         // [A] (off the critical path) pre[j] = bias_g1[o] + W_gg[o] . g_prev[j] of unit gi, for this thread's jets;
         // waits for the unit's small-weight pack first
@@ -538,11 +518,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             for (int q = 0; q < 4; ++q) pre[bb][q] = 0.f;
             if (jb < nj) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) pre[bb][q] = (jb + q < nj) ? unit_bias(Ga, off_ga, j0 + jb + q, r) : 0.f;
+              for (int q = 0; q < 4; ++q) pre[bb][q] = (SIMPLE || jb + q < nj) ? unit_bias(Ga, off_ga, j0 + jb + q, r) : 0.f;
               if (gi >= 1) {
 #pragma unroll
-                for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {
-                  if (z4 * 4 < Z) {
+                for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {       // rows z >= Z of the pack are zero: no bound check
+                  {
                     float w[4];
 #pragma unroll
                     for (int zz = 0; zz < 4; ++zz) w[zz] = __bfloat162float(s.spk.gg[z4 * 4 + zz][r]);
@@ -566,12 +546,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 #pragma unroll
           for (int q = 0; q < 4; ++q) sreg[bb][q] = 0.f;
 
-        for (int gi = 0; gi <= L; ++gi) {
+        compute_pre(0);
+#pragma unroll 1
+        for (int gi = 0;; ++gi) {
+          // ======== residual update epilogue of the h version unit gi pools: the stem's fc_l2 (gi = 0), fc_local2 of layer
+          // gi-2 (gi >= 2; layer 0 pools the same h as the stem, so nothing at gi = 1); gi = L+1: the last layer's.
+          // The TMEM load of chunk c+1 is in flight while chunk c is processed.
+          if (gi != 1) {
+            const bool last = gi == L + 1;
+            PROF_T(0);
+            mbar_wait(&s.accH_full[wg], c_accH++ & 1);
+            tc_fence_after();
+            PROF_T(3);
+            uint32_t va[32], vb[32];
+            const uint32_t spred = last ? 0u : vpred;
+            tmem_ld32(accH, va);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              tmem_wait_ld();
+              tmem_ld32(accH + cc * 64 + 32, vb);
+              epi_h_chunk(va, 2 * cc, spred);
+              tmem_wait_ld();
+              if (cc == 0) tmem_ld32(accH + 64, va);
+              epi_h_chunk(vb, 2 * cc + 1, spred);
+            }
+            PROF_T(4);
+            tmem_wait_st();
+            if (last) break;
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&s.hready[wg]);
+            PROF_T(18);
+          }
           // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
           // Per-jet work is split over the 256 threads as (o = r) x (batches of 4 jets: wg, wg + 2).
           const int Gb = gi == 0 ? LIN_G2 : LIN_LAYER0 + 4 * (gi - 1) + 1;
           const int off_gb = gi == 0 ? 384 : 128;                                 // slice offset inside sbias
-          if (gi <= 1) compute_pre(gi);            // later units: computed while fc_local2 of the previous layer runs
           // ---- [B] pooled sums -> pre-scaled bf16 B operand  St[j][0:128) = S/n (mean), St[j][128:256) = S*s (sum)
           if (gi != 1) {
             mbar_wait(&s.pool_full, c_pool++ & 1);
@@ -581,11 +591,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             for (int bb = 0; bb < 2; ++bb) {
               const int jb = (wg + 2 * bb) * 4;
               if (jb < nj) {
-                uint32_t v[4];
-                tmem_ld4(dpool + jb, v);
+                uint32_t v0[4], v1[4], v2[4], v3[4];
+                tmem_ld4(dpool + jb, v0); tmem_ld4(dpool + 16 + jb, v1); tmem_ld4(dpool + 32 + jb, v2); tmem_ld4(dpool + 48 + jb, v3);
                 tmem_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sreg[bb][q] = __uint_as_float(v[q]);
+                for (int q = 0; q < 4; ++q)
+                  sreg[bb][q] = (__uint_as_float(v0[q]) + __uint_as_float(v1[q])) + (__uint_as_float(v2[q]) + __uint_as_float(v3[q]));
               }
             }
           }
@@ -596,8 +607,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int j = jb + q;
-                *reinterpret_cast<__nv_bfloat16*>(s.sg.St + sw128_offset(j, r, 2048)) = __float2bfloat16(sreg[bb][q] * s.inv_n[j]);
-                *reinterpret_cast<__nv_bfloat16*>(s.sg.St + sw128_offset(j, 128 + r, 2048)) = __float2bfloat16(sreg[bb][q] * p.sum_scale);
+                const uint32_t a = st_addr + sw128_offset(j, r, 2048);       // (j, k = r); (j, k = 128 + r) is 4 KB further
+                const __nv_bfloat16 m = __float2bfloat16(sreg[bb][q] * s.inv_n[j]), sm = __float2bfloat16(sreg[bb][q] * p.sum_scale);
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&m)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + 4096u), "h"(*reinterpret_cast<const unsigned short*>(&sm)) : "memory");
               }
             }
           }
@@ -614,75 +627,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           for (int bb = 0; bb < 2; ++bb) {
             const int jb = (wg + 2 * bb) * 4;
             if (jb < nj) {
-              uint32_t v[4];
-              tmem_ld4(dglob + jb, v);
+              uint32_t v0[4], v1[4], v2[4], v3[4];
+              tmem_ld4(dglob + jb, v0); tmem_ld4(dglob + 16 + jb, v1); tmem_ld4(dglob + 32 + jb, v2); tmem_ld4(dglob + 48 + jb, v3);
               tmem_wait_ld();
 #pragma unroll
-              for (int q = 0; q < 4; ++q) s.sg.g1[jb + q][r] = lrelu_tc(__uint_as_float(v[q]) + pre[bb][q], p.slope);
+              for (int q = 0; q < 4; ++q) {
+                const float d = (__uint_as_float(v0[q]) + __uint_as_float(v1[q])) + (__uint_as_float(v2[q]) + __uint_as_float(v3[q]));
+                s.sg.g1[jb + q][r] = lrelu_tc(d + pre[bb][q], p.slope);
+              }
             }
           }
           tc_fence_before();
           mbar_arrive(&s.d_free);
           ebar();
           PROF_T(10);
-          // ---- [D] fc_g2 / fc_global2 (+ residual for the layers): warp = jet, lane = (k half, z); K = 2 x 64
-          for (int j = (et >> 5); j < nj; j += 8) {
-            const int lane_ = et & 31, z = lane_ & 15, kh = lane_ >> 4;
-            const int zc = z < Z ? z : 0;
-            const uint32_t wa = smem_u32(&s.spk.g2[zc][kh * 64]), ga = smem_u32(&s.sg.g1[j][kh * 64]);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float4 w = lds128(wa + k * 16), g = lds128(ga + k * 16);
-              a0 = fmaf(w.x, g.x, a0); a1 = fmaf(w.y, g.y, a1); a2 = fmaf(w.z, g.z, a2); a3 = fmaf(w.w, g.w, a3);
-            }
-            float acc = (a0 + a1) + (a2 + a3);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (kh == 0 && z < Z) {
-              acc += unit_bias(Gb, off_gb, j0 + j, z);
-              if (gi >= 1) acc += s.gv[j][z];
-              s.gv[j][z] = lrelu_tc(acc, p.slope);
-            }
-          }
-          ebar();
-          PROF_T(12);
-          if (gi == 0) {                           // the stem has no per-particle linears of its own after the pooling
-            mbar_arrive(&s.spk_empty);
-            continue;
-          }
-          const int l = gi - 1;
-          // ---- [E] per-jet biases of fc_local1 (incl. W_glob . g) and fc_local2
+          // ---- [D+E] one warp per jet, no block barrier in between:
+          //   fc_g2 / fc_global2 (+ residual for the layers): lane = (k half, z), K = 2 x 64, one shuffle;
+          //   then the jet's biases of fc_local1 (incl. W_glob . g, g broadcast by shuffles) and fc_local2
           {
+            const int l = gi - 1;
             const int La = LIN_LAYER0 + 4 * l + 2, Lb = LIN_LAYER0 + 4 * l + 3;
-            float wgl[TC_ZMAX];
+            for (int j = (et >> 5); j < nj; j += 8) {
+              const int lane_ = et & 31, z = lane_ & 15, kh = lane_ >> 4;
+              const int zc = z < Z ? z : Z - 1;
+              const uint32_t wa = smem_u32(&s.spk.g2[zc][kh * 64]), ga = smem_u32(&s.sg.g1[j][kh * 64]);
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int z = 0; z < TC_ZMAX; ++z) wgl[z] = z < Z ? __bfloat162float(s.spk.gl[z][r]) : 0.f;
+              for (int k = 0; k < 16; ++k) {
+                const float4 w = lds128(wa + k * 16), g = lds128(ga + k * 16);
+                a0 = fmaf(w.x, g.x, a0); a1 = fmaf(w.y, g.y, a1); a2 = fmaf(w.z, g.z, a2); a3 = fmaf(w.w, g.w, a3);
+              }
+              float acc = (a0 + a1) + (a2 + a3);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+              acc += unit_bias(Gb, off_gb, j0 + j, zc);
+              if (gi >= 1) acc += s.gv[j][zc];
+              const float gz = z < Z ? lrelu_tc(acc, p.slope) : 0.f;
+              __syncwarp();                        // every lane has read the old g before it is overwritten
+              if (kh == 0 && z < Z) s.gv[j][z] = gz;
+              if (gi >= 1) {
+                float b1v[4], b2v[4];
 #pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              const int jb = (wg + 2 * bb) * 4;
-              if (jb < nj) {          // 4 jets at once: independent accumulator chains (rows >= nj hold zeros / stale finite values)
-                float acc[4], b2v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int jq = (jb + q < nj) ? jb + q : nj - 1;
-                  acc[q] = unit_bias(La, 128 + ZP, j0 + jq, r);
-                  b2v[q] = unit_bias(Lb, 256 + ZP, j0 + jq, r);
+                for (int i = 0; i < 4; ++i) {
+                  b1v[i] = unit_bias(La, 128 + ZP, j0 + j, lane_ + 32 * i);
+                  b2v[i] = unit_bias(Lb, 256 + ZP, j0 + j, lane_ + 32 * i);
                 }
 #pragma unroll
-                for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {
-                  if (z4 * 4 < Z) {
+                for (int zz = 0; zz < TC_ZMAX; ++zz) {           // rows zz >= Z of W_glob are zero and gz is 0 there
+                  {
+                    const float g = __shfl_sync(0xffffffffu, gz, zz);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const float4 g = *reinterpret_cast<const float4*>(&s.gv[jb + q][z4 * 4]);
-                      acc[q] = fmaf(wgl[z4 * 4 + 0], g.x, acc[q]); acc[q] = fmaf(wgl[z4 * 4 + 1], g.y, acc[q]);
-                      acc[q] = fmaf(wgl[z4 * 4 + 2], g.z, acc[q]); acc[q] = fmaf(wgl[z4 * 4 + 3], g.w, acc[q]);
-                    }
+                    for (int i = 0; i < 4; ++i) b1v[i] = fmaf(__bfloat162float(s.spk.gl[zz][lane_ + 32 * i]), g, b1v[i]);
                   }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  s.bl1[jb + q][r] = acc[q];
-                  s.bl2[jb + q][r] = b2v[q];
+                for (int i = 0; i < 4; ++i) {
+                  s.bl1[j][lane_ + 32 * i] = b1v[i];
+                  s.bl2[j][lane_ + 32 * i] = b2v[i];
                 }
               }
             }
@@ -690,49 +690,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           mbar_arrive(&s.spk_empty);               // pack + bias slice of this unit are dead: the producer may refill
           ebar();
           PROF_T(13);
-          // ======== fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM ========
-          mbar_wait(&s.accU_full[wg], c_accU++ & 1);
-          tc_fence_after();
-          PROF_T(14);
-          {
-            auto epi1_chunk = [&](uint32_t (&v)[32], int c) {
-              uint32_t u16[16];
-#pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 b = lds128(bl1_addr + (uint32_t)(c * 128 + i4 * 16));
-                bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
-                bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
-                u16[i4 * 2 + 0] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]));
-                u16[i4 * 2 + 1] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 2]), __uint_as_float(v[i4 * 4 + 3]));
-              }
-              tmem_st16(accU + c * 16, u16);        // columns [16c, 16c+16) were already read (16c+16 <= 32c+32)
-            };
+          if (gi >= 1) {
+            // ======== fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM ========
+            mbar_wait(&s.accU_full[wg], c_accU++ & 1);
+            tc_fence_after();
+            PROF_T(14);
             uint32_t va[32], vb[32];
             tmem_ld32(accU, va);
-            tmem_wait_ld();
-            tmem_ld32(accU + 32, vb);
-            epi1_chunk(va, 0);
-            tmem_wait_ld();
-            tmem_ld32(accU + 64, va);
-            epi1_chunk(vb, 1);
-            tmem_wait_ld();
-            tmem_ld32(accU + 96, vb);
-            epi1_chunk(va, 2);
-            tmem_wait_ld();
-            epi1_chunk(vb, 3);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(&s.u_ready[wg]);
-          PROF_T(15);
-          if (gi < L) compute_pre(gi + 1);         // next unit's [A] while the tensor pipe runs fc_local2
-          // ======== fc_local2 epilogue (+ head after the last layer) ========
-          const bool last = (l == L - 1);
-          if (last) {
 #pragma unroll
-            for (int f = 0; f < FP; ++f) vout[f] = 0.f;
+            for (int cc = 0; cc < 2; ++cc) {
+              tmem_wait_ld();
+              tmem_ld32(accU + cc * 64 + 32, vb);
+              epi1_chunk(va, 2 * cc);
+              tmem_wait_ld();
+              if (cc == 0) tmem_ld32(accU + 64, va);
+              epi1_chunk(vb, 2 * cc + 1);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&s.u_ready[wg]);
+            PROF_T(15);
           }
-          epi_h(!last, last);
+          if (gi < L) compute_pre(gi + 1);         // next unit's [A] while the tensor pipe runs fc_local2
+        }
+        // ---------------- head fc_l3 on CUDA cores: h_L (fp32) is re-read from TMEM ----------------
+#pragma unroll
+        for (int f = 0; f < FP; ++f) vout[f] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(accH + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(v[i]);
+            if (FP == 4) {
+              const float4 w4 = lds128(w3_addr + (uint32_t)((c * 32 + i) * 16));
+              vout[0] = fmaf(w4.x, a, vout[0]); vout[1] = fmaf(w4.y, a, vout[1]); vout[2] = fmaf(w4.z, a, vout[2]);
+              vout[3] = fmaf(w4.w, a, vout[3]);
+            } else {
+#pragma unroll
+              for (int f = 0; f < FP; ++f) vout[f] = fmaf(s.w3s[c * 32 + i][f], a, vout[f]);
+            }
+          }
         }
         // ---------------- head bias + activation, integrator step (thread-local) ----------------
 #pragma unroll
@@ -890,9 +890,9 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
   return PFM_OK;
 }
 
-template <int FP, bool PROF>
+template <int FP, bool PROF, bool SIMPLE>
 static int launch_tc(const TcParams& p, int grid, cudaStream_t st) {
-  auto kern = epic_tc_kernel<FP, PROF>;
+  auto kern = epic_tc_kernel<FP, PROF, SIMPLE>;
   const int smem = (int)sizeof(TcSmem<FP>) + 1024;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, TC_THREADS, smem, st>>>(p);
@@ -929,13 +929,15 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;
   const int kmax = a.Kx > c.feats ? a.Kx : c.feats;
+  const bool simple = !p.tbias_per_jet && !p.cbias;
   if (getenv("PFM_TC_PROF")) {        // debug: phase timers of block 0, printed after the kernel
     static long long* dprof = nullptr;
     const int n_ll = 60 + 3 * TRACE_MAX * 2;
     if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, sizeof(long long) * n_ll));
     PFM_CUDA_CHECK(cudaMemsetAsync(dprof, 0, sizeof(long long) * n_ll, st));
     p.prof = dprof;
-    int rc = kmax <= 4 ? launch_tc<4, true>(p, grid, st) : launch_tc<8, true>(p, grid, st);
+    int rc = kmax <= 4 ? (simple ? launch_tc<4, true, true>(p, grid, st) : launch_tc<4, true, false>(p, grid, st))
+                       : launch_tc<8, true, false>(p, grid, st);
     if (rc != PFM_OK) return rc;
     static long long hp[60 + 3 * TRACE_MAX * 2];
     PFM_CUDA_CHECK(cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st));
@@ -959,8 +961,8 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
     }
     return PFM_OK;
   }
-  if (kmax <= 4) return launch_tc<4, false>(p, grid, st);
-  return launch_tc<8, false>(p, grid, st);
+  if (kmax <= 4) return simple ? launch_tc<4, false, true>(p, grid, st) : launch_tc<4, false, false>(p, grid, st);
+  return simple ? launch_tc<8, false, true>(p, grid, st) : launch_tc<8, false, false>(p, grid, st);
 }
 
 }  // namespace pfm
