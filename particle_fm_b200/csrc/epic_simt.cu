@@ -31,6 +31,9 @@ struct SimtParams {
   float* yact;                                              // yact[row][Kx]   network input of every real particle
   float* jact; int junit; int jstride; int LDP_act;         // jact[jet][unit][pool input (LDP) | g1 (Hp) | g]
   float* dpre3; float* loss_acc; const int* rowoff; const int* n_total;
+  // spill mode (jets too large for shared memory, e.g. LHCO 279 x H150): the hidden features live in a per-CTA slab
+  // of global memory (L2-resident) instead of shared memory; everything else is unchanged
+  float* hs_spill;
   // shared-memory carve-up (float offsets)
   int o_xs, o_x0, o_hs, o_tmp, o_wbuf, o_pool, o_g, o_g1, o_bl1, o_bl2, o_v, o_int, total_floats;
   int wbuf_floats, LDB, LDP;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
   extern __shared__ __align__(16) float smem[];
   float* xs = smem + p.o_xs;      // [R_cap, LDX]   current network input (state or midpoint state)
   float* x0 = smem + p.o_x0;      // [R_cap, F]     state at the start of the step
-  float* hs = smem + p.o_hs;      // [R_cap, LDH]
+  float* hs = p.hs_spill ? p.hs_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_hs;      // [R_cap, LDH]
   float* tmp = smem + p.o_tmp;    // [8*RB, LDH]
   float* wbuf = smem + p.o_wbuf;  // 2 stages
   float* pool = smem + p.o_pool;  // [J_cap, LDP]   (LDP >= 2H + Z)
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct SimtShape { int TC, RB, KC, R_cap, J_cap; SimtParams p; size_t smem; };
+struct SimtShape { int TC, RB, KC, R_cap, J_cap; bool spill; SimtParams p; size_t smem; };
 
 static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_force = 0, int J_cap_force = 0) {
   const pfm_epic_cfg& c = h->cfg;
@@ -426,11 +429,23 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_
     if (R_cap >= N || KC == 8) break;
     KC = 8;
   }
+  bool spill = false;
   if (R_cap < N) {
-    set_error("fp32 path: a jet of %d particles does not fit the shared-memory row budget (%d rows at hid=%d)", N,
-              R_cap, H);
-    return PFM_ERR_UNSUPPORTED;
+    // spill mode: hs moves to global memory; the remaining per-row state is tiny
+    spill = true;
+    const int wbuf = s->KC * ldo_max + 32 * s->TC + 32;
+    const int per_jet = LDP + Z + Hp + 2 * LDB;
+    const int fixed = CR * LDH + 2 * wbuf + J_cap * per_jet + (J_cap + 8) + 64;
+    const int per_row = LDX + 2 * F + 1;
+    R_cap = (budget - fixed) / per_row;
+    const int want = N > 512 ? N : 512;
+    if (R_cap > want) R_cap = want;
+    if (R_cap < N) {
+      set_error("fp32 path: a jet of %d particles does not fit even in spill mode (%d rows at hid=%d)", N, R_cap, H);
+      return PFM_ERR_UNSUPPORTED;
+    }
   }
+  s->spill = spill;
   if (R_cap > 1024) R_cap = 1024;
   if (R_cap_force > 0) {          // training: forward and backward kernels share one plan
     if (R_cap_force > R_cap || J_cap_force > J_cap) { set_error("internal: forced group capacity exceeds the forward plan"); return PFM_ERR_INVALID; }
@@ -448,7 +463,7 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   p.o_xs = take(R_cap * LDX);
   p.o_x0 = take(R_cap * F);
-  p.o_hs = take(R_cap * LDH);
+  p.o_hs = spill ? 0 : take(R_cap * LDH);
   p.o_tmp = take(CR * LDH);
   p.o_wbuf = take(2 * p.wbuf_floats);
   p.o_pool = take(J_cap * LDP);
@@ -476,6 +491,20 @@ int simt_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap) {
   return PFM_OK;
 }
 
+static int ensure_spill(pfm_epic* h, SimtShape& s, int grid) {
+  s.p.hs_spill = nullptr;
+  if (!s.spill) return PFM_OK;
+  const size_t need = (size_t)grid * s.R_cap * s.p.LDH;
+  if (need > h->hs_spill_cap) {
+    if (h->hs_spill) cudaFree(h->hs_spill);
+    h->hs_spill = nullptr; h->hs_spill_cap = 0;
+    PFM_CUDA_CHECK(cudaMalloc(&h->hs_spill, sizeof(float) * need));
+    h->hs_spill_cap = need;
+  }
+  s.p.hs_spill = h->hs_spill;
+  return PFM_OK;
+}
+
 template <int TC, int RB, bool TRAIN>
 static int launch_simt(const pfm_epic* h, const SimtShape& s, int grid, cudaStream_t st) {
   auto kern = epic_simt_kernel<TC, RB, TRAIN>;
@@ -500,6 +529,8 @@ int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   // persistent CTAs: one per SM, but never more than there can be groups (every group has >= 1 jet)
   int grid = h->sm_count < a.B ? h->sm_count : a.B;
+  rc = ensure_spill(h, s, grid);
+  if (rc != PFM_OK) return rc;
   if (s.TC == 4) return launch_simt<4, 8, false>(h, s, grid, st);
   if (s.TC == 5) return launch_simt<5, 8, false>(h, s, grid, st);
   return launch_simt<10, 4, false>(h, s, grid, st);
@@ -525,6 +556,8 @@ int simt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   p.jact = h->jact; p.junit = a.lay.junit; p.jstride = a.lay.jstride; p.LDP_act = a.lay.LDP;
   p.dpre3 = h->dpre3; p.loss_acc = h->loss_acc; p.rowoff = h->plan.rowoff; p.n_total = h->plan.n_total;
   int grid = h->sm_count < a.B ? h->sm_count : a.B;
+  rc = ensure_spill(h, s, grid);
+  if (rc != PFM_OK) return rc;
   if (s.TC == 4) return launch_simt<4, 8, true>(h, s, grid, st);
   if (s.TC == 5) return launch_simt<5, 8, true>(h, s, grid, st);
   return launch_simt<10, 4, true>(h, s, grid, st);

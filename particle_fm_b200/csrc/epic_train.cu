@@ -40,6 +40,7 @@ struct BwdParams {
   const float* dpre3;
   float* dbeff; int bstride;
   float* dxs;                 // [rows, Kx] or nullptr
+  float* dh_spill;            // spill mode: dh lives in a per-CTA slab of global memory
   int o_dh, o_tA, o_tB, o_wbuf, o_db1, o_db2, o_dG, o_pg1, o_pg2, o_din, o_int, total_floats;
   int wbuf_floats;
 };
@@ -178,7 +179,7 @@ __device__ __forceinline__ void global_backward(const BwdParams& p, const Lin& G
 template <int TC, int RB>
 __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* dh = smem + p.o_dh;       // [R_cap, LDH]  gradient w.r.t. the hidden features entering the current unit
+  float* dh = p.dh_spill ? p.dh_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_dh;       // [R_cap, LDH]  gradient w.r.t. the hidden features entering the current unit
   float* tA = smem + p.o_tA;       // [8*RB, LDH]   chunk of pre-activation gradients (A operand)
   float* tB = smem + p.o_tB;       // [8*RB, LDH]
   float* wbuf = smem + p.o_wbuf;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ job
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct BwdShape { int TC, RB; BwdParams p; size_t smem; };
+struct BwdShape { int TC, RB; bool spill; BwdParams p; size_t smem; };
 
 static int bwd_plan(const pfm_epic* h, int N, int TC, int RB, int KC, int J_cap, int R_cap_force, BwdShape* s) {
   const pfm_epic_cfg& c = h->cfg;
@@ -449,6 +450,13 @@ static int bwd_plan(const pfm_epic* h, int N, int TC, int RB, int KC, int J_cap,
   const int fixed = 2 * CR * LDH + 2 * wbuf + J_cap * per_jet + (J_cap + 8) + 64;
   int R_cap = (budget - fixed) / (LDH + 1);
   if (R_cap > 1024) R_cap = 1024;
+  bool spill = false;
+  if (R_cap < N || (R_cap_force > 0 && R_cap_force > R_cap)) {     // spill mode: dh in global memory
+    spill = true;
+    R_cap = (budget - fixed) / 1;
+    const int want = N > 512 ? N : 512;
+    if (R_cap > want) R_cap = want;
+  }
   if (R_cap_force > 0) {
     if (R_cap_force > R_cap) { set_error("internal: backward plan smaller than the forced capacity"); return PFM_ERR_INVALID; }
     R_cap = R_cap_force;
@@ -458,6 +466,7 @@ static int bwd_plan(const pfm_epic* h, int N, int TC, int RB, int KC, int J_cap,
               N, R_cap, H);
     return PFM_ERR_UNSUPPORTED;
   }
+  s->spill = spill;
   s->TC = TC; s->RB = RB;
   BwdParams& p = s->p;
   memset(&p, 0, sizeof(p));
@@ -467,7 +476,7 @@ static int bwd_plan(const pfm_epic* h, int N, int TC, int RB, int KC, int J_cap,
   p.wbuf_floats = wbuf;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  p.o_dh = take(R_cap * LDH);
+  p.o_dh = spill ? 0 : take(R_cap * LDH);
   p.o_tA = take(CR * LDH);
   p.o_tB = take(CR * LDH);
   p.o_wbuf = take(2 * wbuf);
@@ -538,6 +547,17 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   p.dpre3 = h->dpre3;
   p.dbeff = h->dbeff; p.bstride = h->bstride;
   p.dxs = a.want_dx ? h->dxs : nullptr;
+  p.dh_spill = nullptr;
+  if (s.spill) {
+    const size_t need = (size_t)(h->sm_count < a.B ? h->sm_count : a.B) * p.R_cap * p.LDH;
+    if (need > h->dh_spill_cap) {
+      if (h->dh_spill) cudaFree(h->dh_spill);
+      h->dh_spill = nullptr; h->dh_spill_cap = 0;
+      PFM_CUDA_CHECK(cudaMalloc(&h->dh_spill, sizeof(float) * need));
+      h->dh_spill_cap = need;
+    }
+    p.dh_spill = h->dh_spill;
+  }
   reset_counter_kernel<<<1, 1, 0, st>>>(h->plan.counter);
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;
   if (TC == 4) rc = launch_bwd<4, 8>(s, grid, st);

@@ -424,6 +424,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->act = nullptr; h->act_cap = 0; h->dact = nullptr; h->dact_cap = 0; h->yact = nullptr; h->yact_cap = 0;
   h->jact = nullptr; h->jact_cap = 0; h->dpre3 = nullptr; h->dpre3_cap = 0;
   h->dbeff = nullptr; h->dbeff_cap = 0; h->dxs = nullptr; h->dxs_cap = 0; h->loss_acc = nullptr; h->ones = nullptr;
+  h->hs_spill = nullptr; h->hs_spill_cap = 0; h->dh_spill = nullptr; h->dh_spill_cap = 0;
   h->jobs_dev = nullptr; h->jobs_cap = 0; h->train_B = 0; h->train_N = 0; h->train_Kx = 0; h->train_xin_off = 0;
   h->tbias = nullptr; h->tbias_cap = 0; h->cbias = nullptr; h->cbias_cap = 0;
   memset(&h->plan, 0, sizeof(h->plan));
@@ -489,6 +490,8 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->dxs) cudaFree(h->dxs);
   if (h->ones) cudaFree(h->ones);
   if (h->jobs_dev) cudaFree(h->jobs_dev);
+  if (h->hs_spill) cudaFree(h->hs_spill);
+  if (h->dh_spill) cudaFree(h->dh_spill);
   if (h->jact) cudaFree(h->jact);
   if (h->dpre3) cudaFree(h->dpre3);
   if (h->dbeff) cudaFree(h->dbeff);

@@ -73,6 +73,8 @@ struct pfm_epic {
   float* dpre3; size_t dpre3_cap;   // gradient at the head pre-activation [rows, F]
   float* dbeff; size_t dbeff_cap;   // gradient of the per-jet effective biases [B, bstride]
   float* dxs; size_t dxs_cap;       // gradient w.r.t. the per-particle input   [rows, Kx]
+  float* hs_spill; size_t hs_spill_cap;   // spill slabs of the fp32 kernels (hidden features of jets too large for smem)
+  float* dh_spill; size_t dh_spill_cap;
   float* loss_acc;                  // [1] sum of squared errors
   float* ones;                      // [1] = 1.0f (the "input" of a bias in the weight-gradient jobs)
   void* jobs_dev; size_t jobs_cap;  // device copy of the weight-gradient job table
