@@ -151,6 +151,48 @@ int pfm_epic_forward_train(pfm_epic* h, const float* t_code, int t_rows, const f
 int pfm_epic_backward(pfm_epic* h, const float* t_code, int t_rows, const float* cond,
                       const float* grad_out, float* grad_x, float* grad_flat, int B, int N, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * PC-Droid-style set transformers (fp32 path):
+ *   pfm_tf_forward  <- FullTransformerEncoder.forward     components/droid_transformer.py:529-548
+ *                      FullCrossAttentionEncoder.forward   components/droid_transformer.py:696-711
+ *                      behind CNF.forward                  flow_matching_module.py:148-161, :191-204
+ *   pfm_tf_sample   <- CNF.decode (euler / midpoint) with those networks, state resident on the device
+ * Padding is skipped (only keys are masked in the reference, every other op is per token); the padded
+ * slots of the result are 0 (the reference leaves unmasked values there that its callers multiply away).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t kind;              /* 0 = FullTransformerEncoder, 1 = FullCrossAttentionEncoder              */
+  int32_t feats;             /* particle features = outp_dim                                            */
+  int32_t t_dim;             /* width of the time code = 2*frequencies                                  */
+  int32_t cond_dim;          /* global_cond_dim (context = [time code, cond])                           */
+  int32_t add_time_to_input; /* time code also concatenated to every particle (True in the YAMLs)       */
+  int32_t model_dim, num_layers, num_heads;
+  int32_t ctxt_out;          /* ctxt_embd_config.outp_dim (64)                                          */
+  int32_t embd_hddn;         /* hidden width of the node / ctxt / outp embedders (2*model_dim)          */
+  int32_t dense_hddn;        /* hidden width of the per-layer feed-forward nets                         */
+  int32_t num_tokens;        /* learned global tokens of the cross-attention encoder (4)                */
+  float neg_slope;           /* nn.LeakyReLU(0.1), get_act("lrlu")                                      */
+  float ln_eps;              /* nn.LayerNorm eps (1e-5)                                                 */
+} pfm_tf_cfg;
+
+typedef struct pfm_tf pfm_tf;
+
+int pfm_tf_create(const pfm_tf_cfg* cfg, int device, pfm_tf** out);
+void pfm_tf_destroy(pfm_tf* h);
+/* Parameter tensors in the canonical order = the reference's state_dict order of CNF.net restricted to
+ * parameters (ctxt_emdb, te.* / cae.*, node_embd, outp_embd); matrices are row-major [rows, cols],
+ * vectors have cols == 1.  pfm_tf_set_weights takes n device pointers in that order. */
+int pfm_tf_num_params(const pfm_tf* h);
+int pfm_tf_param_shape(const pfm_tf* h, int i, int32_t* rows, int32_t* cols);
+int pfm_tf_set_weights(pfm_tf* h, const float* const* params, int n, void* stream);
+/* x [B,N,feats] (WITHOUT the time columns: the library hoists them), t_code [1|B, t_dim], mask [B,N] or
+ * NULL, cond [B,cond_dim] or NULL, out [B,N,feats]. */
+int pfm_tf_forward(pfm_tf* h, const float* t_code, int t_rows, const float* x, const float* mask,
+                   const float* cond, float* out, int B, int N, void* stream);
+int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* cond, const float* t_codes,
+                  const float* dt, int solver, int n_steps, int B, int N, void* stream);
+int pfm_tf_last_launches(const pfm_tf* h);
+
 /* Introspection for tests / bench: kernels launched by the last call on this handle and the
  * number of CTA work groups the last plan produced. */
 int pfm_epic_last_launches(const pfm_epic* h);

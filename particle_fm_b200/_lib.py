@@ -24,6 +24,12 @@ class EpicCfgC(C.Structure):
                [("sum_scale", C.c_float), ("neg_slope", C.c_float)]
 
 
+class TfCfgC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "feats", "t_dim", "cond_dim", "add_time_to_input", "model_dim", "num_layers",
+                                         "num_heads", "ctxt_out", "embd_hddn", "dense_hddn", "num_tokens")] + \
+               [("neg_slope", C.c_float), ("ln_eps", C.c_float)]
+
+
 _F = C.c_void_p     # device pointers travel as integers (tensor.data_ptr())
 _SIGNATURES = {
     "pfm_version": (C.c_int, []),
@@ -41,6 +47,14 @@ _SIGNATURES = {
                                         C.c_int, C.c_void_p]),
     "pfm_epic_forward_train": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_backward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_tf_create": (C.c_int, [C.POINTER(TfCfgC), C.c_int, C.POINTER(C.c_void_p)]),
+    "pfm_tf_destroy": (None, [C.c_void_p]),
+    "pfm_tf_num_params": (C.c_int, [C.c_void_p]),
+    "pfm_tf_param_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pfm_tf_set_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "pfm_tf_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_tf_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_tf_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),
     "pfm_epic_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

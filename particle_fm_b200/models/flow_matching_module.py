@@ -118,8 +118,11 @@ class CNF(nn.Module):
                                     t_global_cat=t_global_cat, global_cond_dim=global_cond_dim,
                                     local_cond_dim=local_cond_dim, dropout=dropout, sum_scale=sum_scale)
         elif model in ("droid_fulltransformer", "droid_fullcrossattention"):
-            raise NotImplementedError(f"model={model!r}: the masked set-transformer kernels are not built yet "
-                                      "(SURVEY 8 rows a10/a11)")
+            from .components.droid_transformer import FullCrossAttentionEncoder, FullTransformerEncoder
+            cls = FullTransformerEncoder if model == "droid_fulltransformer" else FullCrossAttentionEncoder
+            self.net = cls(inpt_dim=input_dim, outp_dim=features, ctxt_dim=global_cond_dim + 2 * frequencies,
+                           **dict(net_config))
+            self.net.t_dim = 2 * frequencies
         else:
             raise NotImplementedError(f"Model {model} not implemented.")
         self.register_buffer("frequencies", 2 ** torch.arange(frequencies) * torch.pi)
