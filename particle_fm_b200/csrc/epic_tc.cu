@@ -107,6 +107,19 @@ __device__ __forceinline__ void bias_lrelu2(uint32_t& v0, uint32_t& v1, float b0
   v1 = __float_as_uint(fmaxf(__uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)(t >> 32))));
 }
 
+// bf16x2( leaky_relu( bf16(v + b) ) ) for two neighbouring columns: packed add in fp32, one cvt, packed mul + max in bf16
+__device__ __forceinline__ uint32_t bias_lrelu_bf16x2(uint32_t v0, uint32_t v1, float b0, float b1, uint32_t slope_bf2) {
+  const unsigned long long v = ((unsigned long long)v1 << 32) | v0;
+  const unsigned long long b = ((unsigned long long)__float_as_uint(b1) << 32) | __float_as_uint(b0);
+  unsigned long long a;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(v), "l"(b));
+  const uint32_t x = pack_bf16x2(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)(a >> 32)));
+  uint32_t t, r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(t) : "r"(x), "r"(slope_bf2));
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(t));
+  return r;
+}
+
 __device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 // descriptor advance (units of 16 bytes) of K-step k inside a 128-wide K-major SW128 image: 64-column blocks are
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       }
       const uint32_t hrow_addr = smem_u32(hrow), rx16 = (uint32_t)(r & 7) << 4, vpred = valid ? 1u : 0u;
       const uint32_t bl1_addr = smem_u32(&s.bl1[myjet][0]), bl2_addr = smem_u32(&s.bl2[myjet][0]);
+      const uint32_t slope_bf2 = pack_bf16x2(p.slope, p.slope);
       const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
       const int ZP = (Z + 3) & ~3;
 
@@ -433,15 +447,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         store_h_bf16(v, c, spred);
       };
       // one 32-column chunk of the fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM
+      // (the activation is applied AFTER the rounding to bf16, on packed pairs: max(x, s*x) in bf16x2 halves the
+      // ALU-pipe work of this epilogue; u is only ever consumed as bf16)
       auto epi1_chunk = [&](uint32_t (&v)[32], int c) {
         uint32_t u16[16];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 b = lds128(bl1_addr + (uint32_t)(c * 128 + i4 * 16));
-          bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
-          bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
-          u16[i4 * 2 + 0] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]));
-          u16[i4 * 2 + 1] = pack_bf16x2(__uint_as_float(v[i4 * 4 + 2]), __uint_as_float(v[i4 * 4 + 3]));
+          u16[i4 * 2 + 0] = bias_lrelu_bf16x2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope_bf2);
+          u16[i4 * 2 + 1] = bias_lrelu_bf16x2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope_bf2);
         }
         tmem_st16(accU + c * 16, u16);        // columns [16c, 16c+16) were already read (16c+16 <= 32c+32)
       };
