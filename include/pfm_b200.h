@@ -191,6 +191,9 @@ int pfm_tf_forward(pfm_tf* h, const float* t_code, int t_rows, const float* x, c
                    const float* cond, float* out, int B, int N, void* stream);
 int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* cond, const float* t_codes,
                   const float* dt, int solver, int n_steps, int B, int N, void* stream);
+/* PFM_PREC_BF16: the large linears (K multiple of 64, N multiple of 128) run on tcgen05 tensor cores with bf16
+ * operands / fp32 accumulation; LayerNorm statistics, attention, biases and residuals stay fp32. */
+int pfm_tf_set_precision(pfm_tf* h, int precision /* pfm_precision */);
 int pfm_tf_last_launches(const pfm_tf* h);
 
 /* Introspection for tests / bench: kernels launched by the last call on this handle and the

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "pfm_tf_set_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "pfm_tf_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_tf_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_tf_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "pfm_tf_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),

@@ -20,6 +20,7 @@
 
 #include "pfm_internal.cuh"
 #include "simt_common.cuh"
+#include "tf_internal.cuh"
 
 namespace pfm {
 
@@ -31,18 +32,6 @@ static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 // ---------------------------------------------------------------------------------------------
 // generic fused linear
 // ---------------------------------------------------------------------------------------------
-struct LinArgs {
-  const float* X; int ldx; int K;
-  const float* ln_g; const float* ln_b;
-  const float* Wt; int ldo; int N;          // k-major: Wt[k*ldo + o]; row 0 = first input column used
-  const float* bias;
-  const float* jb; int jb_stride; const int* rowjet;
-  const float* R; int ldr;
-  float* Y; int ldy;
-  int act; float slope, eps;
-  int rows;
-};
-
 static constexpr int LIN_ROWS = 64;      // rows per CTA = 8 warps x 8 rows
 static constexpr int LIN_KC = 16;
 
@@ -148,6 +137,53 @@ __global__ void __launch_bounds__(kThreads) tf_linear_kernel(const LinArgs a) {
   }
 }
 
+// Narrow output (N <= 8, e.g. the 512 -> 3 output projection): one warp per row, LayerNorm + N dot products by warp
+// shuffles -- memory bound instead of wasting a 64-column tile on 3 outputs.
+__global__ void tf_linear_smalln_kernel(const LinArgs a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  const float* x = a.X + (size_t)row * a.ldx;
+  float mean = 0.f, rstd = 1.f;
+  if (a.ln_g) {
+    float s = 0.f;
+    for (int c = lane; c < a.K; c += 32) s += x[c];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+    mean = s / (float)a.K;
+    float v = 0.f;
+    for (int c = lane; c < a.K; c += 32) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+    rstd = rsqrtf(v / (float)a.K + a.eps);
+  }
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int c = lane; c < a.K; c += 32) {
+    float xv = x[c];
+    if (a.ln_g) xv = (xv - mean) * rstd * a.ln_g[c] + a.ln_b[c];
+    const float* w = a.Wt + (size_t)c * a.ldo;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < a.N) acc[o] = fmaf(xv, w[o], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sh);
+  if (lane < a.N) {
+    float v = 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o == lane) v = acc[o];
+    if (a.bias) v += a.bias[lane];
+    if (a.jb) v += a.jb[(size_t)(a.rowjet ? a.rowjet[row] : row) * a.jb_stride + lane];
+    if (a.act) v = v > 0.f ? v : v * a.slope;
+    if (a.R) v += a.R[(size_t)row * a.ldr + lane];
+    a.Y[(size_t)row * a.ldy + lane] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // attention kernels (head dim dh <= 16)
 // ---------------------------------------------------------------------------------------------
@@ -169,23 +205,40 @@ __global__ void tf_attn_self_kernel(const float* __restrict__ QKV, int ld, int D
     Vs[i] = src[2 * D];
   }
   __syncthreads();
+  const float sl2 = scale * 1.4426950408889634f;          // scores in log2 units: softmax via exp2
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     float q[DH_MAX], o[DH_MAX];
     const float* qs = QKV + (size_t)(r0 + t) * ld + head * dh;
 #pragma unroll
-    for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? qs[d] * scale : 0.f; o[d] = 0.f; }
+    for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? qs[d] * sl2 : 0.f; o[d] = 0.f; }
     float m = -INFINITY, l = 0.f;
-    for (int k = 0; k < n; ++k) {
-      float s = 0.f;
+    for (int k0 = 0; k0 < n; k0 += 8) {                    // online softmax, one rescale per block of 8 keys
+      float sc[8];
+      float bm = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < DH_MAX; ++d)
-        if (d < dh) s = fmaf(q[d], Ks[k * dh + d], s);
-      const float mn = fmaxf(m, s);
-      const float corr = expf(m - mn), p = expf(s - mn);
-      l = l * corr + p;
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j < n ? k0 + j : n - 1;
+        float sv = 0.f;
 #pragma unroll
-      for (int d = 0; d < DH_MAX; ++d)
-        if (d < dh) o[d] = fmaf(p, Vs[k * dh + d], o[d] * corr);
+        for (int d = 0; d < DH_MAX; ++d)
+          if (d < dh) sv = fmaf(q[d], Ks[k * dh + d], sv);
+        sc[j] = k0 + j < n ? sv : -INFINITY;
+        bm = fmaxf(bm, sc[j]);
+      }
+      const float mn = fmaxf(m, bm);
+      const float corr = exp2f(m - mn);
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < DH_MAX; ++d) o[d] *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j < n ? k0 + j : n - 1;
+        const float pj = exp2f(sc[j] - mn);
+        l += pj;
+#pragma unroll
+        for (int d = 0; d < DH_MAX; ++d)
+          if (d < dh) o[d] = fmaf(pj, Vs[k * dh + d], o[d]);
+      }
       m = mn;
     }
     const float inv = 1.f / l;
@@ -207,7 +260,7 @@ __global__ void tf_attn_from_kernel(const float* __restrict__ Qt, int ldq, const
     const int qrow = jet * ntok + tq;
     float q[DH_MAX], o[DH_MAX];
 #pragma unroll
-    for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? Qt[(size_t)qrow * ldq + head * dh + d] * scale : 0.f; o[d] = 0.f; }
+    for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? Qt[(size_t)qrow * ldq + head * dh + d] * (scale * 1.4426950408889634f) : 0.f; o[d] = 0.f; }
     float m = -INFINITY, l = 0.f;
     for (int k = 0; k < n; ++k) {
       const float* kp = KV + (size_t)(r0 + k) * ldkv + head * dh;
@@ -216,7 +269,7 @@ __global__ void tf_attn_from_kernel(const float* __restrict__ Qt, int ldq, const
       for (int d = 0; d < DH_MAX; ++d)
         if (d < dh) s = fmaf(q[d], kp[d], s);
       const float mn = fmaxf(m, s);
-      const float corr = expf(m - mn), p = expf(s - mn);
+      const float corr = exp2f(m - mn), p = exp2f(s - mn);
       l = l * corr + p;
 #pragma unroll
       for (int d = 0; d < DH_MAX; ++d)
@@ -240,7 +293,7 @@ __global__ void tf_attn_to_kernel(const float* __restrict__ Qs, int ldq, const f
   const int jet = rowjet[row];
   float q[DH_MAX], o[DH_MAX];
 #pragma unroll
-  for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? Qs[(size_t)row * ldq + head * dh + d] * scale : 0.f; o[d] = 0.f; }
+  for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? Qs[(size_t)row * ldq + head * dh + d] * (scale * 1.4426950408889634f) : 0.f; o[d] = 0.f; }
   float m = -INFINITY, l = 0.f;
   for (int k = 0; k < ntok; ++k) {
     const float* kp = KVt + (size_t)(jet * ntok + k) * ldkv + head * dh;
@@ -249,7 +302,7 @@ __global__ void tf_attn_to_kernel(const float* __restrict__ Qs, int ldq, const f
     for (int d = 0; d < DH_MAX; ++d)
       if (d < dh) s = fmaf(q[d], kp[d], s);
     const float mn = fmaxf(m, s);
-    const float corr = expf(m - mn), p = expf(s - mn);
+    const float corr = exp2f(m - mn), p = exp2f(s - mn);
     l = l * corr + p;
 #pragma unroll
     for (int d = 0; d < DH_MAX; ++d)
@@ -339,7 +392,7 @@ __global__ void tf_update_kernel(float* __restrict__ x0, float* __restrict__ xc,
 // handle
 // =============================================================================================
 namespace {
-struct TfLinear { int in = 0, out = 0, ldo = 0; float* Wt = nullptr; float* b = nullptr; };
+struct TfLinear { int in = 0, out = 0, ldo = 0; float* Wt = nullptr; float* b = nullptr; uint8_t* img = nullptr; int kblocks = 0; };
 struct TfLN { int d = 0; float* g = nullptr; float* b = nullptr; };
 struct TfDense { TfLinear l1; TfLN ln; TfLinear l2; };
 struct TfLayer { TfLinear qkv_or_q, kv, out; TfLN mha_ln; TfDense dense; TfLN n0, n1, n2; };
@@ -361,6 +414,8 @@ struct pfm_tf {
   int *n_real, *rowoff, *n_total, *rowjet, *tokjet; uint16_t* ridx;
   float *xs, *x0, *v, *h, *H1, *QKV, *A, *tok, *tokA, *tokQ, *tokKV, *tokH1, *ctxin, *c1, *ctx, *jb; size_t jb_floats;
   int last_launches;
+  int precision;                     // PFM_PREC_FP32 / PFM_PREC_BF16 (tcgen05 linears where the shape allows)
+  std::vector<TfLinear*> all_linears;
 };
 
 namespace pfm {
@@ -377,6 +432,12 @@ static bool tf_make_linear(pfm_tf* h, TfLinear* L, int out, int in) {
   L->in = in; L->out = out; L->ldo = round_up_i(out, 64);
   L->Wt = tf_alloc(h, (size_t)(in + 4) * L->ldo);
   L->b = tf_alloc(h, L->ldo);
+  if (out % 128 == 0 && in >= 64) {      // eligible for the tensor-core path: bf16 image of 16 KB [128 n x 64 k] blocks
+    L->kblocks = (in + 63) / 64;
+    L->img = reinterpret_cast<uint8_t*>(tf_alloc(h, (size_t)(out / 128) * L->kblocks * 16384 / sizeof(float)));
+    if (!L->img) return false;
+  }
+  h->all_linears.push_back(L);
   return L->Wt && L->b;
 }
 static bool tf_make_ln(pfm_tf* h, TfLN* n, int d) {
@@ -431,7 +492,15 @@ static int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K
   a.R = R; a.ldr = ldr; a.Y = Y; a.ldy = ldy;
   a.act = act; a.slope = h->cfg.neg_slope; a.eps = h->cfg.ln_eps;
   a.rows = rows;
+  a.img = L.img; a.img_kblocks = L.kblocks; a.kb0 = k0 / 64;
   h->last_launches++;
+  // tensor cores for the per-token linears; the per-jet context / bias tables (a handful of rows) stay fp32
+  if (h->precision == PFM_PREC_BF16 && rows >= 256 && (k0 % 64) == 0 && tf_tc_linear_supported(a)) return tf_tc_linear(a, h->max_smem, st);
+  if (a.N <= 8 && rows >= 64) {
+    tf_linear_smalln_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a);
+    PFM_CUDA_CHECK(cudaGetLastError());
+    return PFM_OK;
+  }
   if (L.ldo % 256 == 0) return launch_linear_tc<8>(h, a, st);
   if (L.ldo % 128 == 0) return launch_linear_tc<4>(h, a, st);
   return launch_linear_tc<2>(h, a, st);
@@ -613,7 +682,7 @@ int pfm_tf_create(const pfm_tf_cfg* cfg, int device, pfm_tf** out) {
   h->capB = 0; h->capBN = 0; h->cap_rows = 0;
   h->n_real = h->rowoff = h->n_total = h->rowjet = h->tokjet = nullptr; h->ridx = nullptr;
   h->xs = h->x0 = h->v = h->h = h->H1 = h->QKV = h->A = h->tok = h->tokA = h->tokQ = h->tokKV = h->tokH1 = h->ctxin = h->c1 = h->ctx = h->jb = nullptr;
-  h->jb_floats = 0; h->last_launches = 0;
+  h->jb_floats = 0; h->last_launches = 0; h->precision = PFM_PREC_FP32;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   const int D = c.model_dim, CO = c.ctxt_out;
@@ -693,8 +762,17 @@ int pfm_tf_set_weights(pfm_tf* h, const float* const* params, int n, void* strea
       PFM_CUDA_CHECK(cudaMemcpyAsync(s.target, params[i], sizeof(float) * (size_t)s.rows * s.cols, cudaMemcpyDeviceToDevice, st));
     }
   }
+  for (TfLinear* L : h->all_linears)
+    if (L->img) { int rc = tf_tc_pack(L->Wt, L->in, L->out, L->ldo, L->img, L->kblocks, st); if (rc != PFM_OK) return rc; }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
+  return PFM_OK;
+}
+
+int pfm_tf_set_precision(pfm_tf* h, int precision) {
+  if (!h) { set_error("null handle"); return PFM_ERR_INVALID; }
+  if (precision != PFM_PREC_FP32 && precision != PFM_PREC_BF16) { set_error("unknown precision %d", precision); return PFM_ERR_INVALID; }
+  h->precision = precision;
   return PFM_OK;
 }
 

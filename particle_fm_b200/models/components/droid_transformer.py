@@ -140,6 +140,14 @@ class _TfEngine:
         _lib.check(self.lib.pfm_tf_create(C.byref(c), self.index, C.byref(h)), "pfm_tf_create")
         self._h = h
         self.weights_key = None
+        self.precision = "fp32"
+
+    def set_precision(self, precision: str):
+        code = {"fp32": _lib.PFM_PREC_FP32, "bf16": _lib.PFM_PREC_BF16}.get(precision)
+        if code is None:
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        _lib.check(self.lib.pfm_tf_set_precision(self._h, code), "pfm_tf_set_precision")
+        self.precision = precision
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -236,6 +244,8 @@ class _DroidNet(nn.Module):
     def _finish(self, inpt_dim, outp_dim, ctxt_dim, t_dim):
         self.inpt_dim, self.outp_dim, self.ctxt_dim, self.t_dim = inpt_dim, outp_dim, ctxt_dim, t_dim
         self._engines: Dict[int, _TfEngine] = {}
+        import os
+        self.precision = os.environ.get("PFM_PRECISION", "fp32")
 
     def _engine_cfg(self) -> Dict:
         core = self.te if self.kind == 0 else self.cae
@@ -263,6 +273,8 @@ class _DroidNet(nn.Module):
                 raise NotImplementedError("the CUDA path expects one hidden width for the node / ctxt / outp embedders")
             eng = _TfEngine(self._engine_cfg(), torch.device("cuda", idx))
             self._engines[idx] = eng
+        if eng.precision != self.precision:
+            eng.set_precision(self.precision)
         if sync_weights:
             key = self._weights_key()
             if eng.weights_key != key:

@@ -144,3 +144,30 @@ def test_cuda_many_jets_midpoint_and_properties(name, lib_built):
         ref = oo.integrate(lambda tt, y: do.cnf_forward(g.sd, g.cfg, tt, y, None if cond is None else cond[:8], mask[:8]) * mask[:8],
                            z, 4, "midpoint")
     assert rel_l2(s, ref * mask[:8]) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["droid_full_n150_cond", "droid_cross_n150_cond"])
+def test_cuda_bf16_tensor_core_linears(name, lib_built):
+    """PFM_PREC_BF16: the per-token linears on tcgen05 (bf16 operands, fp32 accumulate); tolerance 2e-2 per evaluation."""
+    g = G(name)
+    N, B = g.N, 40                                   # enough rows (> 256) for the tensor-core path to engage
+    m = build(g, DEV)
+    x, mask, cond = eo.synth_cloud(B, N, 3, 777, cond_dim=g.cfg.cond_dim)
+    cd = None if cond is None else cond.to(DEV)
+    t = torch.tensor(0.43)
+    with torch.no_grad():
+        v32 = m.flows[0](t.to(DEV), x.to(DEV), cond=cd, mask=mask.to(DEV)).cpu()
+        l32 = m.flows[0].net.engine().last_launches()
+        m.set_precision("bf16")
+        v16 = m.flows[0](t.to(DEV), x.to(DEV), cond=cd, mask=mask.to(DEV)).cpu()
+        sub = torch.arange(0, B, 7)
+        vo = do.cnf_forward(g.sd, g.cfg, t, x[sub], None if cond is None else cond[sub], mask[sub]) * mask[sub]
+        s16 = m.flows[0].decode(x.to(DEV), cd, mask.to(DEV), "midpoint", 4).cpu()
+        m.set_precision("fp32")
+        s32 = m.flows[0].decode(x.to(DEV), cd, mask.to(DEV), "midpoint", 4).cpu()
+    e = rel_l2(v16[sub], vo)
+    print(f"{name}: bf16 vector field rel-L2 {e:.2e} (fp32 path {rel_l2(v32[sub], vo):.2e}); midpoint-4 end point vs fp32 {rel_l2(s16, s32):.2e}")
+    assert 1e-5 < e < 2e-2                            # really a different (bf16) arithmetic, within tolerance
+    assert rel_l2(s16, s32) < 5e-3                  # 3 big midpoint steps: the end point carries the per-evaluation error
+    assert (v16 * (1 - mask)).abs().max() == 0 and l32 > 0
