@@ -140,47 +140,63 @@ __global__ void __launch_bounds__(kThreads) tf_linear_kernel(const LinArgs a) {
 // Narrow output (N <= 8, e.g. the 512 -> 3 output projection): one warp per row, LayerNorm + N dot products by warp
 // shuffles -- memory bound instead of wasting a 64-column tile on 3 outputs.
 __global__ void tf_linear_smalln_kernel(const LinArgs a) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= a.rows) return;
-  const float* x = a.X + (size_t)row * a.ldx;
-  float mean = 0.f, rstd = 1.f;
-  if (a.ln_g) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                      // [K][8]
+  float* gs = sm + (size_t)a.K * 8;    // [K] LayerNorm gain, [K] shift
+  float* bs = gs + a.K;
+  for (int i = threadIdx.x; i < a.K * 8; i += blockDim.x) {
+    const int c = i >> 3, o = i & 7;
+    Ws[i] = o < a.N ? a.Wt[(size_t)c * a.ldo + o] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.K; i += blockDim.x) { gs[i] = a.ln_g ? a.ln_g[i] : 1.f; bs[i] = a.ln_g ? a.ln_b[i] : 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
+    const float* x = a.X + (size_t)row * a.ldx;
+    float xv[16];                      // K <= 512: 16 values per lane, columns lane + 32 i (coalesced)
     float s = 0.f;
-    for (int c = lane; c < a.K; c += 32) s += x[c];
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-    mean = s / (float)a.K;
-    float v = 0.f;
-    for (int c = lane; c < a.K; c += 32) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+    for (int i = 0; i < 16; ++i) { const int c = lane + 32 * i; xv[i] = c < a.K ? __ldg(x + c) : 0.f; s += xv[i]; }
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln_g) {
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
-    rstd = rsqrtf(v / (float)a.K + a.eps);
-  }
-  float acc[8];
+      for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+      mean = s / (float)a.K;
+      float v = 0.f;
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-  for (int c = lane; c < a.K; c += 32) {
-    float xv = x[c];
-    if (a.ln_g) xv = (xv - mean) * rstd * a.ln_g[c] + a.ln_b[c];
-    const float* w = a.Wt + (size_t)c * a.ldo;
+      for (int i = 0; i < 16; ++i) if (lane + 32 * i < a.K) { const float d = xv[i] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+      rstd = rsqrtf(v / (float)a.K + a.eps);
+    }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      if (c < a.K) {
+        const float xn = (xv[i] - mean) * rstd * gs[c] + bs[c];
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + c * 8), w1 = *reinterpret_cast<const float4*>(Ws + c * 8 + 4);
+        acc[0] = fmaf(xn, w0.x, acc[0]); acc[1] = fmaf(xn, w0.y, acc[1]); acc[2] = fmaf(xn, w0.z, acc[2]); acc[3] = fmaf(xn, w0.w, acc[3]);
+        acc[4] = fmaf(xn, w1.x, acc[4]); acc[5] = fmaf(xn, w1.y, acc[5]); acc[6] = fmaf(xn, w1.z, acc[6]); acc[7] = fmaf(xn, w1.w, acc[7]);
+      }
+    }
 #pragma unroll
     for (int o = 0; o < 8; ++o)
-      if (o < a.N) acc[o] = fmaf(xv, w[o], acc[o]);
-  }
 #pragma unroll
-  for (int o = 0; o < 8; ++o)
+      for (int sh = 16; sh > 0; sh >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sh);
+    if (lane < a.N) {
+      float v = 0.f;
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sh);
-  if (lane < a.N) {
-    float v = 0.f;
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-      if (o == lane) v = acc[o];
-    if (a.bias) v += a.bias[lane];
-    if (a.jb) v += a.jb[(size_t)(a.rowjet ? a.rowjet[row] : row) * a.jb_stride + lane];
-    if (a.act) v = v > 0.f ? v : v * a.slope;
-    if (a.R) v += a.R[(size_t)row * a.ldr + lane];
-    a.Y[(size_t)row * a.ldy + lane] = v;
+      for (int o = 0; o < 8; ++o)
+        if (o == lane) v = acc[o];
+      if (a.bias) v += a.bias[lane];
+      if (a.jb) v += a.jb[(size_t)(a.rowjet ? a.rowjet[row] : row) * a.jb_stride + lane];
+      if (a.act) v = v > 0.f ? v : v * a.slope;
+      if (a.R) v += a.R[(size_t)row * a.ldr + lane];
+      a.Y[(size_t)row * a.ldy + lane] = v;
+    }
   }
 }
 
@@ -189,39 +205,50 @@ __global__ void tf_linear_smalln_kernel(const LinArgs a) {
 // ---------------------------------------------------------------------------------------------
 static constexpr int DH_MAX = 16;
 
-// self attention: grid (B, heads); block = queries (real tokens of the jet, looped); K/V of the head in smem
-__global__ void tf_attn_self_kernel(const float* __restrict__ QKV, int ld, int D, int dh, const int* __restrict__ n_real,
+// self attention: grid (B, heads); block = queries (real tokens of the jet, looped); K/V of the head in smem.
+// DH = head dim (compile time: 16-byte shared loads); scores in log2 units, online softmax with one rescale per 8 keys.
+template <int DH>
+__global__ void tf_attn_self_kernel(const float* __restrict__ QKV, int ld, int D, const int* __restrict__ n_real,
                                     const int* __restrict__ rowoff, float* __restrict__ A, int lda, float scale) {
   extern __shared__ __align__(16) float sm[];
   const int jet = blockIdx.x, head = blockIdx.y;
   const int n = n_real[jet], r0 = rowoff[jet];
   if (n == 0) return;
-  float* Ks = sm;                     // [n][dh]
-  float* Vs = sm + (size_t)n * dh;    // [n][dh]
-  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
-    const int t = i / dh, d = i - t * dh;
-    const float* src = QKV + (size_t)(r0 + t) * ld + head * dh + d;
-    Ks[i] = src[D];
-    Vs[i] = src[2 * D];
+  float* Ks = sm;                     // [n][DH]
+  float* Vs = sm + (size_t)n * DH;    // [n][DH]
+  for (int i = threadIdx.x; i < n * (DH / 4); i += blockDim.x) {
+    const int t = i / (DH / 4), d4 = i - t * (DH / 4);
+    const float* src = QKV + (size_t)(r0 + t) * ld + head * DH + d4 * 4;
+    *reinterpret_cast<float4*>(Ks + t * DH + d4 * 4) = *reinterpret_cast<const float4*>(src + D);
+    *reinterpret_cast<float4*>(Vs + t * DH + d4 * 4) = *reinterpret_cast<const float4*>(src + 2 * D);
   }
   __syncthreads();
-  const float sl2 = scale * 1.4426950408889634f;          // scores in log2 units: softmax via exp2
+  const float sl2 = scale * 1.4426950408889634f;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    float q[DH_MAX], o[DH_MAX];
-    const float* qs = QKV + (size_t)(r0 + t) * ld + head * dh;
+    float q[DH], o[DH];
+    const float* qs = QKV + (size_t)(r0 + t) * ld + head * DH;
 #pragma unroll
-    for (int d = 0; d < DH_MAX; ++d) { q[d] = d < dh ? qs[d] * sl2 : 0.f; o[d] = 0.f; }
+    for (int d4 = 0; d4 < DH / 4; ++d4) {
+      const float4 v = *reinterpret_cast<const float4*>(qs + d4 * 4);
+      q[d4 * 4 + 0] = v.x * sl2; q[d4 * 4 + 1] = v.y * sl2; q[d4 * 4 + 2] = v.z * sl2; q[d4 * 4 + 3] = v.w * sl2;
+    }
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
     float m = -INFINITY, l = 0.f;
-    for (int k0 = 0; k0 < n; k0 += 8) {                    // online softmax, one rescale per block of 8 keys
+    for (int k0 = 0; k0 < n; k0 += 8) {
       float sc[8];
       float bm = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = k0 + j < n ? k0 + j : n - 1;
+        const float4* kp = reinterpret_cast<const float4*>(Ks + k * DH);
         float sv = 0.f;
 #pragma unroll
-        for (int d = 0; d < DH_MAX; ++d)
-          if (d < dh) sv = fmaf(q[d], Ks[k * dh + d], sv);
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+          const float4 kv = kp[d4];
+          sv = fmaf(q[d4 * 4 + 0], kv.x, sv); sv = fmaf(q[d4 * 4 + 1], kv.y, sv);
+          sv = fmaf(q[d4 * 4 + 2], kv.z, sv); sv = fmaf(q[d4 * 4 + 3], kv.w, sv);
+        }
         sc[j] = k0 + j < n ? sv : -INFINITY;
         bm = fmaxf(bm, sc[j]);
       }
@@ -229,23 +256,27 @@ __global__ void tf_attn_self_kernel(const float* __restrict__ QKV, int ld, int D
       const float corr = exp2f(m - mn);
       l *= corr;
 #pragma unroll
-      for (int d = 0; d < DH_MAX; ++d) o[d] *= corr;
+      for (int d = 0; d < DH; ++d) o[d] *= corr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = k0 + j < n ? k0 + j : n - 1;
         const float pj = exp2f(sc[j] - mn);
         l += pj;
+        const float4* vp = reinterpret_cast<const float4*>(Vs + k * DH);
 #pragma unroll
-        for (int d = 0; d < DH_MAX; ++d)
-          if (d < dh) o[d] = fmaf(pj, Vs[k * dh + d], o[d]);
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+          const float4 vv = vp[d4];
+          o[d4 * 4 + 0] = fmaf(pj, vv.x, o[d4 * 4 + 0]); o[d4 * 4 + 1] = fmaf(pj, vv.y, o[d4 * 4 + 1]);
+          o[d4 * 4 + 2] = fmaf(pj, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(pj, vv.w, o[d4 * 4 + 3]);
+        }
       }
       m = mn;
     }
     const float inv = 1.f / l;
-    float* dst = A + (size_t)(r0 + t) * lda + head * dh;
+    float* dst = A + (size_t)(r0 + t) * lda + head * DH;
 #pragma unroll
-    for (int d = 0; d < DH_MAX; ++d)
-      if (d < dh) dst[d] = o[d] * inv;
+    for (int d4 = 0; d4 < DH / 4; ++d4)
+      *reinterpret_cast<float4*>(dst + d4 * 4) = make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
   }
 }
 
@@ -496,8 +527,9 @@ static int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K
   h->last_launches++;
   // tensor cores for the per-token linears; the per-jet context / bias tables (a handful of rows) stay fp32
   if (h->precision == PFM_PREC_BF16 && rows >= 256 && (k0 % 64) == 0 && tf_tc_linear_supported(a)) return tf_tc_linear(a, h->max_smem, st);
-  if (a.N <= 8 && rows >= 64) {
-    tf_linear_smalln_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a);
+  if (a.N <= 8 && rows >= 64 && a.K <= 512) {
+    const int blocks = (rows + 63) / 64 < 4 * h->sm_count ? (rows + 63) / 64 : 4 * h->sm_count;
+    tf_linear_smalln_kernel<<<blocks, 256, sizeof(float) * (size_t)a.K * 10, st>>>(a);
     PFM_CUDA_CHECK(cudaGetLastError());
     return PFM_OK;
   }
@@ -598,8 +630,16 @@ static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, 
       TfLayer& Ly = h->layers[l];
       if ((rc = run_linear(h, st, h->h, D, D, &Ly.n1, Ly.qkv_or_q, 0, true, nullptr, 0, nullptr, nullptr, 0, h->QKV, 3 * D, 0,
                            rows)) != PFM_OK) return rc;
-      tf_attn_self_kernel<<<dim3(B, c.num_heads), 128, sizeof(float) * 2 * (size_t)N * dh, st>>>(
-          h->QKV, 3 * D, D, dh, h->n_real, h->rowoff, h->A, D, scale);
+      if (dh == 16)
+        tf_attn_self_kernel<16><<<dim3(B, c.num_heads), 128, sizeof(float) * 2 * (size_t)N * dh, st>>>(h->QKV, 3 * D, D, h->n_real,
+                                                                                                  h->rowoff, h->A, D, scale);
+      else if (dh == 8)
+        tf_attn_self_kernel<8><<<dim3(B, c.num_heads), 128, sizeof(float) * 2 * (size_t)N * dh, st>>>(h->QKV, 3 * D, D, h->n_real,
+                                                                                                 h->rowoff, h->A, D, scale);
+      else if (dh == 4)
+        tf_attn_self_kernel<4><<<dim3(B, c.num_heads), 128, sizeof(float) * 2 * (size_t)N * dh, st>>>(h->QKV, 3 * D, D, h->n_real,
+                                                                                                 h->rowoff, h->A, D, scale);
+      else { set_error("self attention: head dim %d not supported (4, 8, 16)", dh); return PFM_ERR_UNSUPPORTED; }
       h->last_launches++;
       if ((rc = run_linear(h, st, h->A, D, D, &Ly.mha_ln, Ly.out, 0, true, nullptr, 0, nullptr, h->h, D, h->h, D, 0, rows)) != PFM_OK)
         return rc;
@@ -800,7 +840,10 @@ int pfm_tf_forward(pfm_tf* h, const float* t_code, int t_rows, const float* x, c
   if ((rc = tf_plan(h, st, x, mask, B, N, &rows)) != PFM_OK) return rc;
   {
     const size_t smem = sizeof(float) * 2 * (size_t)N * (h->cfg.model_dim / h->cfg.num_heads);
-    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    const int lim = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   }
   if ((rc = tf_eval(h, st, t_code, t_rows, cond, B, N, rows)) != PFM_OK) return rc;
   tf_unpack_kernel<<<(B + 7) / 8, 256, 0, st>>>(h->v, h->n_real, h->ridx, h->rowoff, B, N, h->cfg.feats, out);
@@ -823,7 +866,10 @@ int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* con
   if ((rc = tf_plan(h, st, x_inout, mask, B, N, &rows)) != PFM_OK) return rc;
   {
     const size_t smem = sizeof(float) * 2 * (size_t)N * (h->cfg.model_dim / h->cfg.num_heads);
-    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    const int lim = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(tf_attn_self_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   }
   const int F = h->cfg.feats, T = h->cfg.t_dim;
   const int nel = rows * F;
