@@ -23,6 +23,7 @@ struct SimtParams {
   const Lin* lin;
   const float* tbias; const float* cbias; int bstride; int tbias_per_jet;
   const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
+  const int* jetmap;           // position -> jet (inference plan; nullptr = identity, training)
   const float* x_in; float* x_out; int B, N;
   int n_evals, solver, n_steps; const float* dt;
   // training forward (TRAIN instantiation): interpolation inputs, saved activations, loss
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
   int* ints = reinterpret_cast<int*>(smem + p.o_int);
   int* jrow0 = ints;                       // [J_cap + 1] first row of every jet of the group
   int* s_group = ints + p.J_cap + 1;       // [2]
-  short* rjet = reinterpret_cast<short*>(ints + p.J_cap + 4);   // [R_cap] jet (inside the group) of a row
+  int* jid = ints + p.J_cap + 4;           // [J_cap] batch index of the group's jets
+  short* rjet = reinterpret_cast<short*>(ints + 2 * p.J_cap + 4);   // [R_cap] jet (inside the group) of a row
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, Z = p.Z, F = p.F, LDH = p.LDH, LDX = p.LDX, LDB = p.LDB, LDP = p.LDP;
@@ -82,7 +84,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
     const int j0 = grp.x, nj = grp.y;
     if (tid == 0) {
       int r = 0;
-      for (int j = 0; j < nj; ++j) { jrow0[j] = r; r += p.n_real[j0 + j]; }
+      for (int j = 0; j < nj; ++j) {
+        jid[j] = p.jetmap ? p.jetmap[j0 + j] : j0 + j;
+        jrow0[j] = r;
+        r += p.n_real[jid[j]];
+      }
       jrow0[nj] = r;
     }
     __syncthreads();
@@ -98,13 +104,13 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
       for (int i = tid; i < n; i += kThreads) rjet[r0 + i] = (short)j;
       for (int i = tid; i < n * p.Kx; i += kThreads) {
         const int r = i / p.Kx, c = i - r * p.Kx;
-        const int part = p.ridx[(size_t)(j0 + j) * p.N + r];
-        const size_t gi = ((size_t)(j0 + j) * p.N + part) * p.x_ld + c;
+        const int part = p.ridx[(size_t)jid[j] * p.N + r];
+        const size_t gi = ((size_t)jid[j] * p.N + part) * p.x_ld + c;
         float v;
         if (TRAIN && p.loss_kind >= 0) {
           // flow-matching interpolation y(x1, t, noise) and target u_t (losses.py:56-62, :115-119, :320-326);
           // the target is parked in x0 until the loss is evaluated
-          const float x = p.x1[gi], t = p.tjet[j0 + j], z = p.noise0[gi];
+          const float x = p.x1[gi], t = p.tjet[jid[j]], z = p.noise0[gi];
           float u;
           if (p.loss_kind == PFM_LOSS_FM_OT) {
             v = (1.f - t) * x + (p.sigma + (1.f - p.sigma) * t) * z;
@@ -133,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
         const Lin L1 = lin[LIN_L1], L2 = lin[LIN_L2];
         for (int i = tid; i < nj * H; i += kThreads) {
           const int j = i / H, o = i - j * H;
-          bl1[j * LDB + o] = bias_of(p, L1, ev, j0 + j, o);
-          bl2[j * LDB + o] = bias_of(p, L2, ev, j0 + j, o);
+          bl1[j * LDB + o] = bias_of(p, L1, ev, jid[j], o);
+          bl2[j * LDB + o] = bias_of(p, L2, ev, jid[j], o);
         }
         __syncthreads();
         for (int c0 = 0; c0 < R; c0 += CR) {
@@ -189,32 +195,32 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           pool[j * LDP + o] = s * p.sum_scale;                    // (sum, mean) order in the stem, :373
           pool[j * LDP + H + o] = s / (float)(r1 - r0);
           if (TRAIN) {                                                                                 // unit 0: pool input
-            p.jact[(size_t)(j0 + j) * p.jstride + o] = pool[j * LDP + o];
-            p.jact[(size_t)(j0 + j) * p.jstride + H + o] = pool[j * LDP + H + o];
+            p.jact[(size_t)jid[j] * p.jstride + o] = pool[j * LDP + o];
+            p.jact[(size_t)jid[j] * p.jstride + H + o] = pool[j * LDP + H + o];
           }
         }
         __syncthreads();
         const Lin G1 = lin[LIN_G1], G2 = lin[LIN_G2];
         for (int i = tid; i < nj * H; i += kThreads) {
           const int j = i / H, o = i - j * H;
-          float a = bias_of(p, G1, ev, j0 + j, o);
+          float a = bias_of(p, G1, ev, jid[j], o);
           const float* w = G1.Wt + (size_t)G1.m_off * G1.ldo + o;
           const float* in = pool + j * LDP;
 #pragma unroll 4
           for (int k = 0; k < 2 * H; ++k) a = fmaf(__ldg(w + (size_t)k * G1.ldo), in[k], a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
-          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + p.LDP_act + o] = g1[j * p.Hp + o];        // unit 0: g1
+          if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + p.LDP_act + o] = g1[j * p.Hp + o];        // unit 0: g1
         }
         __syncthreads();
         for (int i = tid; i < nj * Z; i += kThreads) {
           const int j = i / Z, o = i - j * Z;
-          float a = bias_of(p, G2, ev, j0 + j, o);
+          float a = bias_of(p, G2, ev, jid[j], o);
           const float* w = G2.Wt + (size_t)G2.m_off * G2.ldo + o;
           const float* in = g1 + j * p.Hp;
 #pragma unroll 4
           for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * G2.ldo), in[k], a);
           gv[j * Z + o] = lrelu(a, p.slope);                       // no residual in the stem, :378-380
-          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + p.LDP_act + p.Hp_act + o] = gv[j * Z + o]; // unit 0: g
+          if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + p.LDP_act + p.Hp_act + o] = gv[j * Z + o]; // unit 0: g
         }
         __syncthreads();
       }
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           pool[j * LDP + o] = s / (float)(r1 - r0);                // (mean, sum, global) order, :164-171
           pool[j * LDP + H + o] = s * p.sum_scale;
           if (TRAIN) {                                                                                // unit l+1: pool input
-            float* ja = p.jact + (size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit;
+            float* ja = p.jact + (size_t)jid[j] * p.jstride + (size_t)(l + 1) * p.junit;
             ja[o] = pool[j * LDP + o];
             ja[H + o] = pool[j * LDP + H + o];
           }
@@ -238,24 +244,24 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
         for (int i = tid; i < nj * Z; i += kThreads) {
           const int j = i / Z, o = i - j * Z;
           pool[j * LDP + 2 * H + o] = gv[j * Z + o];
-          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + 2 * H + o] = gv[j * Z + o];
+          if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + (size_t)(l + 1) * p.junit + 2 * H + o] = gv[j * Z + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * H; i += kThreads) {            // fc_global1, :180-182
           const int j = i / H, o = i - j * H;
-          float a = bias_of(p, Ga, ev, j0 + j, o);
+          float a = bias_of(p, Ga, ev, jid[j], o);
           const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + o;
           const float* in = pool + j * LDP;
           const int K = 2 * H + Z;
 #pragma unroll 4
           for (int k = 0; k < K; ++k) a = fmaf(__ldg(w + (size_t)k * Ga.ldo), in[k], a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
-          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + o] = g1[j * p.Hp + o];
+          if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + o] = g1[j * p.Hp + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * Z; i += kThreads) {            // fc_global2 + residual, :184-186
           const int j = i / Z, o = i - j * Z;
-          float a = bias_of(p, Gb, ev, j0 + j, o);
+          float a = bias_of(p, Gb, ev, jid[j], o);
           const float* w = Gb.Wt + (size_t)Gb.m_off * Gb.ldo + o;
           const float* in = g1 + j * p.Hp;
 #pragma unroll 4
@@ -263,17 +269,17 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           // the new global vector is written to the pool row first (gv is still being read as the residual
           // by other threads only through gv[j*Z+o] of the SAME (j,o) -> safe in place)
           gv[j * Z + o] = lrelu(a + gv[j * Z + o], p.slope);
-          if (TRAIN) p.jact[(size_t)(j0 + j) * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + p.Hp_act + o] = gv[j * Z + o];
+          if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + p.Hp_act + o] = gv[j * Z + o];
         }
         __syncthreads();
         for (int i = tid; i < nj * H; i += kThreads) {            // per-jet bias of fc_local1 / fc_local2
           const int j = i / H, o = i - j * H;
-          float a = bias_of(p, La, ev, j0 + j, o);
+          float a = bias_of(p, La, ev, jid[j], o);
           const float* w = La.Wt + (size_t)La.g_off * La.ldo + o;
           const float* in = gv + j * Z;
           for (int k = 0; k < Z; ++k) a = fmaf(__ldg(w + (size_t)k * La.ldo), in[k], a);
           bl1[j * LDB + o] = a;
-          bl2[j * LDB + o] = bias_of(p, Lb, ev, j0 + j, o);
+          bl2[j * LDB + o] = bias_of(p, Lb, ev, jid[j], o);
         }
         __syncthreads();
         for (int c0 = 0; c0 < R; c0 += CR) {                      // fc_local1, fc_local2 + residual, :189-200
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
         const float* w3 = L3.Wt + (size_t)L3.m_off * L3.ldo;
         for (int i = tid; i < R * F; i += kThreads) {
           const int row = i / F, f = i - row * F;
-          float a = bias_of(p, L3, ev, j0 + rjet[row], f);
+          float a = bias_of(p, L3, ev, jid[rjet[row]], f);
           const float* hr = hs + (size_t)row * LDH;
           for (int k = 0; k < H; ++k) a = fmaf(__ldg(w3 + (size_t)k * L3.ldo + f), hr[k], a);
           vbuf[i] = lrelu(a, p.slope);
@@ -378,15 +384,15 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
       for (int j = 0; j < nj; ++j) {
         const int n = jrow0[j + 1] - jrow0[j];
         const float fill = n == 0 ? __int_as_float(0x7fc00000) : 0.f;   // empty jet -> NaN like the reference
-        float* dst = p.x_out + (size_t)(j0 + j) * p.N * F;
+        float* dst = p.x_out + (size_t)jid[j] * p.N * F;
         for (int i = tid; i < p.N * F; i += kThreads) dst[i] = fill;
       }
       __syncthreads();
       for (int i = tid; i < R * F; i += kThreads) {
         const int row = i / F, f = i - row * F;
         const int j = rjet[row];
-        const int part = p.ridx[(size_t)(j0 + j) * p.N + (row - jrow0[j])];
-        p.x_out[((size_t)(j0 + j) * p.N + part) * F + f] = src[i];
+        const int part = p.ridx[(size_t)jid[j] * p.N + (row - jrow0[j])];
+        p.x_out[((size_t)jid[j] * p.N + part) * F + f] = src[i];
       }
     }
   }
@@ -417,7 +423,7 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_
   for (int pass = 0; pass < 4; ++pass) {
     const int wbuf = KC * ldo_max + 32 * s->TC + 32;   // + slack for the unguarded column reads
     const int per_jet = LDP + Z + Hp + 2 * LDB;
-    const int fixed = CR * LDH + 2 * wbuf + J_cap * per_jet + (J_cap + 8) + 64;
+    const int fixed = CR * LDH + 2 * wbuf + J_cap * per_jet + (2 * J_cap + 8) + 64;
     const int per_row = LDX + 2 * F + LDH + 1;          // xs, x0, vbuf, hs, rjet(short, rounded up)
     R_cap = (budget - fixed) / per_row;
     s->KC = KC;
@@ -472,7 +478,7 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_
   p.o_bl1 = take(J_cap * LDB);
   p.o_bl2 = take(J_cap * LDB);
   p.o_v = take(R_cap * F);
-  p.o_int = take(J_cap + 8 + (R_cap + 1) / 2);
+  p.o_int = take(2 * J_cap + 8 + (R_cap + 1) / 2);
   p.total_floats = o;
   s->smem = (size_t)o * 4;
   if ((int)s->smem > h->max_smem_optin) {
@@ -524,7 +530,7 @@ int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride;
   p.tbias_per_jet = a.tbias_per_jet;
   p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
-  p.counter = h->plan.counter;
+  p.counter = h->plan.counter; p.jetmap = a.jetmap;
   p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   // persistent CTAs: one per SM, but never more than there can be groups (every group has >= 1 jet)

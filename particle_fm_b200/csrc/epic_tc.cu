@@ -63,6 +63,7 @@ struct TcSmem {
   float inv_n[TC_J];
   int boff[128];                               // bias-table offset of every linear (copied once: no global descriptor loads in the loop)
   int jrow0[TC_J + 1];
+  int jid[TC_J];                               // batch index of the group's jets (the plan bin-packs jets out of order)
   int group;
   uint32_t tmem_base;
   uint64_t full[TC_NSLOT], empty[TC_NSLOT];
@@ -81,7 +82,7 @@ struct TcParams {
   const uint8_t* spk;        // [L+1] small-weight packs
   int boff_stem, boff_layer0, boff_layer_stride, bias_chunk_floats;   // where a unit's 4 linears sit in a bias-table row
   const float* tbias; const float* cbias; int bstride; int tbias_per_jet;
-  const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter;
+  const int* n_real; const uint16_t* ridx; const int2* groups; const int* n_groups; int* counter; const int* jetmap;
   const float* x_in; float* x_out; int B, N;
   int n_evals, solver, n_steps; const float* dt;
   long long* prof;          // [3][20] debug phase timers (PFM_TC_PROF)
@@ -373,9 +374,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 
       if (et == 0) {
         int acc = 0;
+        for (int j = 0; j < TC_J; ++j) s.jid[j] = p.jetmap ? p.jetmap[j0 + (j < nj ? j : 0)] : j0 + (j < nj ? j : 0);
         for (int j = 0; j < nj; ++j) {
           s.jrow0[j] = acc;
-          const int n = p.n_real[j0 + j];
+          const int n = p.n_real[s.jid[j]];
           s.inv_n[j] = 1.f / (float)n;           // n == 0 -> inf -> NaN confined to that jet, like the reference
           acc += n;
         }
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       for (int j = 1; j < nj; ++j) myjet += (row >= s.jrow0[j]) ? 1 : 0;
       if (!valid) myjet = 0;
       if (valid) *reinterpret_cast<__nv_bfloat16*>(s.P + sw128_offset(myjet, row, 2048)) = __float2bfloat16(1.0f);
-      const int jg = j0 + myjet;
+      const int jg = s.jid[myjet];
       // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
       // slow direct path when every jet has its own time (training-style forward)
       auto unit_bias = [&](int lin_idx, int voff, int jet_global, int o) -> float {
@@ -481,8 +483,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
         for (int i = et; i < nj * TCH; i += 256) {
           const int j = i >> 7, o = i & 127;
-          s.bl1[j][o] = unit_bias(LIN_L1, 0, j0 + j, o);
-          s.bl2[j][o] = unit_bias(LIN_L2, 128, j0 + j, o);
+          s.bl1[j][o] = unit_bias(LIN_L1, 0, s.jid[j], o);
+          s.bl2[j][o] = unit_bias(LIN_L2, 128, s.jid[j], o);
         }
         ebar();
         // ---------------- fc_l1 on CUDA cores (K = a few features): h1 -> TMEM (fp32) + shared (bf16) ----------------
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             for (int q = 0; q < 4; ++q) pre[bb][q] = 0.f;
             if (jb < nj) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) pre[bb][q] = (SIMPLE || jb + q < nj) ? unit_bias(Ga, off_ga, j0 + jb + q, r) : 0.f;
+              for (int q = 0; q < 4; ++q) pre[bb][q] = (SIMPLE || jb + q < nj) ? unit_bias(Ga, off_ga, s.jid[jb + q], r) : 0.f;
               if (gi >= 1) {
 #pragma unroll
                 for (int z4 = 0; z4 < TC_ZMAX / 4; ++z4) {       // rows z >= Z of the pack are zero: no bound check
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               }
               float acc = (a0 + a1) + (a2 + a3);
               acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-              acc += unit_bias(Gb, off_gb, j0 + j, zc);
+              acc += unit_bias(Gb, off_gb, s.jid[j], zc);
               if (gi >= 1) acc += s.gv[j][zc];
               const float gz = z < Z ? lrelu_tc(acc, p.slope) : 0.f;
               __syncwarp();                        // every lane has read the old g before it is overwritten
@@ -682,8 +684,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
                 float b1v[4], b2v[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  b1v[i] = unit_bias(La, 128 + ZP, j0 + j, lane_ + 32 * i);
-                  b2v[i] = unit_bias(Lb, 256 + ZP, j0 + j, lane_ + 32 * i);
+                  b1v[i] = unit_bias(La, 128 + ZP, s.jid[j], lane_ + 32 * i);
+                  b2v[i] = unit_bias(Lb, 256 + ZP, s.jid[j], lane_ + 32 * i);
                 }
 #pragma unroll
                 for (int zz = 0; zz < TC_ZMAX; ++zz) {           // rows zz >= Z of W_glob are zero and gz is 0 there
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       for (int j = 0; j < nj; ++j) {
         const int n = s.jrow0[j + 1] - s.jrow0[j];
         const float fill = n == 0 ? __int_as_float(0x7fc00000) : 0.f;
-        float* dst = p.x_out + (size_t)(j0 + j) * p.N * F;
+        float* dst = p.x_out + (size_t)s.jid[j] * p.N * F;
         for (int i = et; i < p.N * F; i += 256) dst[i] = fill;
       }
       ebar();
@@ -938,7 +940,7 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   }
   p.tbias = h->tbias; p.cbias = a.has_cbias ? h->cbias : nullptr; p.bstride = h->bstride; p.tbias_per_jet = a.tbias_per_jet;
   p.n_real = h->plan.n_real; p.ridx = h->plan.ridx; p.groups = h->plan.groups; p.n_groups = h->plan.n_groups;
-  p.counter = h->plan.counter;
+  p.counter = h->plan.counter; p.jetmap = a.jetmap;
   p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;

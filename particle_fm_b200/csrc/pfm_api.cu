@@ -112,6 +112,80 @@ __global__ void plan_group_kernel(const int* __restrict__ n_real, int B, int R_c
   }
 }
 
+// Inference plan: bin-pack the jets into groups of <= R_cap rows / <= J_cap jets (best-fit decreasing on a histogram of
+// the multiplicities).  The fused kernels are latency-bound per group, so their time is proportional to the NUMBER of
+// groups: packing jets of mixed sizes (JetNet-150: 15..150 particles, 256-row groups) raises the fill from ~80 % (greedy
+// over consecutive jets) to ~97 %.  Deterministic (no atomics in the ordering).  One block; warp 0 does the packing.
+__global__ void plan_pack_kernel(const int* __restrict__ n_real, int B, int R_cap, int J_cap, int2* __restrict__ groups,
+                                 int* __restrict__ n_groups, int* __restrict__ counter, int* __restrict__ jetmap,
+                                 int* __restrict__ order) {
+  extern __shared__ int sp[];
+  int* cnt = sp;                       // [R_cap + 1] jets per multiplicity
+  int* start = sp + (R_cap + 1);       // [R_cap + 1] first slot of the bucket in `order` (descending multiplicity)
+  int* cur = sp + 2 * (R_cap + 1);     // [R_cap + 1] used entries of the bucket
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i <= R_cap; i += blockDim.x) { cnt[i] = 0; cur[i] = 0; }
+  __syncthreads();
+  for (int i = tid; i < B; i += blockDim.x) atomicAdd(&cnt[n_real[i] < R_cap ? n_real[i] : R_cap], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int pos = 0;
+    for (int n = R_cap; n >= 0; --n) { start[n] = pos; pos += cnt[n]; }
+    for (int i = 0; i < B; ++i) {      // stable counting sort: jets of equal multiplicity keep their batch order
+      const int n = n_real[i] < R_cap ? n_real[i] : R_cap;
+      order[start[n] + cur[n]++] = i;
+    }
+    for (int n = 0; n <= R_cap; ++n) cur[n] = 0;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+  // largest multiplicity n in [1, lim] with an unused jet, or 0
+  auto find_le = [&](int lim) -> int {
+    for (int base = lim; base >= 1; base -= 32) {
+      const int n = base - lane;
+      const bool ok = n >= 1 && cnt[n] - cur[n] > 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (bal) return base - (__ffs(bal) - 1);
+    }
+    return 0;
+  };
+  int pos = 0, g = 0, top = R_cap;
+  int remaining = B - cnt[0], zero_left = cnt[0];
+  while (remaining > 0) {
+    int n = find_le(top);
+    top = n;
+    const int first = pos;
+    int rows = 0, jets = 0;
+    while (n > 0) {
+      if (lane == 0) { jetmap[pos] = order[start[n] + cur[n]]; cur[n]++; }
+      __syncwarp();
+      ++pos; rows += n; ++jets; --remaining;
+      if (jets >= J_cap || remaining == 0) break;
+      const int lim = (R_cap - rows) < top ? (R_cap - rows) : top;
+      n = lim >= 1 ? find_le(lim) : 0;
+    }
+    while (jets < J_cap && zero_left > 0) {        // empty jets ride along in spare jet slots
+      if (lane == 0) { jetmap[pos] = order[start[0] + cur[0]]; cur[0]++; }
+      __syncwarp();
+      ++pos; ++jets; --zero_left;
+    }
+    if (lane == 0) groups[g] = make_int2(first, jets);
+    ++g;
+  }
+  while (zero_left > 0) {
+    const int first = pos;
+    int jets = 0;
+    while (jets < J_cap && zero_left > 0) {
+      if (lane == 0) { jetmap[pos] = order[start[0] + cur[0]]; cur[0]++; }
+      __syncwarp();
+      ++pos; ++jets; --zero_left;
+    }
+    if (lane == 0) groups[g] = make_int2(first, jets);
+    ++g;
+  }
+  if (lane == 0) { *n_groups = g; *counter = 0; }
+}
+
 __global__ void rowmajor_main_kernel(const float* __restrict__ W, float* __restrict__ Wr, int out, int in, int m_off,
                                      int m_len, int ldr) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,6 +200,10 @@ static int ensure_plan(pfm_epic* h, int B, int N) {
     if (p.n_real) cudaFree(p.n_real);
     if (p.groups) cudaFree(p.groups);
     if (p.rowoff) cudaFree(p.rowoff);
+    if (p.jetmap) cudaFree(p.jetmap);
+    if (p.order) cudaFree(p.order);
+    PFM_CUDA_CHECK(cudaMalloc(&p.jetmap, sizeof(int) * B));
+    PFM_CUDA_CHECK(cudaMalloc(&p.order, sizeof(int) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.n_real, sizeof(int) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.groups, sizeof(int2) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.rowoff, sizeof(int) * B));
@@ -208,12 +286,12 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
     if (rc != PFM_OK) return rc;
     const float* mk = mask ? mask + (size_t)b0 * N : nullptr;
     plan_count_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mk, nb, N, h->plan.n_real, h->plan.ridx);
-    plan_group_kernel<<<1, 1024, sizeof(int) * nb, st>>>(h->plan.n_real, nb, R_cap, J_cap, h->plan.groups,
-                                                         h->plan.n_groups, h->plan.counter, h->plan.rowoff,
-                                                         h->plan.n_total);
+    plan_pack_kernel<<<1, 1024, sizeof(int) * 3 * (R_cap + 1), st>>>(h->plan.n_real, nb, R_cap, J_cap, h->plan.groups,
+                                                                     h->plan.n_groups, h->plan.counter, h->plan.jetmap, h->plan.order);
     h->last_launches += 2;
     PFM_CUDA_CHECK(cudaGetLastError());
     RunArgs a;
+    a.jetmap = h->plan.jetmap;
     a.x_in = x_in + (size_t)b0 * N * Kx;
     a.x_out = x_out + (size_t)b0 * N * c.feats;
     a.B = nb; a.N = N; a.Kx = Kx; a.xin_off = xin_off;
@@ -504,6 +582,8 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->plan.n_groups) cudaFree(h->plan.n_groups);
   if (h->plan.counter) cudaFree(h->plan.counter);
   if (h->plan.rowoff) cudaFree(h->plan.rowoff);
+  if (h->plan.jetmap) cudaFree(h->plan.jetmap);
+  if (h->plan.order) cudaFree(h->plan.order);
   if (h->plan.n_total) cudaFree(h->plan.n_total);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;

@@ -35,6 +35,9 @@ struct Plan {          // device buffers describing how jets are packed into CTA
   int2* groups;        // [B]     (first jet, number of jets) of every group
   int* n_groups;       // [1]
   int* counter;        // [1]     dynamic work counter for persistent CTAs
+  int* jetmap;         // [B]     inference plan: jet handled at position i (groups are ranges of POSITIONS; jets are
+                       //         bin-packed by multiplicity, not taken in batch order)
+  int* order;          // [B]     scratch: jets sorted by multiplicity
   int* rowoff;         // [B]     first packed row of every jet (exclusive prefix sum of n_real)
   int* n_total;        // [1]     total number of real particles (= sum(mask), the loss denominator)
   int capB, capBN;
@@ -108,6 +111,7 @@ struct RunArgs {
   const float* dt;        // [n_steps] device
   int tbias_per_jet;      // 0: bias-table row = evaluation index; 1: row = jet index
   bool has_cbias;
+  const int* jetmap;      // position -> jet (nullptr: identity)
 };
 
 // fp32 CUDA-core path (epic_simt.cu)
