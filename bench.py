@@ -313,6 +313,11 @@ def main():
         flops = (float(n_real.sum()) * FLOP_PER_PARTICLE + B * FLOP_PER_JET) * NFE          # per launch, this rank
         k_ms = statistics.mean(kernel_ms)
         achieved = flops / (k_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if args.precision == "bf16" and os.path.exists(tpath):          # DRAM bytes of one ncu --set full capture, scaled per jet
+            tj = json.load(open(tpath))["epic_tc_kernel"]
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["jets"] * B
         peak = peaks["tf_sustained"]
         line = {"metric": "generated_jets_per_s", "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -327,7 +332,8 @@ def main():
                         "steps": e2e_steps, "api": "SetFlowMatchingLitModule.sample(n, mask=pinned).cpu()"},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None,
+                             "frac": achieved / peak, "traffic": traffic,
+                             "algorithmic_bytes_per_launch": B * (2 * N_PART * FEATS * 4 + N_PART * 4),
                              "kernel": "epic_tc_kernel" if args.precision == "bf16" else "epic_simt_kernel",
                              "kernel_ms": k_ms, "algorithmic_flop_per_launch": flops,
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)"}}
