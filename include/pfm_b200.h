@@ -127,6 +127,14 @@ int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float*
  * --------------------------------------------------------------------------------------------- */
 long long pfm_epic_grad_size(const pfm_epic* h);
 
+/* Data-parallel overlap: the weight gradients of the last backward are produced in pfm_epic_grad_chunks() consecutive
+ * slices of the flat buffer (offset / count in floats).  pfm_epic_stream_wait_grad_chunk makes `stream` wait until slice
+ * i is complete, so the host can enqueue the all-reduce of slice i on a side stream while later slices are still being
+ * computed (the reference gets this overlap from DDP's bucketed reducer, configs/trainer/ddp.yaml:4-9). */
+int pfm_epic_grad_chunks(const pfm_epic* h);
+int pfm_epic_grad_chunk_range(const pfm_epic* h, int i, long long* offset, long long* count);
+int pfm_epic_stream_wait_grad_chunk(pfm_epic* h, int i, void* stream);
+
 /* Fused flow-matching training step:  losses.py:38-77 (FM-OT), :101-136 (CFM), :308-342 (droid)
  * + the autograd backward of the network.  The random draws are the caller's (the reference draws
  * t on the CPU generator and the noise on the device):

@@ -43,6 +43,9 @@ _SIGNATURES = {
     "pfm_epic_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_grad_size": (C.c_longlong, [C.c_void_p]),
+    "pfm_epic_grad_chunks": (C.c_int, [C.c_void_p]),
+    "pfm_epic_grad_chunk_range": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "pfm_epic_stream_wait_grad_chunk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pfm_epic_loss_fwd_bwd": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, _F, _F, C.c_int, C.c_float, _F, _F, C.c_int,
                                         C.c_int, C.c_void_p]),
     "pfm_epic_forward_train": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),

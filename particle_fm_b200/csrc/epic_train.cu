@@ -28,6 +28,7 @@ namespace pfm {
 int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);
 
 static constexpr int kJMax = 16;     // upper bound of J_cap (simt_shape)
+static constexpr int kGradChunks = 3;
 
 struct BwdParams {
   int F, Kx, xin_off, H, Hp, LDH, Z, Zp, L, n_lin, LDP;
@@ -568,8 +569,13 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   if (!a.grad_flat) return PFM_OK;
 
   // ---- weight-gradient job table ----
+  // The jobs are cut into kGradChunks launches by linear index; an event after each lets a data-parallel host start the
+  // all-reduce of that slice of the flat gradient while the next chunk's weight gradients are still being computed.
   std::vector<XtyJob> jobs;
   int tile = 0;
+  const int n_chunks = h->n_lin < kGradChunks ? h->n_lin : kGradChunks;
+  std::vector<int> chunk_job0(n_chunks + 1, 0), chunk_tiles(n_chunks, 0);
+  h->grad_chunk_off.assign(n_chunks + 1, 0);
   size_t maxrows_jet = (size_t)a.B, maxrows_part = (size_t)a.B * a.N;
   auto add = [&](const float* Y, int ldy, int out, const float* X, int ldx, int K, int rows, float* dW, int ldw, int col0) {
     if (K <= 0 || out <= 0) return;
@@ -582,7 +588,13 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   const TrainLayout& lay = a.lay;
   const int Hp = lay.Hp;
   size_t off = 0;
+  int cur_chunk = 0;
   for (int i = 0; i < h->n_lin; ++i) {
+    const int chunk = (int)((long long)i * n_chunks / h->n_lin);
+    if (chunk != cur_chunk) {                       // close the previous chunk
+      chunk_tiles[cur_chunk] = tile; chunk_job0[chunk] = (int)jobs.size(); h->grad_chunk_off[chunk] = (long long)off;
+      cur_chunk = chunk; tile = 0;
+    }
     const Lin& L = h->lin_host[i];
     float* gW = a.grad_flat + off;
     float* gb = gW + (size_t)L.out * L.in;
@@ -619,6 +631,7 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
           c.hid, -1, gW, L.in, L.m_off);
     }
   }
+  chunk_tiles[cur_chunk] = tile; chunk_job0[n_chunks] = (int)jobs.size(); h->grad_chunk_off[n_chunks] = (long long)off;
   const size_t bytes = sizeof(XtyJob) * jobs.size();
   if (h->jobs_cap < bytes) {
     if (h->jobs_dev) cudaFree(h->jobs_dev);
@@ -626,13 +639,25 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
     PFM_CUDA_CHECK(cudaMalloc(&h->jobs_dev, bytes));
     h->jobs_cap = bytes;
   }
+  // pageable source: the runtime stages the table before cudaMemcpyAsync returns, no stream synchronisation needed
   PFM_CUDA_CHECK(cudaMemcpyAsync(h->jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice, st));
-  PFM_CUDA_CHECK(cudaStreamSynchronize(st));      // `jobs` is a host temporary
   const size_t maxrows = maxrows_part > maxrows_jet ? maxrows_part : maxrows_jet;
-  dim3 grid2((unsigned)((maxrows + X_CHUNK - 1) / X_CHUNK), (unsigned)tile);
-  xty_kernel<<<grid2, 256, 0, st>>>(reinterpret_cast<const XtyJob*>(h->jobs_dev), (int)jobs.size(), h->plan.n_total);
+  while ((int)h->grad_ev.size() < n_chunks) {
+    cudaEvent_t e;
+    PFM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->grad_ev.push_back(e);
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int nj = chunk_job0[c + 1] - chunk_job0[c];
+    if (nj > 0 && chunk_tiles[c] > 0) {
+      dim3 grid2((unsigned)((maxrows + X_CHUNK - 1) / X_CHUNK), (unsigned)chunk_tiles[c]);
+      xty_kernel<<<grid2, 256, 0, st>>>(reinterpret_cast<const XtyJob*>(h->jobs_dev) + chunk_job0[c], nj, h->plan.n_total);
+      h->last_launches += 1;
+    }
+    PFM_CUDA_CHECK(cudaEventRecord(h->grad_ev[c], st));
+  }
+  h->grad_chunks = n_chunks;
   PFM_CUDA_CHECK(cudaGetLastError());
-  h->last_launches += 1;
   return PFM_OK;
 }
 

@@ -502,6 +502,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->act = nullptr; h->act_cap = 0; h->dact = nullptr; h->dact_cap = 0; h->yact = nullptr; h->yact_cap = 0;
   h->jact = nullptr; h->jact_cap = 0; h->dpre3 = nullptr; h->dpre3_cap = 0;
   h->dbeff = nullptr; h->dbeff_cap = 0; h->dxs = nullptr; h->dxs_cap = 0; h->loss_acc = nullptr; h->ones = nullptr;
+  h->grad_chunks = 0;
   h->hs_spill = nullptr; h->hs_spill_cap = 0; h->dh_spill = nullptr; h->dh_spill_cap = 0;
   h->jobs_dev = nullptr; h->jobs_cap = 0; h->train_B = 0; h->train_N = 0; h->train_Kx = 0; h->train_xin_off = 0;
   h->tbias = nullptr; h->tbias_cap = 0; h->cbias = nullptr; h->cbias_cap = 0;
@@ -586,6 +587,7 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->plan.order) cudaFree(h->plan.order);
   if (h->plan.n_total) cudaFree(h->plan.n_total);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->grad_ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -689,6 +691,21 @@ float pfm_epic_last_kernel_ms(pfm_epic* h) {
     total += ms;
   }
   return total;
+}
+
+int pfm_epic_grad_chunks(const pfm_epic* h) { return h ? h->grad_chunks : PFM_ERR_INVALID; }
+
+int pfm_epic_grad_chunk_range(const pfm_epic* h, int i, long long* offset, long long* count) {
+  if (!h || i < 0 || i >= h->grad_chunks) { set_error("gradient chunk index out of range"); return PFM_ERR_INVALID; }
+  if (offset) *offset = h->grad_chunk_off[i];
+  if (count) *count = h->grad_chunk_off[i + 1] - h->grad_chunk_off[i];
+  return PFM_OK;
+}
+
+int pfm_epic_stream_wait_grad_chunk(pfm_epic* h, int i, void* stream) {
+  if (!h || i < 0 || i >= h->grad_chunks) { set_error("gradient chunk index out of range"); return PFM_ERR_INVALID; }
+  PFM_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, h->grad_ev[i], 0));
+  return PFM_OK;
 }
 
 long long pfm_epic_grad_size(const pfm_epic* h) { return h ? (long long)grad_floats(h) : (long long)PFM_ERR_INVALID; }

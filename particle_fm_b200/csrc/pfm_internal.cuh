@@ -76,6 +76,9 @@ struct pfm_epic {
   float* dpre3; size_t dpre3_cap;   // gradient at the head pre-activation [rows, F]
   float* dbeff; size_t dbeff_cap;   // gradient of the per-jet effective biases [B, bstride]
   float* dxs; size_t dxs_cap;       // gradient w.r.t. the per-particle input   [rows, Kx]
+  std::vector<cudaEvent_t> grad_ev;      // recorded after every chunk of weight-gradient jobs of the last backward
+  std::vector<long long> grad_chunk_off; // [chunks + 1] offsets of the chunks in the flat gradient
+  int grad_chunks;
   float* hs_spill; size_t hs_spill_cap;   // spill slabs of the fp32 kernels (hidden features of jets too large for smem)
   float* dh_spill; size_t dh_spill_cap;
   float* loss_acc;                  // [1] sum of squared errors

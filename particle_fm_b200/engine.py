@@ -172,6 +172,20 @@ class EpicEngine:
             off += o * i + o
         return views
 
+    def grad_chunks(self):
+        """[(offset, count)] slices of the flat gradient in the order the last backward completes them."""
+        n = int(self.lib.pfm_epic_grad_chunks(self._h))
+        off, cnt = C.c_longlong(), C.c_longlong()
+        out = []
+        for i in range(n):
+            _lib.check(self.lib.pfm_epic_grad_chunk_range(self._h, i, C.byref(off), C.byref(cnt)), "pfm_epic_grad_chunk_range")
+            out.append((off.value, cnt.value))
+        return out
+
+    def stream_wait_grad_chunk(self, i: int, stream: "torch.cuda.Stream"):
+        _lib.check(self.lib.pfm_epic_stream_wait_grad_chunk(self._h, i, C.c_void_p(stream.cuda_stream)),
+                   "pfm_epic_stream_wait_grad_chunk")
+
     def loss_fwd_bwd(self, kind: str, x: Tensor, mask: Optional[Tensor], cond: Optional[Tensor], t: Tensor,
                      t_code: Optional[Tensor], t_code_in: Optional[Tensor], n0: Tensor, n1: Optional[Tensor],
                      sigma: float, want_grad: bool = True):

@@ -18,12 +18,33 @@ import torch.distributed as dist
 
 
 def attach_flat_grad_allreduce(model, group=None):
-    """Average the flat gradient over `group` inside the fused training step of every flow of `model`."""
-    world = dist.get_world_size(group)
+    """Average the flat gradient over `group` inside the fused training step of every flow of `model`.
 
-    def hook(flat: torch.Tensor) -> torch.Tensor:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        return flat.div_(world)
+    The library finishes the weight gradients in a few consecutive slices of the flat buffer and records an event after
+    each; on CUDA the all-reduce of slice i is enqueued on a side stream that waits for that event only, so it overlaps
+    with the weight-gradient kernels of the later slices (and nothing on the host blocks).  The main stream waits for all
+    slices before the gradient is consumed."""
+    world = dist.get_world_size(group)
+    side = {}
+
+    def hook(flat: torch.Tensor, eng=None) -> torch.Tensor:
+        chunks = eng.grad_chunks() if (eng is not None and flat.is_cuda) else []
+        if not chunks:                                    # CPU tensors (gloo tests) or a single slice
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            return flat.div_(world)
+        dev = flat.device
+        if dev not in side:
+            side[dev] = torch.cuda.Stream(device=dev)
+        s = side[dev]
+        for i, (off, cnt) in enumerate(chunks):
+            eng.stream_wait_grad_chunk(i, s)               # slice i of the flat gradient is complete
+            with torch.cuda.stream(s):                     # NCCL orders itself after / before the side stream
+                piece = flat[off:off + cnt]
+                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
+                piece.div_(world)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        flat.record_stream(s)
+        return flat
 
     for f in model.flows:
         f.net.flat_grad_hook = hook

@@ -38,7 +38,7 @@ class _FMLossFn(torch.autograd.Function):
         loss, flat = eng.loss_fwd_bwd(kind, x, mask, cond, t, t_code, t_code_in, n0, n1, sigma, want_grad=want)
         hook = getattr(net, "flat_grad_hook", None)
         if want and hook is not None:
-            flat = hook(flat)                     # e.g. the data-parallel all-reduce of the flat gradient
+            flat = hook(flat, eng)                # e.g. the data-parallel all-reduce of the flat gradient
         ctx.eng, ctx.flat = eng, flat
         return loss.reshape(())
 
