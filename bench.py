@@ -210,7 +210,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PFM_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=0, help="jets per GPU per step (default: 16384 bf16 / 4096 fp32)")
     ap.add_argument("--all-real", action="store_true", help="every particle real (roofline variant)")
-    ap.add_argument("--ref-jets", type=int, default=8, help="jets per step of the CPU reference arm")
+    ap.add_argument("--ref-jets", type=int, default=32, help="jets per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-jets", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
