@@ -27,4 +27,8 @@ int tf_tc_linear(const LinArgs& a, int max_smem, cudaStream_t st);
 // image[(nt*kblocks + kb)*16384 + swizzle(n, k)] = bf16(Wt[k*ldo + n])   (zero beyond `in`)
 int tf_tc_pack(const float* Wt, int in, int out, int ldo, uint8_t* img, int kblocks, cudaStream_t st);
 
+// masked self attention on tcgen05 (tf_attn_tc.cu): head dim 16, <= 256 particles per jet
+int tf_attn_tc(const float* QKV, int ld, int D, int heads, const int* n_real, const int* rowoff, float* A, int lda, float scale,
+               int B, int N, int sm_count, cudaStream_t st);
+
 }  // namespace pfm

@@ -16,6 +16,7 @@
 //   tf_attn_*_kernel   softmax(q.k / sqrt(dh)) v per (jet, head) over the jet's REAL tokens only.
 //   small kernels      packing, context input, integrator update, unpacking.
 // Strict (fp32) path; the tensor-core version of the linear kernel is the next step for these networks.
+#include <cstdlib>
 #include <cstring>
 
 #include "pfm_internal.cuh"
@@ -630,7 +631,9 @@ static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, 
       TfLayer& Ly = h->layers[l];
       if ((rc = run_linear(h, st, h->h, D, D, &Ly.n1, Ly.qkv_or_q, 0, true, nullptr, 0, nullptr, nullptr, 0, h->QKV, 3 * D, 0,
                            rows)) != PFM_OK) return rc;
-      if (dh == 16)
+      if (h->precision == PFM_PREC_BF16 && dh == 16 && N <= 256 && !getenv("PFM_TF_SIMT_ATTN")) {
+        if ((rc = tf_attn_tc(h->QKV, 3 * D, D, c.num_heads, h->n_real, h->rowoff, h->A, D, scale, B, N, h->sm_count, st)) != PFM_OK) return rc;
+      } else if (dh == 16)
         tf_attn_self_kernel<16><<<dim3(B, c.num_heads), 128, sizeof(float) * 2 * (size_t)N * dh, st>>>(h->QKV, 3 * D, D, h->n_real,
                                                                                                   h->rowoff, h->A, D, scale);
       else if (dh == 8)
