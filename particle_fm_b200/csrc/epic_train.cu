@@ -51,11 +51,27 @@ __device__ __forceinline__ float dlrelu(float post, float slope) { return post >
 // d[r][i]: incoming gradient of the warp's RB rows (row = c0 + warp*RB + r, column lane + 32 i).  Multiplies by
 // leaky_relu'(saved post-activation of `stage`), stores the pre-activation gradient to the chunk buffer `tdst`
 // (A operand of the next product) and to dact[stage], and accumulates the per-jet column sums into db[jet][:].
+// Saved post-activations of the warp's RB rows of `stage`, loaded ahead of the GEMM whose result they will mask (the
+// loads are L2 / HBM latency: issued early, they overlap the GEMM instead of stalling the epilogue row by row).
 template <int TC, int RB>
-__device__ __forceinline__ void mask_store(const BwdParams& p, float (&d)[RB][TC], int c0, int R, int row_g0, int stage,
-                                           float* tdst, float* db, const short* rjet) {
+__device__ __forceinline__ void prefetch_act(const BwdParams& p, float (&a)[RB][TC], int c0, int R, int row_g0, int stage) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* a_st = p.act + (size_t)stage * p.stage_stride;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int row = c0 + warp * RB + r;
+#pragma unroll
+    for (int i = 0; i < TC; ++i) {
+      const int o = lane + 32 * i;
+      a[r][i] = (row < R && o < p.H) ? __ldg(a_st + (size_t)(row_g0 + row) * p.Hp_act + o) : 1.f;
+    }
+  }
+}
+
+template <int TC, int RB>
+__device__ __forceinline__ void mask_store(const BwdParams& p, float (&d)[RB][TC], const float (&act)[RB][TC], int c0, int R,
+                                           int row_g0, int stage, float* tdst, float* db, const short* rjet) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* d_st = p.dact + (size_t)stage * p.stage_stride;
   int cur = -1;
   float s[TC];
@@ -82,7 +98,7 @@ __device__ __forceinline__ void mask_store(const BwdParams& p, float (&d)[RB][TC
         const int o = lane + 32 * i;
         if (o < p.H) {
           const size_t gi = (size_t)(row_g0 + row) * p.Hp_act + o;
-          const float v = d[r][i] * dlrelu(a_st[gi], p.slope);
+          const float v = d[r][i] * dlrelu(act[r][i], p.slope);
           d[r][i] = v;
           tdst[(warp * RB + r) * p.LDH + o] = v;
           d_st[gi] = v;
@@ -135,12 +151,25 @@ __device__ __forceinline__ void global_backward(const BwdParams& p, const Lin& G
   }
   __syncthreads();
   // din[j][k] = sum_o W_a[o][m_off + k] pg1[j][o]
+  // every thread owns column k = tid (and tid + 256, 512 ... while < m_len); 4 weight loads are in flight per step
   for (int k = tid; k < Ga.m_len; k += kThreads) {
     float acc[kJMax];
 #pragma unroll
     for (int j = 0; j < kJMax; ++j) acc[j] = 0.f;
-    for (int o = 0; o < H; ++o) {
-      const float w = __ldg(Ga.Wr + (size_t)o * Ga.ldr + k);
+    const float* wk = Ga.Wr + k;
+    int o = 0;
+    for (; o + 4 <= H; o += 4) {
+      float w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = __ldg(wk + (size_t)(o + q) * Ga.ldr);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < kJMax; ++j)
+          if (j < nj) acc[j] = fmaf(w[q], pg1[j * p.Hp + o + q], acc[j]);
+    }
+    for (; o < H; ++o) {
+      const float w = __ldg(wk + (size_t)o * Ga.ldr);
 #pragma unroll
       for (int j = 0; j < kJMax; ++j)
         if (j < nj) acc[j] = fmaf(w, pg1[j * p.Hp + o], acc[j]);
@@ -264,10 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p
             d[r][i] = (row < R && o < H) ? dh[(size_t)row * LDH + o] : 0.f;
           }
         }
-        mask_store<TC, RB>(p, d, c0, R, row_g0, st_h, tA, db2, rjet);          // d pre(fc_local2)
+        float a_h[RB][TC], a_u[RB][TC];
+        prefetch_act<TC, RB>(p, a_h, c0, R, row_g0, st_h);
+        prefetch_act<TC, RB>(p, a_u, c0, R, row_g0, st_u);
+        mask_store<TC, RB>(p, d, a_h, c0, R, row_g0, st_h, tA, db2, rjet);     // d pre(fc_local2)
         __syncwarp();
         gemm_rows<TC, RB>(tA, LDH, Lb.Wr, Lb.out, Lb.ldr, wbuf, p.wbuf_floats, p.KC, d);     // du = dpre2 . W2
-        mask_store<TC, RB>(p, d, c0, R, row_g0, st_u, tB, db1, rjet);          // d pre(fc_local1)
+        mask_store<TC, RB>(p, d, a_u, c0, R, row_g0, st_u, tB, db1, rjet);     // d pre(fc_local1)
         __syncwarp();
         gemm_rows<TC, RB>(tB, LDH, La.Wr, La.out, La.ldr, wbuf, p.wbuf_floats, p.KC, d);     // dpre1 . W1(main)
 #pragma unroll
@@ -318,7 +350,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p
             d[r][i] = (row < R && o < H) ? dh[(size_t)row * LDH + o] : 0.f;
           }
         }
-        mask_store<TC, RB>(p, d, c0, R, row_g0, 1, tA, db2, rjet);             // d pre(fc_l2)
+        float a_h[RB][TC], a_u[RB][TC];
+        prefetch_act<TC, RB>(p, a_h, c0, R, row_g0, 1);
+        prefetch_act<TC, RB>(p, a_u, c0, R, row_g0, 0);
+        mask_store<TC, RB>(p, d, a_h, c0, R, row_g0, 1, tA, db2, rjet);        // d pre(fc_l2)
         __syncwarp();
         gemm_rows<TC, RB>(tA, LDH, L2.Wr, L2.out, L2.ldr, wbuf, p.wbuf_floats, p.KC, d);
 #pragma unroll
@@ -328,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p
             const int o = lane + 32 * i;
             if (o < H) d[r][i] += tA[(warp * RB + r) * LDH + o];               // residual h1
           }
-        mask_store<TC, RB>(p, d, c0, R, row_g0, 0, tB, db1, rjet);             // d pre(fc_l1)
+        mask_store<TC, RB>(p, d, a_u, c0, R, row_g0, 0, tB, db1, rjet);        // d pre(fc_l1)
         __syncwarp();
         if (p.dxs) {     // gradient w.r.t. the per-particle input columns
           for (int r = 0; r < RB; ++r) {
@@ -370,7 +405,7 @@ struct XtyJob {
 
 static constexpr int XT = 128;        // output tile edge
 static constexpr int XR = 16;         // rows staged per iteration
-static constexpr int X_CHUNK = 512;   // rows per block
+static constexpr int X_CHUNK = 512;   // rows per block (2048 was measured 20 % slower: too few blocks)
 
 __global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total) {
   __shared__ __align__(16) float sY[XR][XT];
