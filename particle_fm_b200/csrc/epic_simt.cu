@@ -48,6 +48,21 @@ __device__ __forceinline__ float bias_of(const SimtParams& p, const Lin& L, int 
   return b;
 }
 
+// a + sum_k w[k*ldo] * in[k]  (one output column of a k-major weight block, weights from L2): 8 loads in flight per step
+// -- these per-jet products are latency-bound, not bandwidth-bound; same summation order as a plain loop
+__device__ __forceinline__ float gemv_col(const float* __restrict__ w, int ldo, const float* __restrict__ in, int K, float a) {
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {
+    float wv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wv[q] = __ldg(w + (size_t)(k + q) * ldo);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a = fmaf(wv[q], in[k + q], a);
+  }
+  for (; k < K; ++k) a = fmaf(__ldg(w + (size_t)k * ldo), in[k], a);
+  return a;
+}
+
 template <int TC, int RB, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -206,8 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           float a = bias_of(p, G1, ev, jid[j], o);
           const float* w = G1.Wt + (size_t)G1.m_off * G1.ldo + o;
           const float* in = pool + j * LDP;
-#pragma unroll 4
-          for (int k = 0; k < 2 * H; ++k) a = fmaf(__ldg(w + (size_t)k * G1.ldo), in[k], a);
+          a = gemv_col(w, G1.ldo, in, 2 * H, a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
           if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + p.LDP_act + o] = g1[j * p.Hp + o];        // unit 0: g1
         }
@@ -217,8 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           float a = bias_of(p, G2, ev, jid[j], o);
           const float* w = G2.Wt + (size_t)G2.m_off * G2.ldo + o;
           const float* in = g1 + j * p.Hp;
-#pragma unroll 4
-          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * G2.ldo), in[k], a);
+          a = gemv_col(w, G2.ldo, in, H, a);
           gv[j * Z + o] = lrelu(a, p.slope);                       // no residual in the stem, :378-380
           if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + p.LDP_act + p.Hp_act + o] = gv[j * Z + o]; // unit 0: g
         }
@@ -252,9 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           float a = bias_of(p, Ga, ev, jid[j], o);
           const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + o;
           const float* in = pool + j * LDP;
-          const int K = 2 * H + Z;
-#pragma unroll 4
-          for (int k = 0; k < K; ++k) a = fmaf(__ldg(w + (size_t)k * Ga.ldo), in[k], a);
+          a = gemv_col(w, Ga.ldo, in, 2 * H + Z, a);
           g1[j * p.Hp + o] = lrelu(a, p.slope);
           if (TRAIN) p.jact[(size_t)jid[j] * p.jstride + (size_t)(l + 1) * p.junit + p.LDP_act + o] = g1[j * p.Hp + o];
         }
@@ -264,8 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           float a = bias_of(p, Gb, ev, jid[j], o);
           const float* w = Gb.Wt + (size_t)Gb.m_off * Gb.ldo + o;
           const float* in = g1 + j * p.Hp;
-#pragma unroll 4
-          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w + (size_t)k * Gb.ldo), in[k], a);
+          a = gemv_col(w, Gb.ldo, in, H, a);
           // the new global vector is written to the pool row first (gv is still being read as the residual
           // by other threads only through gv[j*Z+o] of the SAME (j,o) -> safe in place)
           gv[j * Z + o] = lrelu(a + gv[j * Z + o], p.slope);
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           float a = bias_of(p, La, ev, jid[j], o);
           const float* w = La.Wt + (size_t)La.g_off * La.ldo + o;
           const float* in = gv + j * Z;
-          for (int k = 0; k < Z; ++k) a = fmaf(__ldg(w + (size_t)k * La.ldo), in[k], a);
+          a = gemv_col(w, La.ldo, in, Z, a);
           bl1[j * LDB + o] = a;
           bl2[j * LDB + o] = bias_of(p, Lb, ev, jid[j], o);
         }
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
           const int row = i / F, f = i - row * F;
           float a = bias_of(p, L3, ev, jid[rjet[row]], f);
           const float* hr = hs + (size_t)row * LDH;
-          for (int k = 0; k < H; ++k) a = fmaf(__ldg(w3 + (size_t)k * L3.ldo + f), hr[k], a);
+          a = gemv_col(w3 + f, L3.ldo, hr, H, a);
           vbuf[i] = lrelu(a, p.slope);
         }
         __syncthreads();

@@ -321,7 +321,14 @@ __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p
         const int j = i / Z, z = i - j * Z;
         const float* w = La.Wt + (size_t)(La.g_off + z) * La.ldo;
         float a = dG[j * p.Zp + z];
-        for (int o = 0; o < H; ++o) a = fmaf(__ldg(w + o), db1[j * p.Hp + o], a);
+        for (int o = 0; o < H; o += 8) {          // 8 loads in flight (H is a multiple of 4; the tail is guarded)
+          float wv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) wv[q] = o + q < H ? __ldg(w + o + q) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (o + q < H) a = fmaf(wv[q], db1[j * p.Hp + o + q], a);
+        }
         dG[j * p.Zp + z] = a;
       }
       for (int i = tid; i < nj * H; i += kThreads) {
