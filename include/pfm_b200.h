@@ -204,6 +204,24 @@ int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* con
 int pfm_tf_set_precision(pfm_tf* h, int precision /* pfm_precision */);
 int pfm_tf_last_launches(const pfm_tf* h);
 
+/* ---- training of the droid transformers (replaces torch autograd over droid_transformer.py:211-284, 331-344,
+ * 386-397, 529-548, 696-711).  The reference neither masks the networks' output nor the loss terms of padded slots
+ * (losses.py:74-76, 130, 339-341 sum over every slot), so training runs on all B*N rows with only the attention KEYS
+ * restricted to real particles; mask is required.  fp32 whatever pfm_tf_set_precision says.
+ *   pfm_tf_grad_size      floats of the flat gradient: the parameters of pfm_tf_param_shape, in that order, each row-major
+ *   pfm_tf_forward_train  pfm_tf_forward on the dense rows (padded slots get the reference's values, not 0) + saved tape
+ *   pfm_tf_backward       d(out) [B,N,feats] -> grad_flat, consumes the tape of the last pfm_tf_forward_train
+ *   pfm_tf_loss_fwd_bwd   FlowMatchingLoss / ConditionalFlowMatchingLoss / DroidLoss forward (losses.py:38-77, 101-136,
+ *                         308-342) with the given draws (t [B], t_code [B,t_dim], noise0/noise1 [B,N,feats]) and, when
+ *                         grad_flat != NULL, its backward; loss_out: one device float. */
+int64_t pfm_tf_grad_size(const pfm_tf* h);
+int pfm_tf_forward_train(pfm_tf* h, const float* t_code, int t_rows, const float* x, const float* mask,
+                         const float* cond, float* out, int B, int N, void* stream);
+int pfm_tf_backward(pfm_tf* h, const float* dout, float* grad_flat, void* stream);
+int pfm_tf_loss_fwd_bwd(pfm_tf* h, const float* x1, const float* t, const float* t_code, const float* noise0,
+                        const float* noise1, const float* mask, const float* cond, int loss_kind, float sigma,
+                        float* loss_out, float* grad_flat, int B, int N, void* stream);
+
 /* Introspection for tests / bench: kernels launched by the last call on this handle and the
  * number of CTA work groups the last plan produced. */
 int pfm_epic_last_launches(const pfm_epic* h);

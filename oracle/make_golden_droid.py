@@ -72,11 +72,46 @@ def main():
         for a, b, what in ((o_s, v_s, "sampling"), (o_t, v_t, "training")):
             err = float((a - b).abs().max())
             assert err <= 1e-6 * max(1.0, float(b.abs().max())), (name, what, err)
+        # -- training: the reference's own loss modules + autograd vs autograd through the oracle restatement, same draws
+        # (losses.py sums (v - u)^2 over EVERY slot and the droid nets do not mask their output, so padded slots count)
+        import torch.nn as nn
+        from . import loss_oracle as lo
+        extra = {}
+        kw = dict(t_emb="cosine", frequencies=16)
+        for kind, cls in (("FM-OT", "FlowMatchingLoss"), ("CFM", "ConditionalFlowMatchingLoss"), ("droid", "DroidLoss")):
+            loss_mod = getattr(R.losses, cls)(flows=nn.ModuleList([cnf]), sigma=1e-4)
+            cnf.zero_grad()
+            torch.manual_seed(4242)
+            loss_r = loss_mod(x, mask=mask, cond=rc)
+            loss_r.backward()
+            torch.manual_seed(4242)
+            t, n0, n1 = lo.draw_loss_randoms(kind, x)
+            sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            loss_o = lo.fm_loss(lambda tt, y: do.cnf_forward(sd_g, cfg, tt, y, cond, mask, **kw), kind, x, mask, t, n0, n1, 1e-4)
+            loss_o.backward()
+            assert abs(float(loss_r) - float(loss_o)) <= 1e-6 * abs(float(loss_r)), (name, kind, loss_r, loss_o)
+            gmax, gref = 0.0, 0.0
+            params = list(cnf.net.named_parameters())
+            for k, prm in params:
+                gmax = max(gmax, float((prm.grad - sd_g[k].grad).abs().max()))
+                gref = max(gref, float(prm.grad.abs().max()))
+            assert gmax <= 2e-5 * gref, (name, kind, gmax, gref)
+            tag = kind.replace("-", "").lower()
+            extra[f"loss_{tag}"] = loss_r.detach().numpy()
+            extra[f"loss_{tag}_t"] = t.numpy()
+            if kind == "FM-OT":       # the draws and a digest of the reference's gradient for one loss kind
+                extra["loss_n0"] = n0.numpy()
+                extra["grad_fmot_names"] = np.array([k for k, _ in params])
+                extra["grad_fmot_norms"] = np.array([float(prm.grad.double().norm()) for _, prm in params], dtype="float64")
+                extra["grad_fmot_sums"] = np.array([float(prm.grad.double().sum()) for _, prm in params], dtype="float64")
+                extra["grad_fmot_vectors"] = torch.cat([prm.grad.flatten() for _, prm in params if prm.dim() == 1]).numpy()
+            print(f"  {name:22s} loss[{kind}] = {float(loss_r):.6f}  max|grad diff| = {gmax:.2e} (max|grad| {gref:.2e})")
         out = dict(x=x.numpy(), mask=mask.numpy(), t_sample=t_s.numpy(), t_train=t_b.numpy(), v_sample=v_s.numpy(),
                    v_train=v_t.numpy(), sample_euler5=end.numpy(),
                    meta=np.array(json.dumps(dict(cfg=cfg.as_dict(), wseed=c["wseed"], N=c["N"], kind=c["kind"]))))
         if cond is not None:
             out["cond"] = cond.numpy()
+        out.update(extra)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
         print(f"{name}: oracle == reference (max |v| {float(v_s.abs().max()):.3f}), saved")
 

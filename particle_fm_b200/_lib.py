@@ -59,6 +59,11 @@ _SIGNATURES = {
     "pfm_tf_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pfm_tf_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "pfm_tf_last_launches": (C.c_int, [C.c_void_p]),
+    "pfm_tf_grad_size": (C.c_longlong, [C.c_void_p]),
+    "pfm_tf_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
+    "pfm_tf_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pfm_tf_loss_fwd_bwd": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),
     "pfm_epic_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -402,32 +402,16 @@ __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p
 // weight gradients:  dW[o*ldw + col0 + c] += sum_r Y[r*ldy + o] * X[r*ldx + c]      (o < out, c < K, r < rows)
 // grid = (row chunks, tiles of all jobs); one block = one 128 x 128 output tile over one chunk of rows.
 // ---------------------------------------------------------------------------------------------
-struct XtyJob {
-  const float* Y; const float* X; float* dW;
-  int ldy, ldx, ldw, out, K, col0;
-  int rows;            // >= 0: fixed row count;  < 0: *n_total (particle rows)
-  int tile0;           // first tile index of this job in grid.y
-  int tiles_o, tiles_k;
-};
-
 static constexpr int XT = 128;        // output tile edge
 static constexpr int XR = 16;         // rows staged per iteration
 static constexpr int X_CHUNK = 512;   // rows per block (2048 was measured 20 % slower: too few blocks)
 
-__global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total) {
+__device__ __forceinline__ void xty_tile(const XtyJob& J, int rows, int t_local) {
   __shared__ __align__(16) float sY[XR][XT];
   __shared__ __align__(16) float sX[XR][XT];
-  // locate the job of this tile (few dozen jobs: linear scan by one thread would do; every thread scans, it is cheap)
-  int jb = 0;
-  const int tile = blockIdx.y;
-  for (int i = 1; i < n_jobs; ++i)
-    if (jobs[i].tile0 <= tile) jb = i;
-  const XtyJob J = jobs[jb];
-  const int rows = J.rows >= 0 ? J.rows : *n_total;
   const int r_begin = blockIdx.x * X_CHUNK;
   if (r_begin >= rows) return;
   const int r_end = min(rows, r_begin + X_CHUNK);
-  const int t_local = tile - J.tile0;
   const int o0 = (t_local / J.tiles_k) * XT, k0 = (t_local % J.tiles_k) * XT;
   const int tid = threadIdx.x;
   const int to = tid >> 4, tk = tid & 15;      // 16 x 16 threads, 8 x 8 outputs each
@@ -473,6 +457,31 @@ __global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ job
       if (k < J.K) atomicAdd(J.dW + (size_t)o * J.ldw + J.col0 + k, acc[a][b]);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total) {
+  // locate the job of this tile (a few dozen jobs: every thread scans, it is cheap)
+  int jb = 0;
+  const int tile = blockIdx.y;
+  for (int i = 1; i < n_jobs; ++i)
+    if (jobs[i].tile0 <= tile) jb = i;
+  const XtyJob J = jobs[jb];
+  xty_tile(J, J.rows >= 0 ? J.rows : *n_total, tile - J.tile0);
+}
+
+// one job passed by value (the droid training path launches one product per linear)
+__global__ void __launch_bounds__(256) xty_one_kernel(const XtyJob J) { xty_tile(J, J.rows, blockIdx.y); }
+
+int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
+                   cudaStream_t st) {
+  if (rows <= 0 || out <= 0 || K <= 0) return PFM_OK;
+  XtyJob J;
+  J.Y = Y; J.X = X; J.dW = dW; J.ldy = ldy; J.ldx = ldx; J.ldw = ldw; J.out = out; J.K = K; J.col0 = col0; J.rows = rows; J.tile0 = 0;
+  J.tiles_o = (out + XT - 1) / XT; J.tiles_k = (K + XT - 1) / XT;
+  dim3 grid((unsigned)((rows + X_CHUNK - 1) / X_CHUNK), (unsigned)(J.tiles_o * J.tiles_k));
+  xty_one_kernel<<<grid, 256, 0, st>>>(J);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -147,6 +147,16 @@ struct TrainBwdArgs {
   TrainLayout lay;
 };
 int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st);
+// weight-gradient product dW[o*ldw + col0 + c] += sum_r Y[r*ldy + o] * X[r*ldx + c]  (epic_train.cu::xty_kernel)
+struct XtyJob {
+  const float* Y; const float* X; float* dW;
+  int ldy, ldx, ldw, out, K, col0;
+  int rows;            // >= 0: fixed row count;  < 0: *n_total (particle rows)
+  int tile0;           // first tile index of this job in grid.y
+  int tiles_o, tiles_k;
+};
+int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
+                   cudaStream_t st);
 int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);
 // bf16 tcgen05 path (epic_tc.cu)
 int tc_supported(const pfm_epic* h, int N);

@@ -25,9 +25,6 @@
 
 namespace pfm {
 
-// plan kernels of pfm_api.cu
-__global__ void plan_count_kernel(const float* __restrict__ mask, int B, int N, int* __restrict__ n_real, uint16_t* __restrict__ ridx);
-
 static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------
@@ -421,38 +418,11 @@ __global__ void tf_update_kernel(float* __restrict__ x0, float* __restrict__ xc,
 }  // namespace pfm
 
 // =============================================================================================
-// handle
+// handle (struct pfm_tf: tf_internal.cuh)
 // =============================================================================================
-namespace {
-struct TfLinear { int in = 0, out = 0, ldo = 0; float* Wt = nullptr; float* b = nullptr; uint8_t* img = nullptr; int kblocks = 0; };
-struct TfLN { int d = 0; float* g = nullptr; float* b = nullptr; };
-struct TfDense { TfLinear l1; TfLN ln; TfLinear l2; };
-struct TfLayer { TfLinear qkv_or_q, kv, out; TfLN mha_ln; TfDense dense; TfLN n0, n1, n2; };
-struct ParamSlot { int rows, cols; int kind; void* target; int col_off; };   // kind 0: linear W, 1: vector, 2: tokens
-}  // namespace
-
-struct pfm_tf {
-  pfm_tf_cfg cfg;
-  int device, sm_count, max_smem;
-  bool weights_set;
-  TfDense ctxt, node, outp;
-  std::vector<TfLayer> layers;       // full: L layers; cross: from_0..from_{L-1}, to_0..to_{L-1}
-  TfLN final_norm;
-  float* tok0;                       // [ntok, D]
-  std::vector<ParamSlot> slots;      // canonical parameter order
-  std::vector<float*> owned;
-  // plan + workspaces
-  int capB, capBN; size_t cap_rows;
-  int *n_real, *rowoff, *n_total, *rowjet, *tokjet; uint16_t* ridx;
-  float *xs, *x0, *v, *h, *H1, *QKV, *A, *tok, *tokA, *tokQ, *tokKV, *tokH1, *ctxin, *c1, *ctx, *jb; size_t jb_floats;
-  int last_launches;
-  int precision;                     // PFM_PREC_FP32 / PFM_PREC_BF16 (tcgen05 linears where the shape allows)
-  std::vector<TfLinear*> all_linears;
-};
-
 namespace pfm {
 
-static float* tf_alloc(pfm_tf* h, size_t floats) {
+float* tf_alloc(pfm_tf* h, size_t floats) {
   float* p = nullptr;
   if (cudaMalloc(&p, sizeof(float) * (floats ? floats : 1)) != cudaSuccess) return nullptr;
   cudaMemset(p, 0, sizeof(float) * (floats ? floats : 1));
@@ -464,6 +434,9 @@ static bool tf_make_linear(pfm_tf* h, TfLinear* L, int out, int in) {
   L->in = in; L->out = out; L->ldo = round_up_i(out, 64);
   L->Wt = tf_alloc(h, (size_t)(in + 4) * L->ldo);
   L->b = tf_alloc(h, L->ldo);
+  L->ldw = round_up_i(in, 64);
+  L->Wrow = tf_alloc(h, (size_t)(out + 4) * L->ldw + 64);
+  if (!L->Wrow) return false;
   if (out % 128 == 0 && in >= 64) {      // eligible for the tensor-core path: bf16 image of 16 KB [128 n x 64 k] blocks
     L->kblocks = (in + 63) / 64;
     L->img = reinterpret_cast<uint8_t*>(tf_alloc(h, (size_t)(out / 128) * L->kblocks * 16384 / sizeof(float)));
@@ -481,10 +454,16 @@ static bool tf_make_dense(pfm_tf* h, TfDense* d, int inpt, int ctxt, int hddn, i
 }
 static void slot_linear(pfm_tf* h, TfLinear* L, int col_off = 0, int out = -1) {
   const int o = out < 0 ? L->out : out;
+  const int part = L->n_parts++;
+  if (part == 1) L->split = col_off;
+  L->gw_off[part] = h->grad_floats; h->grad_floats += (size_t)o * L->in;
+  L->gb_off[part] = h->grad_floats; h->grad_floats += (size_t)o;
   h->slots.push_back({o, L->in, 0, L, col_off});
   h->slots.push_back({o, 1, 1, L->b + col_off, 0});
 }
 static void slot_ln(pfm_tf* h, TfLN* n) {
+  n->gg_off = h->grad_floats; h->grad_floats += (size_t)n->d;
+  n->gb_off = h->grad_floats; h->grad_floats += (size_t)n->d;
   h->slots.push_back({n->d, 1, 1, n->g, 0});
   h->slots.push_back({n->d, 1, 1, n->b, 0});
 }
@@ -511,9 +490,24 @@ static int launch_linear_tc(const pfm_tf* h, const LinArgs& a, cudaStream_t st) 
 }
 
 // Y[rows, N] = [R +] act(LN(X[rows, K]) . W[k0 : k0+K]^T + bias [+ jb[rowjet]])
-static int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K, const TfLN* ln, const TfLinear& L, int k0,
-                      bool use_bias, const float* jb, int jb_stride, const int* rowjet, const float* R, int ldr, float* Y,
-                      int ldy, int act, int rows) {
+int tf_launch_linear(pfm_tf* h, const LinArgs& a, int ldo_class, bool allow_tc, cudaStream_t st) {
+  h->last_launches++;
+  // tensor cores for the per-token linears; the per-jet context / bias tables (a handful of rows) stay fp32
+  if (allow_tc && h->precision == PFM_PREC_BF16 && a.rows >= 256 && tf_tc_linear_supported(a)) return tf_tc_linear(a, h->max_smem, st);
+  if (a.N <= 8 && a.rows >= 64 && a.K <= 512) {
+    const int blocks = (a.rows + 63) / 64 < 4 * h->sm_count ? (a.rows + 63) / 64 : 4 * h->sm_count;
+    tf_linear_smalln_kernel<<<blocks, 256, sizeof(float) * (size_t)a.K * 10, st>>>(a);
+    PFM_CUDA_CHECK(cudaGetLastError());
+    return PFM_OK;
+  }
+  if (ldo_class % 256 == 0) return launch_linear_tc<8>(h, a, st);
+  if (ldo_class % 128 == 0) return launch_linear_tc<4>(h, a, st);
+  return launch_linear_tc<2>(h, a, st);
+}
+
+int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K, const TfLN* ln, const TfLinear& L, int k0,
+               bool use_bias, const float* jb, int jb_stride, const int* rowjet, const float* R, int ldr, float* Y,
+               int ldy, int act, int rows) {
   if (rows <= 0) return PFM_OK;
   LinArgs a;
   a.X = X; a.ldx = ldx; a.K = K;
@@ -525,18 +519,7 @@ static int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K
   a.act = act; a.slope = h->cfg.neg_slope; a.eps = h->cfg.ln_eps;
   a.rows = rows;
   a.img = L.img; a.img_kblocks = L.kblocks; a.kb0 = k0 / 64;
-  h->last_launches++;
-  // tensor cores for the per-token linears; the per-jet context / bias tables (a handful of rows) stay fp32
-  if (h->precision == PFM_PREC_BF16 && rows >= 256 && (k0 % 64) == 0 && tf_tc_linear_supported(a)) return tf_tc_linear(a, h->max_smem, st);
-  if (a.N <= 8 && rows >= 64 && a.K <= 512) {
-    const int blocks = (rows + 63) / 64 < 4 * h->sm_count ? (rows + 63) / 64 : 4 * h->sm_count;
-    tf_linear_smalln_kernel<<<blocks, 256, sizeof(float) * (size_t)a.K * 10, st>>>(a);
-    PFM_CUDA_CHECK(cudaGetLastError());
-    return PFM_OK;
-  }
-  if (L.ldo % 256 == 0) return launch_linear_tc<8>(h, a, st);
-  if (L.ldo % 128 == 0) return launch_linear_tc<4>(h, a, st);
-  return launch_linear_tc<2>(h, a, st);
+  return tf_launch_linear(h, a, L.ldo, (k0 % 64) == 0, st);
 }
 
 static int tf_ensure(pfm_tf* h, int B, int N) {
@@ -722,6 +705,7 @@ int pfm_tf_create(const pfm_tf_cfg* cfg, int device, pfm_tf** out) {
   PFM_CUDA_CHECK(cudaSetDevice(device));
   pfm_tf* h = new pfm_tf();
   h->cfg = c; h->device = device; h->weights_set = false; h->tok0 = nullptr;
+  h->grad_floats = 0; h->tok0_goff = 0; h->tape = nullptr;
   h->capB = 0; h->capBN = 0; h->cap_rows = 0;
   h->n_real = h->rowoff = h->n_total = h->rowjet = h->tokjet = nullptr; h->ridx = nullptr;
   h->xs = h->x0 = h->v = h->h = h->H1 = h->QKV = h->A = h->tok = h->tokA = h->tokQ = h->tokKV = h->tokH1 = h->ctxin = h->c1 = h->ctx = h->jb = nullptr;
@@ -747,6 +731,7 @@ int pfm_tf_create(const pfm_tf_cfg* cfg, int device, pfm_tf** out) {
   } else {
     h->tok0 = tf_alloc(h, (size_t)c.num_tokens * D);
     ok = ok && h->tok0;
+    h->tok0_goff = h->grad_floats; h->grad_floats += (size_t)c.num_tokens * D;
     h->slots.push_back({c.num_tokens, D, 2, h->tok0, 0});
     for (int l = 0; l < nl && ok; ++l) {
       TfLayer& L = h->layers[l];
@@ -771,6 +756,7 @@ int pfm_tf_create(const pfm_tf_cfg* cfg, int device, pfm_tf** out) {
 void pfm_tf_destroy(pfm_tf* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  tf_tape_destroy(h);
   for (float* p : h->owned) cudaFree(p);
   for (void* p : {(void*)h->n_real, (void*)h->rowoff, (void*)h->n_total, (void*)h->rowjet, (void*)h->tokjet, (void*)h->ridx,
                   (void*)h->xs, (void*)h->x0, (void*)h->v, (void*)h->h, (void*)h->H1, (void*)h->QKV, (void*)h->A, (void*)h->tok,
@@ -801,6 +787,8 @@ int pfm_tf_set_weights(pfm_tf* h, const float* const* params, int n, void* strea
       TfLinear* L = reinterpret_cast<TfLinear*>(s.target);
       const int total = s.rows * s.cols;
       tf_transpose_kernel<<<(total + 255) / 256, 256, 0, st>>>(params[i], L->Wt, s.rows, s.cols, L->ldo, s.col_off);
+      PFM_CUDA_CHECK(cudaMemcpy2DAsync(L->Wrow + (size_t)s.col_off * L->ldw, sizeof(float) * L->ldw, params[i], sizeof(float) * s.cols,
+                                       sizeof(float) * s.cols, s.rows, cudaMemcpyDeviceToDevice, st));
     } else {
       PFM_CUDA_CHECK(cudaMemcpyAsync(s.target, params[i], sizeof(float) * (size_t)s.rows * s.cols, cudaMemcpyDeviceToDevice, st));
     }

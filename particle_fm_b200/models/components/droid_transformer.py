@@ -231,8 +231,119 @@ class _TfEngine:
                        "pfm_tf_sample")
         return x
 
+    # ---- training (fp32, dense rows: the reference neither masks the output nor the loss of padded slots) ----
+    def grad_size(self) -> int:
+        return int(self.lib.pfm_tf_grad_size(self._h))
+
+    def grad_views(self, flat: Tensor):
+        """Per-parameter views of the flat gradient, in parameter (= state_dict) order, each [rows, cols] row-major."""
+        out, off = [], 0
+        for r, c in self.param_shapes():
+            out.append(flat[off:off + r * c])
+            off += r * c
+        return out
+
+    def forward_train(self, t_code: Tensor, x: Tensor, mask: Tensor, cond: Optional[Tensor]) -> Tensor:
+        B, N = int(x.shape[0]), int(x.shape[1])
+        x = self._f32(x, self.device)
+        mask = self._f32(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        t_code = self._f32(t_code, self.device).reshape(-1, self.cfg["t_dim"])
+        out = torch.empty(B, N, self.cfg["feats"], device=self.device, dtype=torch.float32)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_tf_forward_train(self._h, p(t_code), int(t_code.shape[0]), p(x), p(mask), p(cond), p(out), B, N,
+                                                     self._stream()), "pfm_tf_forward_train")
+        self._ticket = getattr(self, "_ticket", 0) + 1
+        return out, self._ticket
+
+    def backward(self, ticket: int, gout: Tensor) -> Tensor:
+        if ticket != getattr(self, "_ticket", None):
+            raise RuntimeError("the droid engine keeps ONE saved forward: backward() was called after another training "
+                               "forward on the same network")
+        gout = self._f32(gout, self.device)
+        flat = torch.empty(self.grad_size(), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_tf_backward(self._h, C.c_void_p(gout.data_ptr()), C.c_void_p(flat.data_ptr()), self._stream()),
+                       "pfm_tf_backward")
+        return flat
+
+    def loss_fwd_bwd(self, kind: str, x, mask, cond, t, t_code, n0, n1, sigma: float, want_grad: bool = True):
+        B, N = int(x.shape[0]), int(x.shape[1])
+        x = self._f32(x, self.device)
+        mask = self._f32(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        t = self._f32(t, self.device).reshape(B)
+        t_code = self._f32(t_code, self.device).reshape(B, self.cfg["t_dim"])
+        n0 = self._f32(n0, self.device)
+        n1 = None if n1 is None else self._f32(n1, self.device)
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        flat = torch.empty(self.grad_size(), device=self.device, dtype=torch.float32) if want_grad else None
+        code = {"FM-OT": _lib.PFM_LOSS_FM_OT, "CFM": _lib.PFM_LOSS_CFM, "droid": _lib.PFM_LOSS_DROID}[kind]
+        p = lambda v: None if v is None else C.c_void_p(v.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_tf_loss_fwd_bwd(self._h, p(x), p(t), p(t_code), p(n0), p(n1), p(mask), p(cond), code, float(sigma),
+                                                    p(loss), p(flat), B, N, self._stream()), "pfm_tf_loss_fwd_bwd")
+        self._ticket = getattr(self, "_ticket", 0) + 1
+        return loss, flat
+
     def last_launches(self) -> int:
         return int(self.lib.pfm_tf_last_launches(self._h))
+
+
+class _DroidFn(torch.autograd.Function):
+    """Differentiable forward of a droid net: gradients w.r.t. its parameters (not w.r.t. the input)."""
+
+    @staticmethod
+    def forward(ctx, eng, t_code, x, mask, cond, *params):
+        out, ticket = eng.forward_train(t_code, x, mask, cond)
+        ctx.eng, ctx.ticket = eng, ticket
+        ctx.shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        flat = ctx.eng.backward(ctx.ticket, gout)
+        grads = [g.view(shp) if need else None
+                 for g, shp, need in zip(ctx.eng.grad_views(flat), ctx.shapes, ctx.needs_input_grad[5:])]
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class _DroidLossFn(torch.autograd.Function):
+    """loss = sum((net(t, y) - u)^2) / sum(mask) with the interpolation, forward and backward in one fused call."""
+
+    @staticmethod
+    def forward(ctx, net, eng, kind, sigma, x, mask, cond, t, t_code, n0, n1, *params):
+        want = any(ctx.needs_input_grad[11:])
+        loss, flat = eng.loss_fwd_bwd(kind, x, mask, cond, t, t_code, n0, n1, sigma, want_grad=want)
+        hook = getattr(net, "flat_grad_hook", None)
+        if want and hook is not None:
+            flat = hook(flat, eng)                # e.g. the data-parallel all-reduce of the flat gradient
+        ctx.eng, ctx.flat = eng, flat
+        ctx.shapes = [p.shape for p in params]
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        head = (None,) * 11
+        if ctx.flat is None:
+            return head + (None,) * len(ctx.shapes)
+        grads = [(gv.view(shp) * g) if need else None
+                 for gv, shp, need in zip(ctx.eng.grad_views(ctx.flat), ctx.shapes, ctx.needs_input_grad[11:])]
+        return head + tuple(grads)
+
+
+def droid_loss_autograd(cnf, kind: str, x: Tensor, mask: Tensor, cond: Optional[Tensor], t: Tensor, n0: Tensor,
+                        n1: Optional[Tensor], sigma: float) -> Tensor:
+    """Scalar flow-matching loss with an autograd graph to the droid net's parameters (t: (B,) per jet)."""
+    net = cnf.net
+    if x.device.type != "cuda":
+        raise RuntimeError(f"the flow-matching loss got a batch on {x.device}: the B200 path needs a CUDA device "
+                           "(no CPU fallback; use oracle/ for CPU reference numbers)")
+    eng = net.engine(x.device)
+    with torch.no_grad():
+        code = cnf.time_code(t.to(x.device))
+    return _DroidLossFn.apply(net, eng, kind, sigma, x, mask, cond, t, code, n0, n1, *list(net.parameters()))
 
 
 class _DroidNet(nn.Module):
@@ -296,13 +407,16 @@ class _DroidNet(nn.Module):
         """t (B,N,T) time code; x (B,N,inpt_dim) (time code first if add_time_to_input); ctxt (B,Cg) or None; mask (B,N,1)."""
         if mask is None:
             raise ValueError("the droid transformers need a mask (the reference calls mask.squeeze(-1).bool())")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("training the droid transformers is not built yet on the B200 path: call under "
-                                      "torch.no_grad() (sampling / validation); EPiC nets train through the fused step")
         t_code = t[:, 0, :]
         if t.stride(0) == 0 or t.shape[0] == 1:
             t_code = t_code[:1]
         xin = x[..., x.shape[-1] - self.outp_dim:]                   # drop the concatenated time columns: they are hoisted
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise NotImplementedError("gradients w.r.t. the input of the droid transformers are not provided by the B200 "
+                                          "path (parameter gradients are)")
+            # training semantics of the reference: every slot is evaluated (padded slots are not masked on output)
+            return _DroidFn.apply(self.engine(x.device), t_code, xin, mask, ctxt, *list(self.parameters()))
         return self.engine(x.device).forward(t_code, xin, mask, ctxt)
 
 

@@ -52,6 +52,9 @@ class _FusedFMLoss(nn.Module):
                                 "losses.py:119,130)")
             mask = torch.ones_like(x[..., 0]).unsqueeze(-1)
         t, n0, n1 = self.draw(x)
+        from .droid_transformer import _DroidNet, droid_loss_autograd
+        if isinstance(self.flows[0].net, _DroidNet):
+            return droid_loss_autograd(self.flows[0], self.kind, x, mask, cond, t, n0, n1, float(self.sigma))
         from ...training import fm_loss_autograd
         return fm_loss_autograd(self.flows[0], self.kind, x, mask, cond, t, n0, n1, float(self.sigma))
 

@@ -38,7 +38,7 @@ class G:
     def __init__(self, name):
         z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
         self.meta = json.loads(str(z["meta"]))
-        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+        self.a = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta" and z[k].dtype.kind in "fiu"}
         self.cfg = do.DroidCfg(**self.meta["cfg"])
         self.sd = do.synth_state_dict(self.cfg, self.meta["wseed"])
         self.kind, self.N = self.meta["kind"], self.meta["N"]
