@@ -20,6 +20,8 @@
 // Gradients are produced w.r.t. the FOLDED weights W = g*v/||v|| in the flat layout
 // [W_0 | b_0 | W_1 | b_1 | ...]; the host maps them onto weight_g / weight_v (torch._weight_norm backward), see
 // SURVEY A.6.
+#include <cstdlib>
+
 #include "pfm_internal.cuh"
 #include "simt_common.cuh"
 
@@ -472,6 +474,12 @@ __global__ void __launch_bounds__(256) xty_kernel(const XtyJob* __restrict__ job
 // one job passed by value (the droid training path launches one product per linear)
 __global__ void __launch_bounds__(256) xty_one_kernel(const XtyJob J) { xty_tile(J, J.rows, blockIdx.y); }
 
+// PFM_XTY_SIMT=1 selects the fp32 CUDA-core weight-gradient kernels (debugging / A-B measurements)
+bool xty_use_simt() {
+  static const bool v = [] { const char* e = getenv("PFM_XTY_SIMT"); return e && e[0] == '1'; }();
+  return v;
+}
+
 int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
                    cudaStream_t st) {
   if (rows <= 0 || out <= 0 || K <= 0) return PFM_OK;
@@ -701,8 +709,14 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   for (int c = 0; c < n_chunks; ++c) {
     const int nj = chunk_job0[c + 1] - chunk_job0[c];
     if (nj > 0 && chunk_tiles[c] > 0) {
-      dim3 grid2((unsigned)((maxrows + X_CHUNK - 1) / X_CHUNK), (unsigned)chunk_tiles[c]);
-      xty_kernel<<<grid2, 256, 0, st>>>(reinterpret_cast<const XtyJob*>(h->jobs_dev) + chunk_job0[c], nj, h->plan.n_total);
+      const XtyJob* jd = reinterpret_cast<const XtyJob*>(h->jobs_dev) + chunk_job0[c];
+      if (!xty_use_simt()) {                         // tensor cores, 3-term bf16 split (fp32-accurate): xty_tc.cu
+        int rc = xty_tc_launch(jd, nj, chunk_tiles[c], h->plan.n_total, (int)maxrows, h->sm_count, st);
+        if (rc != PFM_OK) return rc;
+      } else {
+        dim3 grid2((unsigned)((maxrows + X_CHUNK - 1) / X_CHUNK), (unsigned)chunk_tiles[c]);
+        xty_kernel<<<grid2, 256, 0, st>>>(jd, nj, h->plan.n_total);
+      }
       h->last_launches += 1;
     }
     PFM_CUDA_CHECK(cudaEventRecord(h->grad_ev[c], st));

@@ -155,6 +155,10 @@ struct XtyJob {
   int tile0;           // first tile index of this job in grid.y
   int tiles_o, tiles_k;
 };
+bool xty_use_simt();
+int xty_tc_launch(const XtyJob* jobs_dev, int n_jobs, int tiles, const int* n_total, int max_rows, int sm_count, cudaStream_t st);
+int xty_tc_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
+                      int sm_count, cudaStream_t st);
 int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
                    cudaStream_t st);
 int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);

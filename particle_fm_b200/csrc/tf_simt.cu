@@ -434,7 +434,7 @@ static bool tf_make_linear(pfm_tf* h, TfLinear* L, int out, int in) {
   L->in = in; L->out = out; L->ldo = round_up_i(out, 64);
   L->Wt = tf_alloc(h, (size_t)(in + 4) * L->ldo);
   L->b = tf_alloc(h, L->ldo);
-  L->ldw = round_up_i(in, 64);
+  L->ldw = round_up_i(in, 256);          // a multiple of the widest column tile of tf_linear_kernel (backward: dX = dY . Wrow)
   L->Wrow = tf_alloc(h, (size_t)(out + 4) * L->ldw + 64);
   if (!L->Wrow) return false;
   if (out % 128 == 0 && in >= 64) {      // eligible for the tensor-core path: bf16 image of 16 KB [128 n x 64 k] blocks

@@ -670,7 +670,7 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
     a.X = dY; a.ldx = ldy; a.K = N;
     a.Wt = L.Wrow + o.k0; a.ldo = L.ldw; a.N = o.K;
     a.Y = tp.dxn; a.ldy = o.K; a.rows = rows; a.slope = 0.f; a.eps = 0.f;
-    if ((rc = tf_launch_linear(h, a, 64, false, st)) != PFM_OK) return rc;
+    if ((rc = tf_launch_linear(h, a, L.ldw, false, st)) != PFM_OK) return rc;
     const int blocks = (rows + 7) / 8 < 8 * h->sm_count ? (rows + 7) / 8 : 8 * h->sm_count;
     tt_ln_bwd_kernel<<<blocks, 256, 0, st>>>(tp.dxn, o.K, Xsrc, ldxs, o.K, o.ln->g, o.ln->b, h->cfg.ln_eps, rows, dX, ldxs, tp.xn, o.K,
                                              flat + o.ln->gg_off, flat + o.ln->gb_off);
@@ -683,7 +683,7 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
       a.X = dY; a.ldx = ldy; a.K = N;
       a.Wt = L.Wrow + o.k0; a.ldo = L.ldw; a.N = o.K;
       a.R = dX; a.ldr = tp.T[o.X].w; a.Y = dX; a.ldy = tp.T[o.X].w; a.rows = rows;
-      if ((rc = tf_launch_linear(h, a, 64, false, st)) != PFM_OK) return rc;
+      if ((rc = tf_launch_linear(h, a, L.ldw, false, st)) != PFM_OK) return rc;
     } else {
       const int total = rows * o.K;
       tt_dx_small_kernel<<<(total + 127) / 128, 128, 0, st>>>(dY, ldy, N, L.Wrow, L.ldw, o.k0, o.K, rows, dX, tp.T[o.X].w);
@@ -694,7 +694,9 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
   for (int p = 0; p < (L.n_parts > 1 ? 2 : 1); ++p) {
     const int o0 = p == 0 ? 0 : L.split;
     const int o1 = (L.n_parts > 1 && p == 0) ? L.split : N;
-    if ((rc = xty_launch_one(dY + o0, ldy, Xsrc, ldxs, flat + L.gw_off[p], L.in, o1 - o0, o.K, o.k0, rows, st)) != PFM_OK) return rc;
+    rc = xty_use_simt() ? xty_launch_one(dY + o0, ldy, Xsrc, ldxs, flat + L.gw_off[p], L.in, o1 - o0, o.K, o.k0, rows, st)
+                        : xty_tc_launch_one(dY + o0, ldy, Xsrc, ldxs, flat + L.gw_off[p], L.in, o1 - o0, o.K, o.k0, rows, h->sm_count, st);
+    if (rc != PFM_OK) return rc;
     h->last_launches++;
   }
   return PFM_OK;

@@ -287,6 +287,10 @@ class _TfEngine:
         self._ticket = getattr(self, "_ticket", 0) + 1
         return loss, flat
 
+    def grad_chunks(self):
+        """The droid backward finishes the flat gradient as a whole: the data-parallel hook all-reduces it in one piece."""
+        return []
+
     def last_launches(self) -> int:
         return int(self.lib.pfm_tf_last_launches(self._h))
 
