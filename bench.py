@@ -171,7 +171,7 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
     ms = float(ms.item())
     return {"value": world * B * steps / (ms / 1e3), "unit": "jets/s", "batch_per_gpu": B, "steps": steps,
             "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss),
-            "step": "fused loss fwd+bwd (fp32 CUDA cores) + flat-grad all-reduce + clip 0.5 + AdamW",
+            "step": "fused loss fwd+bwd (fp32 CUDA cores; weight gradients on tcgen05, 3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + clip 0.5 + AdamW",
             "mean_real_particles": float(n_real.float().mean())}
 
 

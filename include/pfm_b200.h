@@ -92,6 +92,15 @@ int pfm_epic_linear_shape(const pfm_epic* h, int i, int32_t* out_features, int32
  * parameters change (optimizer step, EMA swap). */
 int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* const* biases, int n,
                          void* stream);
+/* The same with the weight-norm fold done by the library: v[i] = weight_v [out,in], g[i] = weight_g [out] (NULL for a plain
+ * linear: v[i] is then the weight itself), b[i] = bias; one launch for all linears (replaces the forward pre-hook of
+ * torch's nn.utils.weight_norm, epic.py:66-81).  pfm_epic_param_grads maps the flat folded-weight gradient of the training
+ * calls onto d(weight_v), d(weight_g), d(bias) (what autograd does through torch._weight_norm in the reference), scaled by
+ * *scale (one device float, e.g. the upstream gradient of the loss; NULL = 1). */
+int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* g, const float* const* b, int n,
+                        void* stream);
+int pfm_epic_param_grads(pfm_epic* h, const float* grad_flat, const float* scale, const float* const* v,
+                         const float* const* g, float* const* dv, float* const* dg, float* const* db, int n, void* stream);
 
 int pfm_epic_set_precision(pfm_epic* h, int precision /* pfm_precision */);
 

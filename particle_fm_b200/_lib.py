@@ -42,6 +42,8 @@ _SIGNATURES = {
     "pfm_epic_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "pfm_epic_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pfm_epic_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "pfm_epic_param_grads": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]),
     "pfm_epic_grad_size": (C.c_longlong, [C.c_void_p]),
     "pfm_epic_grad_chunks": (C.c_int, [C.c_void_p]),
     "pfm_epic_grad_chunk_range": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -498,6 +498,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->precision = PFM_PREC_FP32;
   h->weights_set = false;
   h->lin_dev = nullptr; h->wt_store = nullptr; h->b_store = nullptr; h->tc_store = nullptr; h->tc_bytes = 0;
+  h->wn_rows = nullptr; h->wn_total_rows = 0; h->wn_goff = nullptr; h->wn_ptrs = nullptr;
   h->wr_store = nullptr; h->wr_floats = 0;
   h->act = nullptr; h->act_cap = 0; h->dact = nullptr; h->dact_cap = 0; h->yact = nullptr; h->yact_cap = 0;
   h->jact = nullptr; h->jact_cap = 0; h->dpre3 = nullptr; h->dpre3_cap = 0;
@@ -559,6 +560,9 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->lin_dev) cudaFree(h->lin_dev);
+  if (h->wn_rows) cudaFree(h->wn_rows);
+  if (h->wn_goff) cudaFree(h->wn_goff);
+  if (h->wn_ptrs) cudaFree(h->wn_ptrs);
   if (h->wt_store) cudaFree(h->wt_store);
   if (h->b_store) cudaFree(h->b_store);
   if (h->tc_store) cudaFree(h->tc_store);
@@ -623,6 +627,137 @@ int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* 
     int rc = tc_pack_weights(h, st);
     if (rc != PFM_OK) return rc;
   }
+  return PFM_OK;
+}
+
+// ---- weight-norm fold and its backward, one launch each for all linears ------------------------------------------
+// (the reference re-creates `weight = g * v / ||v||` in a forward pre-hook of every linear, epic.py:66-81 with torch's old
+// nn.utils.weight_norm, and autograd differentiates it; here: block = one output row of one linear)
+static int wn_tables(pfm_epic* h) {
+  if (h->wn_rows) return PFM_OK;
+  std::vector<int2> rows;
+  std::vector<long long> goff(2 * (size_t)h->n_lin);
+  long long off = 0;
+  for (int i = 0; i < h->n_lin; ++i) {
+    const Lin& L = h->lin_host[i];
+    for (int o = 0; o < L.out; ++o) rows.push_back(make_int2(i, o));
+    goff[2 * i] = off; off += (long long)L.out * L.in;
+    goff[2 * i + 1] = off; off += L.out;
+  }
+  h->wn_total_rows = (int)rows.size();
+  PFM_CUDA_CHECK(cudaMalloc(&h->wn_rows, sizeof(int2) * rows.size()));
+  PFM_CUDA_CHECK(cudaMalloc(&h->wn_goff, sizeof(long long) * goff.size()));
+  PFM_CUDA_CHECK(cudaMalloc(&h->wn_ptrs, sizeof(float*) * 8 * (size_t)h->n_lin));
+  PFM_CUDA_CHECK(cudaMemcpy(h->wn_rows, rows.data(), sizeof(int2) * rows.size(), cudaMemcpyHostToDevice));
+  PFM_CUDA_CHECK(cudaMemcpy(h->wn_goff, goff.data(), sizeof(long long) * goff.size(), cudaMemcpyHostToDevice));
+  return PFM_OK;
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// ptrs: [v_0..v_{n-1} | g_0.. | b_0..]   (g_i == NULL: plain linear, v_i is the weight itself)
+__global__ void __launch_bounds__(128) wn_fold_kernel(const Lin* __restrict__ lins, const int2* __restrict__ rows,
+                                                      const float* const* __restrict__ ptrs, int n) {
+  __shared__ float red[4];
+  const int2 lr = rows[blockIdx.x];
+  const Lin L = lins[lr.x];
+  const int o = lr.y;
+  const float* v = ptrs[lr.x] + (size_t)o * L.in;
+  const float* g = ptrs[n + lr.x];
+  float scale = 1.f;
+  if (g) {
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < L.in; k += 128) { const float x = v[k]; ss = fmaf(x, x, ss); }
+    ss = block_sum_128(ss, red);
+    scale = g[o] / sqrtf(ss);
+  }
+  float* Wt = const_cast<float*>(L.Wt);
+  float* Wr = const_cast<float*>(L.Wr);
+  for (int k = threadIdx.x; k < L.in; k += 128) {
+    const float w = v[k] * scale;
+    Wt[(size_t)k * L.ldo + o] = w;
+    const int km = k - L.m_off;
+    if (km >= 0 && km < L.m_len) Wr[(size_t)o * L.ldr + km] = w;
+  }
+  if (threadIdx.x == 0) const_cast<float*>(L.b)[o] = ptrs[2 * n + lr.x][o];
+}
+
+// ptrs: [v | g | dv | dg | db];  dW = grad_flat[goff[2i] + o*in + k],  db = grad_flat[goff[2i+1] + o];  all scaled by *scale
+__global__ void __launch_bounds__(128) wn_bwd_kernel(const Lin* __restrict__ lins, const int2* __restrict__ rows,
+                                                     const long long* __restrict__ goff, const float* __restrict__ grad_flat,
+                                                     const float* __restrict__ scale_ptr, const float* const* __restrict__ ptrs, int n) {
+  __shared__ float red[4];
+  const int2 lr = rows[blockIdx.x];
+  const int in = lins[lr.x].in, o = lr.y;
+  const float s = scale_ptr ? *scale_ptr : 1.f;
+  const float* v = ptrs[lr.x] + (size_t)o * in;
+  const float* g = ptrs[n + lr.x];
+  float* dv = const_cast<float*>(ptrs[2 * n + lr.x]) + (size_t)o * in;
+  float* dg = const_cast<float*>(ptrs[3 * n + lr.x]);
+  float* db = const_cast<float*>(ptrs[4 * n + lr.x]);
+  const float* dw = grad_flat + goff[2 * lr.x] + (size_t)o * in;
+  if (g) {
+    float ss = 0.f, dot = 0.f;
+    for (int k = threadIdx.x; k < in; k += 128) { const float x = v[k]; ss = fmaf(x, x, ss); dot = fmaf(dw[k], x, dot); }
+    ss = block_sum_128(ss, red);
+    dot = block_sum_128(dot, red);
+    const float nrm = sqrtf(ss), gv = g[o];
+    const float a = s * gv / nrm, b = dot / ss;
+    for (int k = threadIdx.x; k < in; k += 128) dv[k] = a * (dw[k] - v[k] * b);
+    if (threadIdx.x == 0) dg[o] = s * dot / nrm;
+  } else {
+    for (int k = threadIdx.x; k < in; k += 128) dv[k] = s * dw[k];
+  }
+  if (threadIdx.x == 0) db[o] = s * grad_flat[goff[2 * lr.x + 1] + o];
+}
+
+int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* g, const float* const* b, int n, void* stream) {
+  if (!h || !v || !g || !b) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (n != h->n_lin) { set_error("expected %d linears, got %d", h->n_lin, n); return PFM_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PFM_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = wn_tables(h);
+  if (rc != PFM_OK) return rc;
+  std::vector<const float*> tab(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (!v[i] || !b[i]) { set_error("null weight/bias pointer for linear %d", i); return PFM_ERR_INVALID; }
+    tab[i] = v[i]; tab[n + i] = g[i]; tab[2 * n + i] = b[i];
+  }
+  // pageable source: staged by the runtime before the call returns
+  PFM_CUDA_CHECK(cudaMemcpyAsync(h->wn_ptrs, tab.data(), sizeof(float*) * tab.size(), cudaMemcpyHostToDevice, st));
+  wn_fold_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_ptrs, n);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->weights_set = true;
+  if (h->precision == PFM_PREC_BF16) {
+    rc = tc_pack_weights(h, st);
+    if (rc != PFM_OK) return rc;
+  }
+  return PFM_OK;
+}
+
+int pfm_epic_param_grads(pfm_epic* h, const float* grad_flat, const float* scale, const float* const* v, const float* const* g,
+                         float* const* dv, float* const* dg, float* const* db, int n, void* stream) {
+  if (!h || !grad_flat || !v || !g || !dv || !dg || !db) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (n != h->n_lin) { set_error("expected %d linears, got %d", h->n_lin, n); return PFM_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PFM_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = wn_tables(h);
+  if (rc != PFM_OK) return rc;
+  std::vector<const float*> tab(5 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (!v[i] || !dv[i] || !db[i] || (g[i] && !dg[i])) { set_error("null pointer for linear %d", i); return PFM_ERR_INVALID; }
+    tab[i] = v[i]; tab[n + i] = g[i]; tab[2 * n + i] = dv[i]; tab[3 * n + i] = dg[i]; tab[4 * n + i] = db[i];
+  }
+  PFM_CUDA_CHECK(cudaMemcpyAsync(h->wn_ptrs + 3 * (size_t)n, tab.data(), sizeof(float*) * tab.size(), cudaMemcpyHostToDevice, st));
+  wn_bwd_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_goff, grad_flat, scale, h->wn_ptrs + 3 * (size_t)n, n);
+  PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
 

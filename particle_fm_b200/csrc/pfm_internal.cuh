@@ -85,6 +85,11 @@ struct pfm_epic {
   float* ones;                      // [1] = 1.0f (the "input" of a bias in the weight-gradient jobs)
   void* jobs_dev; size_t jobs_cap;  // device copy of the weight-gradient job table
   int train_B, train_N, train_Kx, train_xin_off;   // shape of the saved forward (0 = none)
+  // weight-norm fold / backward inside the library (pfm_epic_set_params / pfm_epic_param_grads)
+  int2* wn_rows;                    // [wn_total_rows] (linear, output row) of every block of the fold kernels
+  int wn_total_rows;
+  long long* wn_goff;               // [2 n_lin] offsets of W_i and b_i in the flat gradient
+  const float** wn_ptrs;            // [8 n_lin] device copy of the caller's pointer tables
   bool timing;
   std::vector<cudaEvent_t> ev_pool;   // start/stop pairs of the main kernel, one pair per chunk of a call
   int ev_used;

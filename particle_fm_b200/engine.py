@@ -112,6 +112,55 @@ class EpicEngine:
         self._keepalive = (ws, bs)      # until the stream has consumed them
         self.weights_key = key
 
+    def set_params(self, linears, key=None):
+        """Raw parameters of the linears (weight_v / weight_g / bias, or weight / bias for a plain linear): the library folds
+        the weight norm and repacks in one launch (pfm_epic_set_params)."""
+        if len(linears) != self.n_lin:
+            raise ValueError(f"expected {self.n_lin} linears, got {len(linears)}")
+        vs, gs, bs = [], [], []
+        for k, ((o, i), lin) in enumerate(zip(self.linear_shapes_cached(), linears)):
+            v = _f32c(lin.weight_v if lin.weight_norm else lin.weight, self.device)
+            g = _f32c(lin.weight_g, self.device) if lin.weight_norm else None
+            b = _f32c(lin.bias, self.device)
+            if tuple(v.shape) != (o, i) or tuple(b.shape) != (o,) or (g is not None and g.numel() != o):
+                raise ValueError(f"linear {k}: expected weight {(o, i)} / bias {(o,)}, got {tuple(v.shape)} / {tuple(b.shape)}")
+            vs.append(v); gs.append(g); bs.append(b)
+        n = self.n_lin
+        arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_set_params(self._h, arr(vs), arr(gs), arr(bs), n, self._stream()), "pfm_epic_set_params")
+        self._keepalive = (vs, gs, bs)
+        self.weights_key = key
+
+    def linear_shapes_cached(self):
+        if getattr(self, "_shapes", None) is None:
+            self._shapes = self.linear_shapes()
+        return self._shapes
+
+    def param_grads(self, flat: Tensor, scale: Optional[Tensor], linears):
+        """Flat folded-weight gradient -> gradients of the raw parameters, one launch (pfm_epic_param_grads).
+        Returns [(d weight_v | d weight, d weight_g | None, d bias)] in the order of ``linears``."""
+        n = self.n_lin
+        vs = [_f32c(lin.weight_v if lin.weight_norm else lin.weight, self.device) for lin in linears]
+        gs = [_f32c(lin.weight_g, self.device) if lin.weight_norm else None for lin in linears]
+        total = sum(v.numel() + (0 if g is None else g.numel()) + v.shape[0] for v, g in zip(vs, gs))
+        buf = torch.empty(total, device=self.device, dtype=torch.float32)     # one allocation, per-parameter views
+        out, off = [], 0
+        for v, g in zip(vs, gs):
+            dv = buf[off:off + v.numel()].view(v.shape); off += v.numel()
+            dg = None
+            if g is not None:
+                dg = buf[off:off + g.numel()].view(g.shape); off += g.numel()
+            db = buf[off:off + v.shape[0]]; off += v.shape[0]
+            out.append((dv, dg, db))
+        arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        scale = None if scale is None else _f32c(scale, self.device).reshape(1)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_param_grads(self._h, _ptr(flat), _ptr(scale), arr(vs), arr(gs), arr([d[0] for d in out]),
+                                                     arr([d[1] for d in out]), arr([d[2] for d in out]), n, self._stream()),
+                       "pfm_epic_param_grads")
+        return out
+
     # -- hot path ------------------------------------------------------------------------------
     def forward(self, t_code: Optional[Tensor], x: Tensor, mask: Optional[Tensor], cond: Optional[Tensor]) -> Tensor:
         """t_code [1|B, t_dim], x [B,N,input_dim], mask [B,N] (or [B,N,1]), cond [B,C] -> [B,N,feats]."""

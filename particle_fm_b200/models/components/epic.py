@@ -164,9 +164,7 @@ class EPiC_encoder(nn.Module):
         if sync_weights:
             key = self._weights_key()
             if eng.weights_key != key:
-                with torch.no_grad():
-                    folded = [lin.folded() for lin in self.linears()]
-                eng.set_weights([w for w, _ in folded], [b for _, b in folded], key=key)
+                eng.set_params(self.linears(), key=key)      # weight-norm fold + repack inside the library
         return eng
 
     def _apply(self, fn, *a, **k):      # .to()/.cuda(): parameters move, packed copies are rebuilt lazily

@@ -1,10 +1,11 @@
 """Autograd glue of the fused training kernels.
 
 The reference obtains gradients from torch autograd over the eager network; here the
-whole loss forward + backward is libpfm_b200 (``pfm_epic_loss_fwd_bwd``), and a ``torch.autograd.Function``
-hands the result to autograd as the gradient of the FOLDED weights ``W = g*v/||v||`` -- the fold itself
-(``torch._weight_norm``) stays a differentiable torch op, so ``weight_g`` / ``weight_v`` / ``bias``
-receive their gradients, and optimizers, gradient clipping, DDP hooks and the EMA callback keep working.
+whole loss forward + backward is libpfm_b200 (``pfm_epic_loss_fwd_bwd``), including the weight-norm fold
+``W = g*v/||v||`` (``pfm_epic_set_params``) and its chain rule (``pfm_epic_param_grads``): a
+``torch.autograd.Function`` hands autograd the gradients of the raw parameters ``weight_g`` / ``weight_v`` /
+``bias``, so optimizers, gradient clipping, DDP hooks and the EMA callback keep working.  (The generic
+differentiable forward ``_EpicFn`` keeps the fold as a torch op.)
 """
 from __future__ import annotations
 
@@ -29,28 +30,36 @@ def _folded_and_engine(net, device):
     return eng, flat
 
 
-class _FMLossFn(torch.autograd.Function):
-    """loss = sum((net(t, y) - u)^2) / sum(mask), forward and backward in one fused call."""
+def _raw_params(net):
+    """[weight_v | weight, weight_g (weight-normed only), bias] of every linear, in the library's order."""
+    out = []
+    for lin in net.linears():
+        out += [lin.weight_v, lin.weight_g, lin.bias] if lin.weight_norm else [lin.weight, lin.bias]
+    return out
+
+
+class _FMLossParamFn(torch.autograd.Function):
+    """loss = sum((net(t, y) - u)^2) / sum(mask): forward, backward AND the weight-norm chain rule inside libpfm_b200;
+    autograd sees the raw parameters (weight_v, weight_g, bias)."""
 
     @staticmethod
-    def forward(ctx, net, eng, kind, sigma, x, mask, cond, t, t_code, t_code_in, n0, n1, *wb):
+    def forward(ctx, net, eng, kind, sigma, x, mask, cond, t, t_code, t_code_in, n0, n1, *params):
         want = any(ctx.needs_input_grad[12:])
         loss, flat = eng.loss_fwd_bwd(kind, x, mask, cond, t, t_code, t_code_in, n0, n1, sigma, want_grad=want)
         hook = getattr(net, "flat_grad_hook", None)
         if want and hook is not None:
             flat = hook(flat, eng)                # e.g. the data-parallel all-reduce of the flat gradient
-        ctx.eng, ctx.flat = eng, flat
+        ctx.net, ctx.eng, ctx.flat = net, eng, flat
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         grads = [None] * 12
+        lins = ctx.net.linears()
         if ctx.flat is None:
-            return tuple(grads) + (None,) * (2 * ctx.eng.n_lin)
-        for (gw, gb), need_w, need_b in zip(ctx.eng.grad_views(ctx.flat), ctx.needs_input_grad[12::2],
-                                            ctx.needs_input_grad[13::2]):
-            grads.append(gw * g if need_w else None)
-            grads.append(gb * g if need_b else None)
+            return tuple(grads) + (None,) * sum(3 if l.weight_norm else 2 for l in lins)
+        for lin, (dv, dg, db) in zip(lins, ctx.eng.param_grads(ctx.flat, g, lins)):
+            grads += [dv, dg.view(lin.weight_g.shape), db] if lin.weight_norm else [dv, db]
         return tuple(grads)
 
 
@@ -61,12 +70,12 @@ def fm_loss_autograd(cnf, kind: str, x: Tensor, mask: Tensor, cond: Optional[Ten
     if x.device.type != "cuda":
         raise RuntimeError(f"the flow-matching loss got a batch on {x.device}: the B200 path needs a CUDA device "
                            "(no CPU fallback; use oracle/ for CPU reference numbers)")
-    eng, wb = _folded_and_engine(net, x.device)
+    eng = net.engine(x.device)                       # folds the weight norm and repacks when a parameter changed
     takes = net.t_local_cat or net.t_global_cat
     with torch.no_grad():
         code = cnf.time_code(t.to(x.device)) if (takes or cnf.add_time_to_input) else None     # [B, 2*frequencies]
-    return _FMLossFn.apply(net, eng, kind, sigma, x, mask, cond, t, code if takes else None,
-                           code if cnf.add_time_to_input else None, n0, n1, *wb)
+    return _FMLossParamFn.apply(net, eng, kind, sigma, x, mask, cond, t, code if takes else None,
+                                code if cnf.add_time_to_input else None, n0, n1, *_raw_params(net))
 
 
 class _EpicFn(torch.autograd.Function):
