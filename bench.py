@@ -170,7 +170,7 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     return {"value": world * B * steps / (ms / 1e3), "unit": "jets/s", "batch_per_gpu": B, "steps": steps,
-            "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss),
+            "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss.detach()),
             "step": "fused loss fwd+bwd (fp32 CUDA cores; weight gradients on tcgen05, 3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + clip 0.5 + AdamW",
             "mean_real_particles": float(n_real.float().mean())}
 
@@ -210,8 +210,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PFM_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=0, help="jets per GPU per step (default: 16384 bf16 / 4096 fp32)")
     ap.add_argument("--all-real", action="store_true", help="every particle real (roofline variant)")
-    ap.add_argument("--ref-jets", type=int, default=32, help="jets per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-jets", type=int, default=32)
+    ap.add_argument("--ref-jets", type=int, default=192, help="jets per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-jets", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
     args = ap.parse_args()
