@@ -44,6 +44,7 @@ struct TfLinear {
   // training: row-major copy Wrow[o*ldw + k] (dX = dY . W) and where the gradients go in the flat buffer;
   // a linear fed from two state_dict entries (k_linear | v_linear) has two parts split at output row `split`
   float* Wrow = nullptr; int ldw = 0;
+  uint8_t* img_bwd = nullptr; int kblocks_bwd = 0;   // bf16 image of Wrow viewed k-major (k = output row): dX on tcgen05
   int n_parts = 0, split = 0;
   size_t gw_off[2] = {0, 0}, gb_off[2] = {0, 0};
 };

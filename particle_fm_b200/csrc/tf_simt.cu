@@ -442,6 +442,11 @@ static bool tf_make_linear(pfm_tf* h, TfLinear* L, int out, int in) {
     L->img = reinterpret_cast<uint8_t*>(tf_alloc(h, (size_t)(out / 128) * L->kblocks * 16384 / sizeof(float)));
     if (!L->img) return false;
   }
+  if (out % 64 == 0 && in >= 128) {      // backward dX = dY . W on the tensor cores: K = out, N = input columns
+    L->kblocks_bwd = out / 64;
+    L->img_bwd = reinterpret_cast<uint8_t*>(tf_alloc(h, (size_t)(L->ldw / 128) * L->kblocks_bwd * 16384 / sizeof(float)));
+    if (!L->img_bwd) return false;
+  }
   h->all_linears.push_back(L);
   return L->Wt && L->b;
 }
@@ -793,8 +798,10 @@ int pfm_tf_set_weights(pfm_tf* h, const float* const* params, int n, void* strea
       PFM_CUDA_CHECK(cudaMemcpyAsync(s.target, params[i], sizeof(float) * (size_t)s.rows * s.cols, cudaMemcpyDeviceToDevice, st));
     }
   }
-  for (TfLinear* L : h->all_linears)
+  for (TfLinear* L : h->all_linears) {
     if (L->img) { int rc = tf_tc_pack(L->Wt, L->in, L->out, L->ldo, L->img, L->kblocks, st); if (rc != PFM_OK) return rc; }
+    if (L->img_bwd) { int rc = tf_tc_pack(L->Wrow, L->out, L->ldw, L->ldw, L->img_bwd, L->kblocks_bwd, st); if (rc != PFM_OK) return rc; }
+  }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
   return PFM_OK;

@@ -581,6 +581,7 @@ static void fill_lin(pfm_tf* h, TfTape& tp, const TOp& o, LinArgs& a) {
   a.Y = tdata(tp, o.Y); a.ldy = tp.T[o.Y].w;
   a.act = o.act; a.slope = h->cfg.neg_slope; a.eps = h->cfg.ln_eps;
   a.rows = o.rows;
+  a.img = o.L->img; a.img_kblocks = o.L->kblocks; a.kb0 = o.k0 / 64;
 }
 
 __global__ void tt_rowjet_kernel(int* __restrict__ rowjet, int rows, int per) {
@@ -619,7 +620,7 @@ static int tape_forward(pfm_tf* h, TfTape& tp, cudaStream_t st) {
     if (o.kind == 0) {
       LinArgs a;
       fill_lin(h, tp, o, a);
-      if ((rc = tf_launch_linear(h, a, o.L->ldo, false, st)) != PFM_OK) return rc;
+      if ((rc = tf_launch_linear(h, a, o.L->ldo, (o.k0 % 64) == 0, st)) != PFM_OK) return rc;      // bf16 mode: tcgen05 linears
     } else if (o.kind == 1) {
       if ((rc = run_attention(h, tp, o.ad, false, st)) != PFM_OK) return rc;
     } else {
@@ -629,6 +630,29 @@ static int tape_forward(pfm_tf* h, TfTape& tp, cudaStream_t st) {
     }
   }
   PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+// dXout[rows, K] = [R +] dY[rows, N] . Wrow[:, k0 : k0+K]   (fp32 row-block GEMM, or tcgen05 bf16 in PFM_PREC_BF16 mode;
+// the tensor-core kernel holds a [128 x <=512] A tile, so wider dY (the fused QKV projection: 768) goes in slices)
+static int dx_linear(pfm_tf* h, const TfLinear& L, const float* dY, int ldy, int N, int k0, int K, const float* R, int ldr, float* out,
+                     int ldo, int rows, cudaStream_t st) {
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = dY; a.ldx = ldy; a.K = N;
+  a.Wt = L.Wrow + k0; a.ldo = L.ldw; a.N = K;
+  a.R = R; a.ldr = ldr; a.Y = out; a.ldy = ldo; a.rows = rows;
+  const bool tc = h->precision == PFM_PREC_BF16 && L.img_bwd && k0 == 0 && rows >= 256 && (K & 127) == 0 && (N & 63) == 0 &&
+                  (ldy & 3) == 0 && (ldo & 3) == 0 && (!R || (ldr & 3) == 0);
+  if (!tc) return tf_launch_linear(h, a, L.ldw, false, st);
+  for (int n0 = 0; n0 < N; n0 += 512) {
+    LinArgs b = a;
+    b.X = dY + n0; b.K = N - n0 < 512 ? N - n0 : 512;
+    b.img = L.img_bwd; b.img_kblocks = L.kblocks_bwd; b.kb0 = n0 / 64;
+    if (n0 > 0) { b.R = out; b.ldr = ldo; }
+    int rc = tf_launch_linear(h, b, L.ldw, true, st);
+    if (rc != PFM_OK) return rc;
+  }
   return PFM_OK;
 }
 
@@ -665,12 +689,7 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
   int ldxs = tp.T[o.X].w;
   if (o.ln) {
     if (!dX) { set_error("internal: LayerNorm input without gradient"); return PFM_ERR_INVALID; }
-    LinArgs a;
-    memset(&a, 0, sizeof(a));
-    a.X = dY; a.ldx = ldy; a.K = N;
-    a.Wt = L.Wrow + o.k0; a.ldo = L.ldw; a.N = o.K;
-    a.Y = tp.dxn; a.ldy = o.K; a.rows = rows; a.slope = 0.f; a.eps = 0.f;
-    if ((rc = tf_launch_linear(h, a, L.ldw, false, st)) != PFM_OK) return rc;
+    if ((rc = dx_linear(h, L, dY, ldy, N, o.k0, o.K, nullptr, 0, tp.dxn, o.K, rows, st)) != PFM_OK) return rc;
     const int blocks = (rows + 7) / 8 < 8 * h->sm_count ? (rows + 7) / 8 : 8 * h->sm_count;
     tt_ln_bwd_kernel<<<blocks, 256, 0, st>>>(tp.dxn, o.K, Xsrc, ldxs, o.K, o.ln->g, o.ln->b, h->cfg.ln_eps, rows, dX, ldxs, tp.xn, o.K,
                                              flat + o.ln->gg_off, flat + o.ln->gb_off);
@@ -678,12 +697,7 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
     Xsrc = tp.xn; ldxs = o.K;
   } else if (dX) {
     if ((o.k0 & 3) == 0 && rows >= 64) {
-      LinArgs a;
-      memset(&a, 0, sizeof(a));
-      a.X = dY; a.ldx = ldy; a.K = N;
-      a.Wt = L.Wrow + o.k0; a.ldo = L.ldw; a.N = o.K;
-      a.R = dX; a.ldr = tp.T[o.X].w; a.Y = dX; a.ldy = tp.T[o.X].w; a.rows = rows;
-      if ((rc = tf_launch_linear(h, a, L.ldw, false, st)) != PFM_OK) return rc;
+      if ((rc = dx_linear(h, L, dY, ldy, N, o.k0, o.K, dX, tp.T[o.X].w, dX, tp.T[o.X].w, rows, st)) != PFM_OK) return rc;
     } else {
       const int total = rows * o.K;
       tt_dx_small_kernel<<<(total + 127) / 128, 128, 0, st>>>(dY, ldy, N, L.Wrow, L.ldw, o.k0, o.K, rows, dX, tp.T[o.X].w);

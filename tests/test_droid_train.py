@@ -238,3 +238,33 @@ def test_cuda_training_step_many_jets_variable_multiplicity(kind, lib_built):
     with torch.no_grad():
         loss2 = droid_loss_autograd(cnf, "FM-OT", x.to(DEV), mask.to(DEV), cond.to(DEV), t.to(DEV), n0.to(DEV), None, 1e-4)
     assert float(loss2) < float(loss)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["full", "cross"])
+def test_cuda_bf16_training_linears(kind, lib_built):
+    """set_precision("bf16"): the per-row linears of the training forward and of dX run on tcgen05 with bf16 operands
+    (fp32 accumulation; LayerNorm, attention, loss, weight gradients stay fp32-accurate).  Tolerance of the bf16 mode
+    (north star: 2e-2 per evaluation): loss 2e-2 relative, whole gradient vector 5e-2 relative L2."""
+    g = GT(f"droid_{kind}_n150_cond")
+    B, N = 40, 150
+    gen = torch.Generator().manual_seed(78)
+    x = torch.randn(B, N, 3, generator=gen)
+    n = torch.randint(1, N + 1, (B,), generator=gen)
+    mask = (torch.arange(N).unsqueeze(0) < n.unsqueeze(1)).float().unsqueeze(-1)
+    x = x * mask
+    cond = torch.randn(B, g.cfg.cond_dim, generator=gen)
+    t = torch.rand(B, generator=gen)
+    n0 = torch.randn(B, N, 3, generator=gen)
+    ref_loss, ref_g = g.oracle_loss_and_grads("droid", x, mask, cond, draws=(t, n0, None))
+    m = build(g, DEV)
+    m.set_precision("bf16")
+    cnf = m.flows[0]
+    from particle_fm_b200.models.components.droid_transformer import droid_loss_autograd
+    loss = droid_loss_autograd(cnf, "droid", x.to(DEV), mask.to(DEV), cond.to(DEV), t.to(DEV), n0.to(DEV), None, 1e-4)
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)), (float(loss.detach()), float(ref_loss))
+    loss.backward()
+    got = torch.cat([p.grad.detach().cpu().flatten().double() for _, p in cnf.net.named_parameters()])
+    ref = torch.cat([ref_g[k].flatten().double() for k, _ in cnf.net.named_parameters()])
+    err = float((got - ref).norm() / ref.norm())
+    assert 1e-5 < err < 5e-2, err          # > 1e-5: the bf16 path really ran
