@@ -284,11 +284,18 @@ __global__ void __launch_bounds__(256) tt_ln_bwd_kernel(const float* __restrict_
       }
     }
   }
-  if (dg) {
+  if (dg) {                                        // block-level sum of the warps' partial gain / shift gradients, then one
+    __shared__ float red[8][512];                  // atomic per column and block
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = lane + 32 * i;
-      if (c < K) { atomicAdd(dg + c, ag[i]); atomicAdd(dbeta + c, ab[i]); }
+      for (int i = 0; i < 16; ++i) red[warp][lane + 32 * i] = pass == 0 ? ag[i] : ab[i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < wpb; ++w) t += red[w][c];
+        atomicAdd((pass == 0 ? dg : dbeta) + c, t);
+      }
     }
   }
 }
@@ -690,7 +697,7 @@ static int linear_backward(pfm_tf* h, TfTape& tp, const TOp& o, float* flat, cud
   if (o.ln) {
     if (!dX) { set_error("internal: LayerNorm input without gradient"); return PFM_ERR_INVALID; }
     if ((rc = dx_linear(h, L, dY, ldy, N, o.k0, o.K, nullptr, 0, tp.dxn, o.K, rows, st)) != PFM_OK) return rc;
-    const int blocks = (rows + 7) / 8 < 8 * h->sm_count ? (rows + 7) / 8 : 8 * h->sm_count;
+    const int blocks = (rows + 7) / 8 < 2 * h->sm_count ? (rows + 7) / 8 : 2 * h->sm_count;
     tt_ln_bwd_kernel<<<blocks, 256, 0, st>>>(tp.dxn, o.K, Xsrc, ldxs, o.K, o.ln->g, o.ln->b, h->cfg.ln_eps, rows, dX, ldxs, tp.xn, o.K,
                                              flat + o.ln->gg_off, flat + o.ln->gb_off);
     h->last_launches++;
