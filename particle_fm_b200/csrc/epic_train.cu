@@ -183,11 +183,17 @@ __device__ __forceinline__ void global_backward(const BwdParams& p, const Lin& G
   __syncthreads();
   // pooled gradient back onto the particles:  S -> (mean = S/n, sum = S*s)
   const int o_mean = unit == 0 ? H : 0, o_sum = unit == 0 ? 0 : H;
-  for (int i = tid; i < R * H; i += kThreads) {
-    const int row = i / H, c = i - row * H;
-    const int j = rjet[row];
+  // (combined once per jet, in place over the mean section, then one add per particle element: warp = row, lane = column)
+  for (int i = tid; i < nj * H; i += kThreads) {
+    const int j = i / H, c = i - j * H;
     const float n = (float)(jrow0[j + 1] - jrow0[j]);
-    dh[(size_t)row * p.LDH + c] += din[j * p.LDP + o_mean + c] / n + p.sum_scale * din[j * p.LDP + o_sum + c];
+    din[j * p.LDP + o_mean + c] = din[j * p.LDP + o_mean + c] / n + p.sum_scale * din[j * p.LDP + o_sum + c];
+  }
+  __syncthreads();
+  for (int row = tid >> 5; row < R; row += kWarps) {
+    const float* comb = din + (int)rjet[row] * p.LDP + o_mean;
+    float* d = dh + (size_t)row * p.LDH;
+    for (int c = tid & 31; c < H; c += 32) d[c] += comb[c];
   }
   // gradient w.r.t. the incoming global vector: through fc_global1's global columns and the residual
   if (unit > 0) {
