@@ -307,6 +307,9 @@ def main():
     train = None
     if not args.no_train:
         train = train_bench(model, dev, world, rank)
+        if world > 1:          # also the strong-scaling figure, global batch 1024 split over the ranks
+            strong = train_bench(model, dev, world, rank, B=max(1, 1024 // world))
+            train["strong_scaling"] = {k: strong[k] for k in ("value", "unit", "batch_per_gpu", "ms_per_step")}
 
     if rank == 0:
         peaks = measured_peaks()

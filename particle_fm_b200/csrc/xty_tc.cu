@@ -7,7 +7,7 @@
 // does.  fp32 accuracy is kept by the 3-term split  x = hi + lo (two bf16):  X^T Y ~ Xh^T Yh + Xh^T Yl + Xl^T Yh  (the
 // dropped Xl^T Yl term is 2^-16 relative), three tcgen05.mma M=128 N=128 K=16 per 16 rows, fp32 accumulation in TMEM.
 // D[m = c][n = o]: TMEM lane = input column c, so the atomics of a warp hit 32 consecutive floats of one dW row.
-// One CTA = one 128 x 128 tile of dW over a chunk of rows; double-buffered stages, the MMAs of stage s overlap the
+// One CTA = one 128 x 128 tile of dW over a chunk of rows (two CTAs per SM); double-buffered 32-row stages, the MMAs of stage s overlap the
 // global loads + conversion of stage s+1.  Bound: HBM/L2 (each operand element is read once per 128-wide tile).
 #include "pfm_internal.cuh"
 #include "tc_ptx.cuh"
@@ -16,7 +16,7 @@ namespace pfm {
 
 using namespace tc;
 
-static constexpr int XS_ROWS = 64;                  // rows per stage
+static constexpr int XS_ROWS = 32;                  // rows per stage (64 KB of stage buffers: two CTAs per SM)
 static constexpr int XS_TILE = XS_ROWS * 128 * 2;   // bytes of one bf16 [64 x 128] operand tile
 
 struct XtyTcSmem {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void xty_store4(uint8_t* hi, uint8_t* lo, int r, int 
   *reinterpret_cast<uint2*>(lo + off) = l;
 }
 
-__global__ void __launch_bounds__(256, 1) xty_tc_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total,
+__global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total,
                                                         const XtyJob single, int use_single) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   XtyTcSmem& s = *reinterpret_cast<XtyTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -89,11 +89,12 @@ __global__ void __launch_bounds__(256, 1) xty_tc_kernel(const XtyJob* __restrict
   const uint32_t tm = s.tmem;
   const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
   const int n_st = (r_end - r_begin + XS_ROWS - 1) / XS_ROWS;
-  float4 xv[8], yv[8];
-  auto fetch = [&](int st) {                       // 16 independent 16-byte loads in flight per thread
+  constexpr int NLD = XS_ROWS * 32 / 256;          // 16-byte loads per thread and operand
+  float4 xv[NLD], yv[NLD];
+  auto fetch = [&](int st) {                       // 2 NLD independent 16-byte loads in flight per thread
     const int r0 = r_begin + st * XS_ROWS;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NLD; ++i) {
       const int idx = tid + 256 * i, r = idx >> 5, c = (idx & 31) * 4;
       xv[i] = xty_load4(Xb, J.ldx, r0 + r, r_end, c, wx < 128 ? wx : 128, vx);
       yv[i] = xty_load4(Yb, J.ldy, r0 + r, r_end, c, wy < 128 ? wy : 128, vy);
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256, 1) xty_tc_kernel(const XtyJob* __restrict
     const int b = st & 1;
     if (st >= 2) mbar_wait(&s.mbar[b], (uint32_t)(((st >> 1) - 1) & 1));     // the MMAs that read this buffer are done
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NLD; ++i) {
       const int idx = tid + 256 * i, r = idx >> 5, c = (idx & 31) * 4;
       xty_store4(s.buf[b][0], s.buf[b][1], r, c, xv[i]);
       xty_store4(s.buf[b][2], s.buf[b][3], r, c, yv[i]);
