@@ -22,7 +22,7 @@ struct TtSmemTail {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(TT_THREADS, 1) tf_linear_tc_kernel(const LinArgs a, int n_slots) {
+__global__ void __launch_bounds__(TT_THREADS, 2) tf_linear_tc_kernel(const LinArgs a, int n_slots) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int KB = a.K >> 6;                                   // k blocks of the A tile
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tf_linear_tc_kernel(const LinAr
     const bool live = row < a.rows;
     const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
     const float* jbrow = (a.jb && live) ? a.jb + (size_t)(a.rowjet ? a.rowjet[row] : row) * a.jb_stride : nullptr;
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&t) + 256) + warp * (32 * 17);   // [32 rows][16 + 1]
     for (int nt = 0; nt < n_tiles; ++nt) {
       const int buf = nt & 1;
       mbar_wait(&t.acc_full[buf], (nt >> 1) & 1);
@@ -188,32 +189,53 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tf_linear_tc_kernel(const LinAr
         uint32_t v[32];
         tmem_ld32(lane_base + buf * 128 + c * 32, v);
         tmem_wait_ld();
-        const int n0 = nt * 128 + c * 32;
-        if (live) {
-          float* yrow = a.Y + (size_t)row * a.ldy + n0;
-          const float* rrow = a.R ? a.R + (size_t)row * a.ldr + n0 : nullptr;
+        // 16 columns at a time through a warp-private shared-memory tile: the residual is READ and the result WRITTEN as
+        // 64-byte row segments (two rows per instruction) instead of one 16-byte piece per lane and row, and the per-thread
+        // bias loads of a half are all in flight together
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float o[4];
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + q * 4));
-            if (jbrow) {
-              const float4 jv = __ldg(reinterpret_cast<const float4*>(jbrow + n0 + q * 4));
-              bv.x += jv.x; bv.y += jv.y; bv.z += jv.z; bv.w += jv.w;
+        for (int half = 0; half < 2; ++half) {
+          const int n0 = nt * 128 + c * 32 + half * 16;
+          float4 bq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bq[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (jbrow) {
+            float4 jv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jv[q] = __ldg(reinterpret_cast<const float4*>(jbrow + n0 + q * 4));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { bq[q].x += jv[q].x; bq[q].y += jv[q].y; bq[q].z += jv[q].z; bq[q].w += jv[q].w; }
+          }
+          if (a.R) {
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              const int rr = it * 2 + (lane >> 4), cc = lane & 15;
+              const int grow = row0 + warp * 32 + rr;
+              stg[rr * 17 + cc] = grow < a.rows ? a.R[(size_t)grow * a.ldr + n0 + cc] : 0.f;
             }
-            const float badd[4] = {bv.x, bv.y, bv.z, bv.w};
+            __syncwarp();
+          }
+          float o[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float badd[4] = {bq[q].x, bq[q].y, bq[q].z, bq[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[q * 4 + e]) + badd[e];
+              float x = __uint_as_float(v[half * 16 + q * 4 + e]) + badd[e];
               if (a.act) x = x > 0.f ? x : x * a.slope;
-              o[e] = x;
+              if (a.R) x += stg[lane * 17 + q * 4 + e];
+              o[q * 4 + e] = x;
             }
-            if (rrow) {
-              const float4 rv = *reinterpret_cast<const float4*>(rrow + q * 4);
-              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-            }
-            *reinterpret_cast<float4*>(yrow + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) stg[lane * 17 + e] = o[e];
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int rr = it * 2 + (lane >> 4), cc = lane & 15;
+            const int grow = row0 + warp * 32 + rr;
+            if (grow < a.rows) a.Y[(size_t)grow * a.ldy + n0 + cc] = stg[rr * 17 + cc];
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -247,8 +269,9 @@ bool tf_tc_linear_supported(const LinArgs& a) {
 int tf_tc_linear(const LinArgs& a, int max_smem, cudaStream_t st) {
   const int KB = a.K >> 6;
   int n_slots = KB <= 4 ? 2 : 4;            // K <= 256: 96 KB per CTA -> two CTAs per SM overlap load / MMA / epilogue
-  size_t smem = (size_t)(KB + n_slots) * TT_BLK + sizeof(TtSmemTail) + 1024;
-  if ((int)smem > max_smem) { n_slots = 2; smem = (size_t)(KB + n_slots) * TT_BLK + sizeof(TtSmemTail) + 1024; }
+  const size_t tail = 256 + 4 * 32 * 17 * sizeof(float) + 1024;      // barriers, epilogue staging tiles, alignment slack
+  size_t smem = (size_t)(KB + n_slots) * TT_BLK + tail;
+  if ((int)smem > max_smem) { n_slots = 2; smem = (size_t)(KB + n_slots) * TT_BLK + tail; }
   if ((int)smem > max_smem) { set_error("bf16 transformer linear: K=%d does not fit shared memory", a.K); return PFM_ERR_UNSUPPORTED; }
   static bool attr_set = false;
   if (!attr_set) {
