@@ -527,8 +527,22 @@ int run_linear(pfm_tf* h, cudaStream_t st, const float* X, int ldx, int K, const
   return tf_launch_linear(h, a, L.ldo, (k0 % 64) == 0, st);
 }
 
-static int tf_ensure(pfm_tf* h, int B, int N) {
+static int tf_ensure(pfm_tf* h, int B, int N, int ctx_rows = 0) {
   const pfm_tf_cfg& c = h->cfg;
+  {   // context rows: one per jet, or one per evaluation of an integration when the jets share the time code
+    const size_t need = (size_t)(B > ctx_rows ? B : ctx_rows);
+    if (need > h->cap_rows) {
+      for (float** p : {&h->ctxin, &h->c1, &h->ctx, &h->jb}) { if (*p) cudaFree(*p); *p = nullptr; }
+      const int n_tables = 2 + (int)h->layers.size();
+      const int hmax = c.embd_hddn > c.dense_hddn ? c.embd_hddn : c.dense_hddn;
+      h->jb_floats = (size_t)hmax;
+      PFM_CUDA_CHECK(cudaMalloc(&h->ctxin, sizeof(float) * need * (c.t_dim + c.cond_dim)));
+      PFM_CUDA_CHECK(cudaMalloc(&h->c1, sizeof(float) * need * c.embd_hddn));
+      PFM_CUDA_CHECK(cudaMalloc(&h->ctx, sizeof(float) * need * c.ctxt_out));
+      PFM_CUDA_CHECK(cudaMalloc(&h->jb, sizeof(float) * need * hmax * n_tables));
+      h->cap_rows = need;
+    }
+  }
   if (B > h->capB) {
     for (void* p : {(void*)h->n_real, (void*)h->rowoff, (void*)h->tokjet}) if (p) cudaFree(p);
     PFM_CUDA_CHECK(cudaMalloc(&h->n_real, sizeof(int) * B));
@@ -536,7 +550,7 @@ static int tf_ensure(pfm_tf* h, int B, int N) {
     PFM_CUDA_CHECK(cudaMalloc(&h->tokjet, sizeof(int) * B * c.num_tokens));
     if (!h->n_total) PFM_CUDA_CHECK(cudaMalloc(&h->n_total, sizeof(int)));
     h->capB = B;
-    for (float** p : {&h->tok, &h->tokA, &h->tokQ, &h->tokKV, &h->tokH1, &h->ctxin, &h->c1, &h->ctx, &h->jb}) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (float** p : {&h->tok, &h->tokA, &h->tokQ, &h->tokKV, &h->tokH1}) { if (*p) cudaFree(*p); *p = nullptr; }
     const size_t T4 = (size_t)B * c.num_tokens;
     const int D = c.model_dim;
     PFM_CUDA_CHECK(cudaMalloc(&h->tok, sizeof(float) * T4 * D));
@@ -544,13 +558,6 @@ static int tf_ensure(pfm_tf* h, int B, int N) {
     PFM_CUDA_CHECK(cudaMalloc(&h->tokQ, sizeof(float) * T4 * D));
     PFM_CUDA_CHECK(cudaMalloc(&h->tokKV, sizeof(float) * T4 * 2 * D));
     PFM_CUDA_CHECK(cudaMalloc(&h->tokH1, sizeof(float) * T4 * c.dense_hddn));
-    PFM_CUDA_CHECK(cudaMalloc(&h->ctxin, sizeof(float) * (size_t)B * (c.t_dim + c.cond_dim)));
-    PFM_CUDA_CHECK(cudaMalloc(&h->c1, sizeof(float) * (size_t)B * c.embd_hddn));
-    PFM_CUDA_CHECK(cudaMalloc(&h->ctx, sizeof(float) * (size_t)B * c.ctxt_out));
-    const int n_tables = 2 + (int)h->layers.size();
-    const int hmax = c.embd_hddn > c.dense_hddn ? c.embd_hddn : c.dense_hddn;
-    h->jb_floats = (size_t)hmax;
-    PFM_CUDA_CHECK(cudaMalloc(&h->jb, sizeof(float) * (size_t)B * hmax * n_tables));
   }
   if ((long long)B * N > h->capBN) {
     for (void* p : {(void*)h->ridx, (void*)h->rowjet}) if (p) cudaFree(p);
@@ -572,25 +579,21 @@ static int tf_ensure(pfm_tf* h, int B, int N) {
   return PFM_OK;
 }
 
-// One evaluation of the network on the packed state h->xs -> h->v.   t_code: one row (t_stride 0) or one per jet.
-static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, const float* cond, int B, int N, int rows) {
+// Context vector and hoisted bias tables for `Bc` context rows (jets, or -- when every jet shares the time and there is
+// no conditioning -- the evaluations of a whole integration at once): table i, row r at  h->jb + (i*cap + r)*hmax.
+static int tf_context(pfm_tf* h, cudaStream_t st, const float* t_code, int t_stride, const float* cond, int Bc, int cap) {
   const pfm_tf_cfg& c = h->cfg;
   const int D = c.model_dim, T = c.t_dim, C = c.cond_dim, F = c.feats, CO = c.ctxt_out;
-  const bool per_jet = (t_rows == B && B > 1) || C > 0;
-  const int Bc = per_jet ? B : 1;
-  const int t_stride = (t_rows == B && B > 1) ? T : 0;
   const int hmax = (int)h->jb_floats;
-  const int jbs = per_jet ? hmax : 0;                 // row stride of the per-jet bias tables
   const int t_in = c.add_time_to_input ? T : 0;
   int rc;
-  // ---- context vector and hoisted per-jet biases
   tf_ctxin_kernel<<<(Bc * (T + C) + 255) / 256, 256, 0, st>>>(t_code, t_stride, T, cond, C, Bc, h->ctxin);
   h->last_launches++;
   if ((rc = run_linear(h, st, h->ctxin, T + C, T + C, nullptr, h->ctxt.l1, 0, true, nullptr, 0, nullptr, nullptr, 0, h->c1,
                        c.embd_hddn, 1, Bc)) != PFM_OK) return rc;
   if ((rc = run_linear(h, st, h->c1, c.embd_hddn, c.embd_hddn, &h->ctxt.ln, h->ctxt.l2, 0, true, nullptr, 0, nullptr, nullptr, 0,
                        h->ctx, CO, 0, Bc)) != PFM_OK) return rc;
-  auto table = [&](int i) { return h->jb + (size_t)i * B * hmax; };
+  auto table = [&](int i) { return h->jb + (size_t)i * cap * hmax; };
   auto jet_bias = [&](const TfDense& d, int inpt, float* dst) -> int {     // b + W[:, inpt:inpt+CO] . ctx
     return run_linear(h, st, h->ctx, CO, CO, nullptr, d.l1, inpt, true, nullptr, 0, nullptr, nullptr, 0, dst, hmax, 0, Bc);
   };
@@ -601,6 +604,24 @@ static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, 
   if ((rc = jet_bias(h->outp, D, table(1))) != PFM_OK) return rc;
   for (size_t l = 0; l < h->layers.size(); ++l)
     if ((rc = jet_bias(h->layers[l].dense, D, table(2 + (int)l))) != PFM_OK) return rc;
+  return PFM_OK;
+}
+
+// One evaluation of the network on the packed state h->xs -> h->v.   t_code: one row (t_stride 0) or one per jet.
+// pre_ev >= 0: the tables were filled by tf_context for all evaluations of the integration (row pre_ev, capacity pre_cap).
+static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, const float* cond, int B, int N, int rows,
+                   int pre_ev = -1, int pre_cap = 0) {
+  const pfm_tf_cfg& c = h->cfg;
+  const int D = c.model_dim, T = c.t_dim, C = c.cond_dim, F = c.feats, CO = c.ctxt_out;
+  const bool per_jet = (t_rows == B && B > 1) || C > 0;
+  const int Bc = per_jet ? B : 1;
+  const int t_stride = (t_rows == B && B > 1) ? T : 0;
+  const int hmax = (int)h->jb_floats;
+  const int jbs = per_jet ? hmax : 0;                 // row stride of the per-jet bias tables
+  int rc;
+  const int cap = pre_ev >= 0 ? pre_cap : B;
+  if (pre_ev < 0 && (rc = tf_context(h, st, t_code, t_stride, cond, Bc, cap)) != PFM_OK) return rc;
+  auto table = [&](int i) { return h->jb + ((size_t)i * cap + (pre_ev >= 0 ? pre_ev : 0)) * hmax; };
   const int* rj = per_jet ? h->rowjet : nullptr;       // shared tables: stride 0, any row index works
   const int* tj = per_jet ? h->tokjet : nullptr;
   auto dense_tail = [&](const TfDense& d, const TfLN* pre, const float* X, int K, float* jbt, const int* jets, float* Hbuf,
@@ -670,8 +691,8 @@ static int tf_eval(pfm_tf* h, cudaStream_t st, const float* t_code, int t_rows, 
   return PFM_OK;
 }
 
-static int tf_plan(pfm_tf* h, cudaStream_t st, const float* x, const float* mask, int B, int N, int* rows_out) {
-  int rc = tf_ensure(h, B, N);
+static int tf_plan(pfm_tf* h, cudaStream_t st, const float* x, const float* mask, int B, int N, int* rows_out, int ctx_rows = 0) {
+  int rc = tf_ensure(h, B, N, ctx_rows);
   if (rc != PFM_OK) return rc;
   plan_count_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, B, N, h->n_real, h->ridx);
   tf_rowoff_kernel<<<1, 32, 0, st>>>(h->n_real, B, h->rowoff, h->n_total);
@@ -861,7 +882,11 @@ int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* con
   PFM_CUDA_CHECK(cudaSetDevice(h->device));
   h->last_launches = 0;
   int rows = 0;
-  if ((rc = tf_plan(h, st, x_inout, mask, B, N, &rows)) != PFM_OK) return rc;
+  const int n_evals = n_steps * (solver == PFM_SOLVER_MIDPOINT ? 2 : 1);
+  const bool shared_ctx = h->cfg.cond_dim == 0;      // every jet shares the time code: one context row per EVALUATION
+  if ((rc = tf_plan(h, st, x_inout, mask, B, N, &rows, shared_ctx ? n_evals : 0)) != PFM_OK) return rc;
+  const int ctx_cap = (int)h->cap_rows;
+  if (shared_ctx && (rc = tf_context(h, st, t_codes, h->cfg.t_dim, nullptr, n_evals, ctx_cap)) != PFM_OK) return rc;
   {
     const size_t smem = sizeof(float) * 2 * (size_t)N * (h->cfg.model_dim / h->cfg.num_heads);
     const int lim = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
@@ -876,7 +901,7 @@ int pfm_tf_sample(pfm_tf* h, float* x_inout, const float* mask, const float* con
   int ev = 0;
   for (int s = 0; s < n_steps; ++s) {
     for (int stage = 0; stage < (mid ? 2 : 1); ++stage, ++ev) {
-      if ((rc = tf_eval(h, st, t_codes + (size_t)ev * T, 1, cond, B, N, rows)) != PFM_OK) return rc;
+      if ((rc = tf_eval(h, st, t_codes + (size_t)ev * T, 1, cond, B, N, rows, shared_ctx ? ev : -1, ctx_cap)) != PFM_OK) return rc;
       if (nel > 0) tf_update_kernel<<<(nel + 255) / 256, 256, 0, st>>>(h->x0, h->xs, h->v, dt, s, (mid && stage == 0) ? 1 : 0, nel);
       h->last_launches++;
     }
