@@ -24,9 +24,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   acc[r][i] = sum_k A[row0 + r][k] * Wt[k][lane + 32 i]
 // A rows are zero in their padding columns [K, round_up(K,4)), so the k loop runs on multiples of 4.
 // ---------------------------------------------------------------------------------------------
-template <int TC, int RB>
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int K,
-                                          int ldo, float* wbuf, int wbuf_half, int KC, float (&acc)[RB][TC]) {
+template <int TC, int RB, int LDA_CT, int LDO_CT, int KC_CT>
+__device__ __forceinline__ void gemm_rows_impl(const float* __restrict__ A, int lda_rt, const float* __restrict__ Wt, int K,
+                                               int ldo_rt, float* wbuf, int wbuf_half, int KC_rt, float (&acc)[RB][TC]) {
+  // LDA_CT / LDO_CT / KC_CT != 0: leading dimensions and chunk depth known at compile time (the H = 128 nets): every
+  // shared-memory access of the inner loop gets an immediate offset instead of integer multiply-adds per load
+  const int lda = LDA_CT ? LDA_CT : lda_rt, ldo = LDO_CT ? LDO_CT : ldo_rt, KC = KC_CT ? KC_CT : KC_rt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int r = 0; r < RB; ++r)
@@ -58,7 +61,8 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, 
     }
     __syncthreads();
     const float* wb = wbuf + (c & 1) * wbuf_half;
-    const int kc = (Kp - k0) < KC ? (Kp - k0) : KC;
+    const int kc = KC_CT ? KC_CT : ((Kp - k0) < KC ? (Kp - k0) : KC);      // compile-time path: K is a multiple of KC_CT
+#pragma unroll
     for (int kk = 0; kk < kc; kk += 4) {
       float4 a[RB];
 #pragma unroll
@@ -80,5 +84,18 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, 
   }
 }
 
+
+
+template <int TC, int RB>
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, const float* __restrict__ Wt, int K,
+                                          int ldo, float* wbuf, int wbuf_half, int KC, float (&acc)[RB][TC]) {
+  if constexpr (TC == 4) {
+    if (lda == 132 && ldo == 128 && KC == 16 && (K & 15) == 0) {          // uniform over the block
+      gemm_rows_impl<TC, RB, 132, 128, 16>(A, lda, Wt, K, ldo, wbuf, wbuf_half, KC, acc);
+      return;
+    }
+  }
+  gemm_rows_impl<TC, RB, 0, 0, 0>(A, lda, Wt, K, ldo, wbuf, wbuf_half, KC, acc);
+}
 
 }  // namespace pfm
