@@ -63,12 +63,12 @@ __device__ __forceinline__ float gemv_col(const float* __restrict__ w, int ldo, 
   return a;
 }
 
-template <int TC, int RB, bool TRAIN>
+template <int TC, int RB, bool TRAIN, bool SPILL>
 __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams p) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem + p.o_xs;      // [R_cap, LDX]   current network input (state or midpoint state)
   float* x0 = smem + p.o_x0;      // [R_cap, F]     state at the start of the step
-  float* hs = p.hs_spill ? p.hs_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_hs;      // [R_cap, LDH]
+  float* hs = SPILL ? p.hs_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_hs;      // [R_cap, LDH]; SPILL is a compile-time flag so that the common case compiles to shared-memory instructions
   float* tmp = smem + p.o_tmp;    // [8*RB, LDH]
   float* wbuf = smem + p.o_wbuf;  // 2 stages
   float* pool = smem + p.o_pool;  // [J_cap, LDP]   (LDP >= 2H + Z)
@@ -521,13 +521,18 @@ static int ensure_spill(pfm_epic* h, SimtShape& s, int grid) {
   return PFM_OK;
 }
 
-template <int TC, int RB, bool TRAIN>
-static int launch_simt(const pfm_epic* h, const SimtShape& s, int grid, cudaStream_t st) {
-  auto kern = epic_simt_kernel<TC, RB, TRAIN>;
+template <int TC, int RB, bool TRAIN, bool SPILL>
+static int launch_simt_s(const SimtShape& s, int grid, cudaStream_t st) {
+  auto kern = epic_simt_kernel<TC, RB, TRAIN, SPILL>;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
   kern<<<grid, kThreads, s.smem, st>>>(s.p);
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
+}
+template <int TC, int RB, bool TRAIN>
+static int launch_simt(const pfm_epic* h, const SimtShape& s, int grid, cudaStream_t st) {
+  (void)h;
+  return s.p.hs_spill ? launch_simt_s<TC, RB, TRAIN, true>(s, grid, st) : launch_simt_s<TC, RB, TRAIN, false>(s, grid, st);
 }
 
 int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {

@@ -214,10 +214,11 @@ __device__ __forceinline__ void global_backward(const BwdParams& p, const Lin& G
   __syncthreads();
 }
 
-template <int TC, int RB>
+// SPILL (compile time): dh lives in global memory; otherwise every access to it is a shared-memory instruction
+template <int TC, int RB, bool SPILL>
 __global__ void __launch_bounds__(kThreads, 1) epic_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* dh = p.dh_spill ? p.dh_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_dh;       // [R_cap, LDH]  gradient w.r.t. the hidden features entering the current unit
+  float* dh = SPILL ? p.dh_spill + (size_t)blockIdx.x * p.R_cap * p.LDH : smem + p.o_dh;       // [R_cap, LDH]  gradient w.r.t. the hidden features entering the current unit
   float* tA = smem + p.o_tA;       // [8*RB, LDH]   chunk of pre-activation gradients (A operand)
   float* tB = smem + p.o_tB;       // [8*RB, LDH]
   float* wbuf = smem + p.o_wbuf;
@@ -584,13 +585,17 @@ int train_layout(const pfm_epic* h, int B, int N, TrainLayout* lay) {
   return PFM_OK;
 }
 
-template <int TC, int RB>
-static int launch_bwd(const BwdShape& s, int grid, cudaStream_t st) {
-  auto kern = epic_bwd_kernel<TC, RB>;
+template <int TC, int RB, bool SPILL>
+static int launch_bwd_s(const BwdShape& s, int grid, cudaStream_t st) {
+  auto kern = epic_bwd_kernel<TC, RB, SPILL>;
   PFM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem));
   kern<<<grid, kThreads, s.smem, st>>>(s.p);
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
+}
+template <int TC, int RB>
+static int launch_bwd(const BwdShape& s, int grid, cudaStream_t st) {
+  return s.p.dh_spill ? launch_bwd_s<TC, RB, true>(s, grid, st) : launch_bwd_s<TC, RB, false>(s, grid, st);
 }
 
 __global__ void reset_counter_kernel(int* counter) { *counter = 0; }
