@@ -95,6 +95,12 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, 
       return;
     }
   }
+  if constexpr (TC == 5) {                                                 // H = 150 (LHCO): leading dimensions only
+    if (lda == 156 && ldo == 152) { gemm_rows_impl<TC, RB, 156, 152, 0>(A, lda, Wt, K, ldo, wbuf, wbuf_half, KC, acc); return; }
+  }
+  if constexpr (TC == 10) {                                                // H = 300 (JetClass cond)
+    if (lda == 304 && ldo == 300) { gemm_rows_impl<TC, RB, 304, 300, 0>(A, lda, Wt, K, ldo, wbuf, wbuf_half, KC, acc); return; }
+  }
   gemm_rows_impl<TC, RB, 0, 0, 0>(A, lda, Wt, K, ldo, wbuf, wbuf_half, KC, acc);
 }
 
