@@ -418,7 +418,7 @@ static int simt_shape(const pfm_epic* h, int N, int Kx, SimtShape* s, int R_cap_
   const int H = c.hid, Z = c.latent, F = c.feats;
   if (H > 320) { set_error("fp32 path supports hid <= 320 (got %d)", H); return PFM_ERR_UNSUPPORTED; }
   s->TC = H <= 128 ? 4 : (H <= 160 ? 5 : 10);
-  s->RB = H <= 160 ? 8 : 4;
+  s->RB = 8;
   const int Hp = (H + 3) & ~3;
   const int LDH = Hp + 4;
   const int Kxmax = c.input_dim > F ? c.input_dim : F;
@@ -554,7 +554,7 @@ int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   if (rc != PFM_OK) return rc;
   if (s.TC == 4) return launch_simt<4, 8, false>(h, s, grid, st);
   if (s.TC == 5) return launch_simt<5, 8, false>(h, s, grid, st);
-  return launch_simt<10, 4, false>(h, s, grid, st);
+  return launch_simt<10, 8, false>(h, s, grid, st);
 }
 
 // training forward: same kernel with the interpolation prologue (loss_kind >= 0), the activation saves and the
@@ -581,7 +581,7 @@ int simt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   if (rc != PFM_OK) return rc;
   if (s.TC == 4) return launch_simt<4, 8, true>(h, s, grid, st);
   if (s.TC == 5) return launch_simt<5, 8, true>(h, s, grid, st);
-  return launch_simt<10, 4, true>(h, s, grid, st);
+  return launch_simt<10, 8, true>(h, s, grid, st);
 }
 
 // group capacity of the forward kernel (the training plan takes the minimum with the backward kernel's)

@@ -633,7 +633,7 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   const int grid = h->sm_count < a.B ? h->sm_count : a.B;
   if (TC == 4) rc = launch_bwd<4, 8>(s, grid, st);
   else if (TC == 5) rc = launch_bwd<5, 8>(s, grid, st);
-  else rc = launch_bwd<10, 4>(s, grid, st);
+  else rc = launch_bwd<10, 8>(s, grid, st);
   if (rc != PFM_OK) return rc;
   h->last_launches += 2;
   if (!a.grad_flat) return PFM_OK;
