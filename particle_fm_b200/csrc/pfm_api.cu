@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "pfm_internal.cuh"
 
 namespace pfm {

@@ -19,4 +19,5 @@ for it in range(4):
     torch.cuda.synchronize(); t2 = time.perf_counter()
     torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5); opt.step()
     torch.cuda.synchronize(); t3 = time.perf_counter()
+    if it == 3: print("groups", m.flows[0].net.engine().last_groups())
     print(f"step {it}: fused fwd+bwd {1e3*(t1-t0):.2f} ms, autograd tail {1e3*(t2-t1):.2f} ms, clip+AdamW {1e3*(t3-t2):.2f} ms")
