@@ -117,30 +117,51 @@ __global__ void plan_group_kernel(const int* __restrict__ n_real, int B, int R_c
 // Inference plan: bin-pack the jets into groups of <= R_cap rows / <= J_cap jets (best-fit decreasing on a histogram of
 // the multiplicities).  The fused kernels are latency-bound per group, so their time is proportional to the NUMBER of
 // groups: packing jets of mixed sizes (JetNet-150: 15..150 particles, 256-row groups) raises the fill from ~80 % (greedy
-// over consecutive jets) to ~97 %.  Deterministic (no atomics in the ordering).  One block; warp 0 does the packing.
-__global__ void plan_pack_kernel(const int* __restrict__ n_real, int B, int R_cap, int J_cap, int2* __restrict__ groups,
-                                 int* __restrict__ n_groups, int* __restrict__ counter, int* __restrict__ jetmap,
-                                 int* __restrict__ order) {
+// over consecutive jets) to ~97 %.  Deterministic (no atomics in the ordering).  One block of PP_WARPS warps: every warp
+// packs a contiguous range of the jets on its own (its own histogram in shared memory, stable counting sort with
+// warp-match ranks, best-fit loop), then the per-warp group lists are compacted into one -- the price is at most one
+// partly filled group per warp.
+static constexpr int PP_WARPS = 8;
+
+__global__ void __launch_bounds__(PP_WARPS * 32) plan_pack_kernel(const int* __restrict__ n_real, int B, int R_cap, int J_cap,
+                                                                  int2* __restrict__ groups, int2* __restrict__ groups_tmp,
+                                                                  int* __restrict__ n_groups, int* __restrict__ counter,
+                                                                  int* __restrict__ jetmap, int* __restrict__ order) {
   extern __shared__ int sp[];
-  int* cnt = sp;                       // [R_cap + 1] jets per multiplicity
-  int* start = sp + (R_cap + 1);       // [R_cap + 1] first slot of the bucket in `order` (descending multiplicity)
-  int* cur = sp + 2 * (R_cap + 1);     // [R_cap + 1] used entries of the bucket
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i <= R_cap; i += blockDim.x) { cnt[i] = 0; cur[i] = 0; }
-  __syncthreads();
-  for (int i = tid; i < B; i += blockDim.x) atomicAdd(&cnt[n_real[i] < R_cap ? n_real[i] : R_cap], 1);
-  __syncthreads();
-  if (tid == 0) {
+  __shared__ int g_of[PP_WARPS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stride = R_cap + 1;
+  int* cnt = sp + warp * 3 * stride;   // [R_cap + 1] jets per multiplicity
+  int* start = cnt + stride;           // [R_cap + 1] first slot of the bucket in this warp's part of `order` (descending multiplicity)
+  int* cur = cnt + 2 * stride;         // [R_cap + 1] used entries of the bucket
+  const int per = (B + PP_WARPS - 1) / PP_WARPS;
+  const int seg0 = min(B, warp * per), seg1 = min(B, seg0 + per);
+  const int nseg = seg1 - seg0;
+  for (int i = lane; i <= R_cap; i += 32) { cnt[i] = 0; cur[i] = 0; }
+  __syncwarp();
+  for (int i = seg0 + lane; i < seg1; i += 32) atomicAdd(&cnt[min(n_real[i], R_cap)], 1);
+  __syncwarp();
+  if (lane == 0) {
     int pos = 0;
     for (int n = R_cap; n >= 0; --n) { start[n] = pos; pos += cnt[n]; }
-    for (int i = 0; i < B; ++i) {      // stable counting sort: jets of equal multiplicity keep their batch order
-      const int n = n_real[i] < R_cap ? n_real[i] : R_cap;
-      order[start[n] + cur[n]++] = i;
-    }
-    for (int n = 0; n <= R_cap; ++n) cur[n] = 0;
   }
-  __syncthreads();
-  if (tid >= 32) return;
+  __syncwarp();
+  // stable counting sort: jets of equal multiplicity keep their batch order (rank inside a block of 32 by warp match)
+  for (int i0 = seg0; i0 < seg1; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < seg1;
+    const int n = valid ? min(n_real[i], R_cap) : -1 - lane;            // invalid lanes: unique keys
+    const unsigned same = __match_any_sync(0xffffffffu, n);
+    const int leader = __ffs(same) - 1;
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    int base = 0;
+    if (valid && lane == leader) { base = cur[n]; cur[n] = base + __popc(same); }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) order[seg0 + start[n] + base + rank] = i;
+    __syncwarp();
+  }
+  for (int n = lane; n <= R_cap; n += 32) cur[n] = 0;
+  __syncwarp();
   // largest multiplicity n in [1, lim] with an unused jet, or 0
   auto find_le = [&](int lim) -> int {
     for (int base = lim; base >= 1; base -= 32) {
@@ -152,14 +173,14 @@ __global__ void plan_pack_kernel(const int* __restrict__ n_real, int B, int R_ca
     return 0;
   };
   int pos = 0, g = 0, top = R_cap;
-  int remaining = B - cnt[0], zero_left = cnt[0];
+  int remaining = nseg - cnt[0], zero_left = cnt[0];
   while (remaining > 0) {
     int n = find_le(top);
     top = n;
     const int first = pos;
     int rows = 0, jets = 0;
     while (n > 0) {
-      if (lane == 0) { jetmap[pos] = order[start[n] + cur[n]]; cur[n]++; }
+      if (lane == 0) { jetmap[seg0 + pos] = order[seg0 + start[n] + cur[n]]; cur[n]++; }
       __syncwarp();
       ++pos; rows += n; ++jets; --remaining;
       if (jets >= J_cap || remaining == 0) break;
@@ -167,25 +188,37 @@ __global__ void plan_pack_kernel(const int* __restrict__ n_real, int B, int R_ca
       n = lim >= 1 ? find_le(lim) : 0;
     }
     while (jets < J_cap && zero_left > 0) {        // empty jets ride along in spare jet slots
-      if (lane == 0) { jetmap[pos] = order[start[0] + cur[0]]; cur[0]++; }
+      if (lane == 0) { jetmap[seg0 + pos] = order[seg0 + start[0] + cur[0]]; cur[0]++; }
       __syncwarp();
       ++pos; ++jets; --zero_left;
     }
-    if (lane == 0) groups[g] = make_int2(first, jets);
+    if (lane == 0) groups_tmp[seg0 + g] = make_int2(seg0 + first, jets);
     ++g;
   }
   while (zero_left > 0) {
     const int first = pos;
     int jets = 0;
     while (jets < J_cap && zero_left > 0) {
-      if (lane == 0) { jetmap[pos] = order[start[0] + cur[0]]; cur[0]++; }
+      if (lane == 0) { jetmap[seg0 + pos] = order[seg0 + start[0] + cur[0]]; cur[0]++; }
       __syncwarp();
       ++pos; ++jets; --zero_left;
     }
-    if (lane == 0) groups[g] = make_int2(first, jets);
+    if (lane == 0) groups_tmp[seg0 + g] = make_int2(seg0 + first, jets);
     ++g;
   }
-  if (lane == 0) { *n_groups = g; *counter = 0; }
+  if (lane == 0) g_of[warp + 1] = g;
+  __syncthreads();
+  if (tid == 0) {
+    g_of[0] = 0;
+    for (int w = 0; w < PP_WARPS; ++w) g_of[w + 1] += g_of[w];
+    *n_groups = g_of[PP_WARPS];
+    *counter = 0;
+  }
+  __syncthreads();
+  for (int w = 0; w < PP_WARPS; ++w) {
+    const int s0 = min(B, w * per), cntw = g_of[w + 1] - g_of[w];
+    for (int i = tid; i < cntw; i += blockDim.x) groups[g_of[w] + i] = groups_tmp[s0 + i];
+  }
 }
 
 __global__ void rowmajor_main_kernel(const float* __restrict__ W, float* __restrict__ Wr, int out, int in, int m_off,
@@ -204,6 +237,8 @@ static int ensure_plan(pfm_epic* h, int B, int N) {
     if (p.rowoff) cudaFree(p.rowoff);
     if (p.jetmap) cudaFree(p.jetmap);
     if (p.order) cudaFree(p.order);
+    if (p.groups_tmp) cudaFree(p.groups_tmp);
+    PFM_CUDA_CHECK(cudaMalloc(&p.groups_tmp, sizeof(int2) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.jetmap, sizeof(int) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.order, sizeof(int) * B));
     PFM_CUDA_CHECK(cudaMalloc(&p.n_real, sizeof(int) * B));
@@ -234,7 +269,8 @@ static int ensure_floats(float** buf, size_t* cap, size_t need) {
   return PFM_OK;
 }
 
-static const int kMaxJetsPerCall = 12000;   // plan_group_kernel stages n_real in 48 KB of shared memory
+static const int kMaxJetsPerCall = 12000;   // training: plan_group_kernel stages n_real in 48 KB of shared memory
+static const int kMaxJetsPerLaunch = 1 << 20;   // sampling / forward: jets per fused launch (larger requests run in slices)
 
 // Everything one hot-path call needs besides the kernel itself.
 static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_jet_t, const float* t_code_in,
@@ -282,14 +318,17 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
   }
   PFM_CUDA_CHECK(cudaGetLastError());
 
-  for (int b0 = 0; b0 < B; b0 += kMaxJetsPerCall) {
-    const int nb = (B - b0 < kMaxJetsPerCall) ? (B - b0) : kMaxJetsPerCall;
+  for (int b0 = 0; b0 < B; b0 += kMaxJetsPerLaunch) {
+    const int nb = (B - b0 < kMaxJetsPerLaunch) ? (B - b0) : kMaxJetsPerLaunch;
     rc = ensure_plan(h, nb, N);
     if (rc != PFM_OK) return rc;
     const float* mk = mask ? mask + (size_t)b0 * N : nullptr;
     plan_count_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mk, nb, N, h->plan.n_real, h->plan.ridx);
-    plan_pack_kernel<<<1, 1024, sizeof(int) * 3 * (R_cap + 1), st>>>(h->plan.n_real, nb, R_cap, J_cap, h->plan.groups,
-                                                                     h->plan.n_groups, h->plan.counter, h->plan.jetmap, h->plan.order);
+    const size_t pp_smem = sizeof(int) * 3 * (size_t)(R_cap + 1) * PP_WARPS;
+    if (pp_smem > 48 * 1024) PFM_CUDA_CHECK(cudaFuncSetAttribute(plan_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem));
+    plan_pack_kernel<<<1, PP_WARPS * 32, pp_smem, st>>>(
+        h->plan.n_real, nb, R_cap, J_cap, h->plan.groups, h->plan.groups_tmp, h->plan.n_groups, h->plan.counter, h->plan.jetmap,
+        h->plan.order);
     h->last_launches += 2;
     PFM_CUDA_CHECK(cudaGetLastError());
     RunArgs a;
@@ -591,6 +630,7 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->plan.rowoff) cudaFree(h->plan.rowoff);
   if (h->plan.jetmap) cudaFree(h->plan.jetmap);
   if (h->plan.order) cudaFree(h->plan.order);
+  if (h->plan.groups_tmp) cudaFree(h->plan.groups_tmp);
   if (h->plan.n_total) cudaFree(h->plan.n_total);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->grad_ev) cudaEventDestroy(e);

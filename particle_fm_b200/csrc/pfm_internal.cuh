@@ -33,6 +33,7 @@ struct Plan {          // device buffers describing how jets are packed into CTA
   int* n_real;         // [B]     real particles per jet
   uint16_t* ridx;      // [B*N]   ridx[b*N + r] = particle index of the r-th real particle of jet b
   int2* groups;        // [B]     (first jet, number of jets) of every group
+  int2* groups_tmp;    // [B]     per-warp group lists of the inference plan before compaction
   int* n_groups;       // [1]
   int* counter;        // [1]     dynamic work counter for persistent CTAs
   int* jetmap;         // [B]     inference plan: jet handled at position i (groups are ranges of POSITIONS; jets are

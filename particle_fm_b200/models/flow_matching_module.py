@@ -175,6 +175,11 @@ class CNF(nn.Module):
             t_eval, dt = fixed_step_grid(ode_steps, ode_solver)
             cache[key] = (self.time_code(t_eval), dt)  # [n_evals, T], evaluated on the CPU like the oracle
         codes, dt = cache[key]
+        if z.device.type == "cuda":               # device copies cached too: a pageable host -> device copy per call would
+            dkey = (key, z.device)                #  make the host wait for the GPU work already queued on the stream
+            if dkey not in cache:
+                cache[dkey] = (codes.to(z.device), dt.to(z.device))
+            codes, dt = cache[dkey]
         eng = self.net.engine()
         takes = self.net.t_local_cat or self.net.t_global_cat
         return eng.sample(z, mask, cond, codes if takes else None, codes if self.add_time_to_input else None, dt,
@@ -282,32 +287,52 @@ class SetFlowMatchingLitModule(_LightningBase):
                     "lr_scheduler": {"scheduler": scheduler, "monitor": "val/loss", "interval": "epoch", "frequency": 1}}
         return {"optimizer": optimizer}
 
+    def __getstate__(self):             # transfer helpers (pinned buffer, event, copy stream) are per-process: never pickled / deep-copied
+        st = self.__dict__.copy()
+        for k in ("_noise_pin", "_noise_evt", "_copy_stream"):
+            st.pop(k, None)
+        return st
+
     @torch.no_grad()
     def sample(self, n_samples: int, cond: Tensor = None, mask: Tensor = None, ode_solver: str = "midpoint",
                ode_steps: int = 100, num_points: int = None):
         """Generate samples (flow_matching_module.py:637-677): noise from the CPU default generator
         (same stream as the reference), masked, integrated 1 -> 0 on the GPU in one launch."""
         shape = (n_samples, num_points if num_points else self.hparams.num_particles, self.hparams.features)
-        if self.device.type == "cuda":
-            # same CPU-generator stream as torch.randn(shape) (checked in tests), drawn into a cached pinned buffer so
-            # that the host -> device copy of the noise runs at PCIe speed
-            buf = self.__dict__.get("_noise_pin")
-            if buf is None or buf.numel() < shape[0] * shape[1] * shape[2]:
-                buf = torch.empty(shape[0] * shape[1] * shape[2], pin_memory=True)
-                self.__dict__["_noise_pin"] = buf
-            evt = self.__dict__.get("_noise_evt")
-            if evt is not None:
-                evt.synchronize()              # the previous call's copy out of this buffer has completed
-            z = torch.randn(shape, out=buf[:shape[0] * shape[1] * shape[2]].view(shape)).to(self.device, non_blocking=True)
-            evt = torch.cuda.Event()
-            evt.record(torch.cuda.current_stream(self.device))
-            self.__dict__["_noise_evt"] = evt
-        else:
-            z = torch.randn(shape).to(self.device)
         if cond is not None:
             cond = cond.to(self.device)
         if mask is not None:
             mask = mask[:n_samples]
             mask = mask.to(self.device)
+        if self.device.type != "cuda":
+            z = torch.randn(shape).to(self.device)
+            if mask is not None:
+                z = z * mask
+            return self.forward(z, cond=cond, mask=mask, reverse=True, ode_solver=ode_solver, ode_steps=ode_steps)
+        # The noise comes from the CPU default generator like the reference's torch.randn(shape), drawn straight into a
+        # cached pinned buffer and copied on a side stream: nothing here waits for GPU work already queued, so in a loop of
+        # calls (generate_data batches) the draw for call k+1 runs while the GPU integrates call k.
+        numel = n_samples * shape[1] * shape[2]
+        buf = self.__dict__.get("_noise_pin")
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(numel, pin_memory=True)
+            self.__dict__["_noise_pin"] = buf
+        evt = self.__dict__.get("_noise_evt")
+        if evt is not None:
+            evt.synchronize()                  # the previous call's copy out of this buffer has completed
+        zc = torch.randn(shape, out=buf[:numel].view(shape))
+        main = torch.cuda.current_stream(self.device)
+        side = self.__dict__.get("_copy_stream")
+        if side is None or side.device != self.device:
+            side = torch.cuda.Stream(device=self.device)
+            self.__dict__["_copy_stream"] = side
+        with torch.cuda.stream(side):
+            z = zc.to(self.device, non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(side)
+        self.__dict__["_noise_evt"] = evt
+        main.wait_event(evt)
+        z.record_stream(main)
+        if mask is not None:
             z = z * mask
         return self.forward(z, cond=cond, mask=mask, reverse=True, ode_solver=ode_solver, ode_steps=ode_steps)
