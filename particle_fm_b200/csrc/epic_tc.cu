@@ -68,7 +68,7 @@ struct TcSmem {
   uint32_t tmem_base;
   uint64_t full[TC_NSLOT], empty[TC_NSLOT];
   uint64_t hready[2], accU_full[2], u_ready[2], accH_full[2];
-  uint64_t pool_full, glob_go, glob_full, d_free;
+  uint64_t pool_full, glob_go, glob_full, d_free, wg1_ready;
   uint64_t spk_full, spk_empty;
 };
 
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
     }
     mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 256); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 256);
+    mbar_init(&s.wg1_ready, 128);
     mbar_init(&s.spk_full, 1); mbar_init(&s.spk_empty, 256);
     fence_barrier_init();
   }
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 
   // running use counters of every barrier (parity = count & 1); each role only advances the ones it uses
   uint32_t ring_it = 0;                                     // producer / MMA: weight items consumed so far
-  uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0}, c_globgo = 0, c_dfree = 0;           // MMA side
+  uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0}, c_globgo = 0, c_dfree = 0, c_wg1 = 0;   // MMA side
+  uint32_t ring_e = 0;                                      // epilogue: mirror of the weight-ring position (tile A stages W_g1 into TMEM)
   uint32_t c_accH = 0, c_accU = 0, c_pool = 0, c_glob = 0, c_spk = 0;                         // epilogue side
   uint32_t spk_it = 0;                                      // producer: small-weight packs issued so far
 
@@ -305,26 +307,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . mean[jet][:] + W_sum[o][:] . sum[jet][:]
             // (issued before fc_local1: it is on the serial per-jet chain, fc_local1's result is not needed before the chain ends)
             const uint32_t it_gm = ring_it++, it_gs = ring_it++;
+            // The 128 x 256 weight block is the A operand: read from shared memory it costs 64 cycles per K = 16 step
+            // whatever N is (operand fetch at 64 B/clk), and these 16 steps sit on the serial per-jet chain.  Tile A's
+            // epilogue warps therefore copy the two images into TMEM (the fc_local1 accumulator of tile A is free until
+            // this unit's fc_local1) while the pooling MMAs run, and the MMAs take A from TMEM: ~8 cycles per step.
             PROF_T(0);
+            mbar_wait(&s.wg1_ready, c_wg1++ & 1);
+            tc_fence_after();
+            if (elect_one()) { mbar_arrive(&s.empty[it_gm % TC_NSLOT]); mbar_arrive(&s.empty[it_gs % TC_NSLOT]); }   // images consumed
+            __syncwarp();
+            PROF_T(6);
             mbar_wait(&s.glob_go, c_globgo++ & 1);
             tc_fence_after();
             PROF_T(5);
-            for (int m = 0; m < 2; ++m) {
-              const uint32_t itw = m ? it_gs : it_gm;
-              wait_full(itw);
-              PROF_T(6);
-              const uint64_t wd = wslot(itw);
-              if (elect_one()) {
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  mma_ss(dglob + (uint32_t)((k & 3) * 16), wd + kstep16(k), sdesc + (uint64_t)((m * 2 + (k >> 2)) * 128 + (k & 3) * 2), idesc_glob,
-                         (m | (k >> 2)) ? 1u : 0u);
-              }
-              __syncwarp();
+              for (int kk = 0; kk < 16; ++kk)
+                mma_ts(dglob + (uint32_t)((kk & 3) * 16), accU0 + (uint32_t)kk * 8u, sdesc + (uint64_t)((kk >> 2) * 128 + (kk & 3) * 2), idesc_glob,
+                       (kk >> 2) ? 1u : 0u);
             }
+            __syncwarp();
             commit_to(&s.glob_full);
-            commit_to(&s.empty[it_gm % TC_NSLOT]);
-            commit_to(&s.empty[it_gs % TC_NSLOT]);
             if (gi >= 1) {   // fc_local1 of tile A
               PROF_T(0);
               wait_full(it_w1);
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           for (int q = 0; q < 4; ++q) sreg[bb][q] = 0.f;
 
         compute_pre(0);
+        ++ring_e;                                  // the stem's fc_l2 image
 #pragma unroll 1
         for (int gi = 0;; ++gi) {
           // ======== residual update epilogue of the h version unit gi pools: the stem's fc_l2 (gi = 0), fc_local2 of layer
@@ -593,6 +597,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
             tc_fence_before();
             mbar_arrive(&s.hready[wg]);
             PROF_T(18);
+          }
+          // ======== tile A's warps stage this unit's W_g1 (mean | sum images of the ring) into TMEM as the A operand of the
+          // fc_global1 MMAs: thread = output row o, 2 x 128 k values = 128 packed columns of tile A's fc_local1 accumulator
+          {
+            if (gi >= 1) ++ring_e;                 // fc_local1 image comes first in the ring
+            const uint32_t it_gm = ring_e++, it_gs = ring_e++;
+            if (gi >= 1) ++ring_e;                 // fc_local2 image
+            if (wg == 0) {
+#pragma unroll 1
+              for (int m = 0; m < 2; ++m) {
+                const uint32_t itw = m ? it_gs : it_gm;
+                mbar_wait(&s.full[itw % TC_NSLOT], (itw / TC_NSLOT) & 1);
+                const uint32_t img = smem_u32(s.w[itw % TC_NSLOT]) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  uint32_t v[32];
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 q = lds128(img + (uint32_t)(half * 16384) + ((uint32_t)(c << 4) ^ rx16));
+                    v[c * 4 + 0] = __float_as_uint(q.x); v[c * 4 + 1] = __float_as_uint(q.y);
+                    v[c * 4 + 2] = __float_as_uint(q.z); v[c * 4 + 3] = __float_as_uint(q.w);
+                  }
+                  tmem_st32(accU + (uint32_t)(m * 64 + half * 32), v);
+                }
+              }
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&s.wg1_ready);
+            }
           }
           // ======== global phase gi: 0 = stem (fc_g1, fc_g2), gi >= 1 = EPiC layer gi-1 (fc_global1/2) ========
           // Per-jet work is split over the 256 threads as (o = r) x (batches of 4 jets: wg, wg + 2).
