@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         for (int ev = 0; ev < p.n_evals; ++ev) {
           for (int it = 0; it < p.n_items; ++it, ++ring_it) {
             // the small-weight pack + bias slice of unit u travel just before the unit's global-MLP images
-            const int u = it == 1 ? 0 : ((it >= 4 && ((it - 4) & 3) == 0) ? 1 + ((it - 4) >> 2) : -1);
+            const int u = it == 1 ? 0 : ((it >= 3 && ((it - 3) & 3) == 0) ? 1 + ((it - 3) >> 2) : -1);
             if (u >= 0) {
               mbar_wait(&s.spk_empty, (spk_it & 1) ^ 1);
               ++spk_it;
@@ -303,10 +303,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               }
               commit_to(&s.pool_full);
             }
-            if (gi >= 1) it_w1 = ring_it++;          // ring order: fc_local1 | fc_global1 mean | sum | fc_local2
+            // ring order: fc_global1 mean | sum | fc_local1 | fc_local2
             // ---- 256 -> 128 part of fc_g1 / fc_global1:  D[o][jet] = W_mean[o][:] . mean[jet][:] + W_sum[o][:] . sum[jet][:]
             // (issued before fc_local1: it is on the serial per-jet chain, fc_local1's result is not needed before the chain ends)
             const uint32_t it_gm = ring_it++, it_gs = ring_it++;
+            if (gi >= 1) it_w1 = ring_it++;
             // The 128 x 256 weight block is the A operand: read from shared memory it costs 64 cycles per K = 16 step
             // whatever N is (operand fetch at 64 B/clk), and these 16 steps sit on the serial per-jet chain.  Tile A's
             // epilogue warps therefore copy the two images into TMEM (the fc_local1 accumulator of tile A is free until
@@ -601,9 +602,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           // ======== tile A's warps stage this unit's W_g1 (mean | sum images of the ring) into TMEM as the A operand of the
           // fc_global1 MMAs: thread = output row o, 2 x 128 k values = 128 packed columns of tile A's fc_local1 accumulator
           {
-            if (gi >= 1) ++ring_e;                 // fc_local1 image comes first in the ring
             const uint32_t it_gm = ring_e++, it_gs = ring_e++;
-            if (gi >= 1) ++ring_e;                 // fc_local2 image
+            if (gi >= 1) ring_e += 2;              // fc_local1, fc_local2 images
             if (wg == 0) {
 #pragma unroll 1
               for (int m = 0; m < 2; ++m) {
@@ -894,9 +894,9 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
   src[it++] = mk(LIN_G1, TCH);      // stem concat order is (sum, mean): the mean block is second (epic.py:373)
   src[it++] = mk(LIN_G1, 0);
   for (int l = 0; l < c.layers; ++l) {
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, 0);       // fc_global1: (mean, sum, global) order (epic.py:164-171); first in the
+    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, TCH);     //  ring: tile A's warps stage them into TMEM as soon as they land
     src[it++] = mk(LIN_LAYER0 + 4 * l + 2, 0);       // fc_local1, particle columns
-    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, 0);       // fc_global1: (mean, sum, global) order (epic.py:164-171)
-    src[it++] = mk(LIN_LAYER0 + 4 * l + 0, TCH);
     src[it++] = mk(LIN_LAYER0 + 4 * l + 3, 0);       // fc_local2
   }
   std::vector<SpkSrc> spk(c.layers + 1);
