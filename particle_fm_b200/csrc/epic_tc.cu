@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
     }
     mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 256); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 256);
-    mbar_init(&s.wg1_ready, 128);
+    mbar_init(&s.wg1_ready, 256);
     mbar_init(&s.spk_full, 1); mbar_init(&s.spk_empty, 256);
     fence_barrier_init();
   }
@@ -604,9 +604,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           {
             const uint32_t it_gm = ring_e++, it_gs = ring_e++;
             if (gi >= 1) ring_e += 2;              // fc_local1, fc_local2 images
-            if (wg == 0) {
-#pragma unroll 1
-              for (int m = 0; m < 2; ++m) {
+            {                                      // tile A's warps copy the mean image, tile B's the sum image (same TMEM lanes)
+              {
+                const int m = wg;
                 const uint32_t itw = m ? it_gs : it_gm;
                 mbar_wait(&s.full[itw % TC_NSLOT], (itw / TC_NSLOT) & 1);
                 const uint32_t img = smem_u32(s.w[itw % TC_NSLOT]) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
                     v[c * 4 + 0] = __float_as_uint(q.x); v[c * 4 + 1] = __float_as_uint(q.y);
                     v[c * 4 + 2] = __float_as_uint(q.z); v[c * 4 + 3] = __float_as_uint(q.w);
                   }
-                  tmem_st32(accU + (uint32_t)(m * 64 + half * 32), v);
+                  tmem_st32(lane_base + 256u + (uint32_t)(m * 64 + half * 32), v);      // tile A's fc_local1 accumulator
                 }
               }
               tmem_wait_st();
