@@ -67,7 +67,7 @@ struct TcSmem {
   int group;
   uint32_t tmem_base;
   uint64_t full[TC_NSLOT], empty[TC_NSLOT];
-  uint64_t hready[2], accU_full[2], u_ready[2], accH_full[2];
+  uint64_t hready[2], accU_full[2], u_ready[2][2], accH_full[2];      // u_ready[tile][half of the 128 u columns]
   uint64_t pool_full, glob_go, glob_full, d_free, wg1_ready;
   uint64_t spk_full, spk_empty;
 };
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t], 128); mbar_init(&s.accH_full[t], 1);
+      mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t][0], 128); mbar_init(&s.u_ready[t][1], 128);
+      mbar_init(&s.accH_full[t], 1);
     }
     mbar_init(&s.pool_full, 1); mbar_init(&s.glob_go, 256); mbar_init(&s.glob_full, 1); mbar_init(&s.d_free, 256);
     mbar_init(&s.wg1_ready, 256);
@@ -345,20 +346,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               commit_to(&s.accU_full[1]);
               commit_to(&s.empty[it_w1 % TC_NSLOT]);
               const uint32_t it_w2 = ring_it++;
-              for (int t = 0; t < 2; ++t) {          // fc_local2: accH[t] += u[t] (bf16 in TMEM) . W2^T
-                PROF_T(0);
-                mbar_wait(&s.u_ready[t], c_uready[t]++ & 1);
-                tc_fence_after();
-                PROF_T(8 + t);
-                if (t == 0) wait_full(it_w2);
-                PROF_T(10);
-                const uint64_t wd = wslot(it_w2);
-                if (elect_one()) {
+              // fc_local2: accH[t] += u[t] (bf16 in TMEM) . W2^T.  The fc_local1 epilogue hands over u in two halves of 64
+              // columns, so the first four K steps of both tiles run while the second half is still being written.
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) mma_ts(t ? accH1 : accH0, (t ? accU1 : accU0) + (uint32_t)k * 8u, wd + kstep16(k), idesc, 1u);
+              for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                  PROF_T(0);
+                  mbar_wait(&s.u_ready[t][half], c_uready[t] & 1);
+                  tc_fence_after();
+                  PROF_T(8 + t);
+                  if (t == 0 && half == 0) wait_full(it_w2);
+                  PROF_T(10);
+                  const uint64_t wd = wslot(it_w2);
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k = half * 4; k < half * 4 + 4; ++k)
+                      mma_ts(t ? accH1 : accH0, (t ? accU1 : accU0) + (uint32_t)k * 8u, wd + kstep16(k), idesc, 1u);
+                  }
+                  __syncwarp();
+                  if (half == 1) { commit_to(&s.accH_full[t]); ++c_uready[t]; }
                 }
-                __syncwarp();
-                commit_to(&s.accH_full[t]);
               }
               commit_to(&s.empty[it_w2 % TC_NSLOT]);
             }
@@ -754,10 +762,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               tmem_wait_ld();
               if (cc == 0) tmem_ld32(accU + 64, va);
               epi1_chunk(vb, 2 * cc + 1);
+              tmem_wait_st();                      // u columns [32 cc, 32 cc + 32) = K steps 4 cc .. 4 cc + 3 of fc_local2
+              tc_fence_before();
+              mbar_arrive(&s.u_ready[wg][cc]);
             }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&s.u_ready[wg]);
             PROF_T(15);
           }
           if (gi < L) compute_pre(gi + 1);         // next unit's [A] while the tensor pipe runs fc_local2
