@@ -722,25 +722,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               __syncwarp();                        // every lane has read the old g before it is overwritten
               if (kh == 0 && z < Z) s.gv[j][z] = gz;
               if (gi >= 1) {
+                // lane = 4 consecutive outputs: one 8-byte load of W_glob per z, 16-byte bias loads / stores
+                const int o4 = lane_ * 4;
                 float b1v[4], b2v[4];
+                if (SIMPLE) {
+                  const float4 t1 = *reinterpret_cast<const float4*>(&s.sbias[128 + ZP + o4]);
+                  const float4 t2 = *reinterpret_cast<const float4*>(&s.sbias[256 + ZP + o4]);
+                  b1v[0] = t1.x; b1v[1] = t1.y; b1v[2] = t1.z; b1v[3] = t1.w;
+                  b2v[0] = t2.x; b2v[1] = t2.y; b2v[2] = t2.z; b2v[3] = t2.w;
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  b1v[i] = unit_bias(La, 128 + ZP, s.jid[j], lane_ + 32 * i);
-                  b2v[i] = unit_bias(Lb, 256 + ZP, s.jid[j], lane_ + 32 * i);
-                }
-#pragma unroll
-                for (int zz = 0; zz < TC_ZMAX; ++zz) {           // rows zz >= Z of W_glob are zero and gz is 0 there
-                  {
-                    const float g = __shfl_sync(0xffffffffu, gz, zz);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) b1v[i] = fmaf(__bfloat162float(s.spk.gl[zz][lane_ + 32 * i]), g, b1v[i]);
+                  for (int i = 0; i < 4; ++i) {
+                    b1v[i] = unit_bias(La, 128 + ZP, s.jid[j], o4 + i);
+                    b2v[i] = unit_bias(Lb, 256 + ZP, s.jid[j], o4 + i);
                   }
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  s.bl1[j][lane_ + 32 * i] = b1v[i];
-                  s.bl2[j][lane_ + 32 * i] = b2v[i];
+                for (int zz = 0; zz < TC_ZMAX; ++zz) {           // rows zz >= Z of W_glob are zero and gz is 0 there
+                  const float g = __shfl_sync(0xffffffffu, gz, zz);
+                  const uint2 w = *reinterpret_cast<const uint2*>(&s.spk.gl[zz][o4]);
+                  b1v[0] = fmaf(__uint_as_float(w.x << 16), g, b1v[0]);
+                  b1v[1] = fmaf(__uint_as_float(w.x & 0xffff0000u), g, b1v[1]);
+                  b1v[2] = fmaf(__uint_as_float(w.y << 16), g, b1v[2]);
+                  b1v[3] = fmaf(__uint_as_float(w.y & 0xffff0000u), g, b1v[3]);
                 }
+                *reinterpret_cast<float4*>(&s.bl1[j][o4]) = make_float4(b1v[0], b1v[1], b1v[2], b1v[3]);
+                *reinterpret_cast<float4*>(&s.bl2[j][o4]) = make_float4(b2v[0], b2v[1], b2v[2], b2v[3]);
               }
             }
           }
