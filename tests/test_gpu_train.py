@@ -132,3 +132,42 @@ def test_optimizer_step_changes_the_packed_weights():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_weight_norm_fold_and_chain_rule_in_the_library():
+    """pfm_epic_set_params / pfm_epic_param_grads against torch._weight_norm and its autograd (what the reference runs as
+    a forward pre-hook on every linear, epic.py:66-81): folded weights give the same vector field as handing over the
+    torch-folded weights, and an arbitrary flat folded-weight gradient maps onto the same d weight_v / d weight_g / d bias."""
+    g = Golden("cond_lhco_like")
+    m = build_module(g.ctor, g.sd, device=DEV)
+    net = m.flows[0].net
+    lins = net.linears()
+    eng = net.engine(sync_weights=False)
+    # forward: library fold vs torch fold
+    eng.set_params(lins, key=None)
+    t = torch.tensor(0.41, device=DEV)
+    with torch.no_grad():
+        cond = g.cond.to(DEV)
+        code = m.flows[0].time_code(t)
+        v_lib = eng.forward(code, g.x.to(DEV), g.mask.to(DEV), cond)
+        folded = [lin.folded() for lin in lins]
+        eng.set_weights([w for w, _ in folded], [b for _, b in folded], key=None)
+        v_torch = eng.forward(code, g.x.to(DEV), g.mask.to(DEV), cond)
+    assert rel_l2(v_lib.cpu(), v_torch.cpu()) < 1e-6
+    # backward: random flat gradient of the folded weights
+    gen = torch.Generator().manual_seed(9)
+    flat = torch.randn(eng.grad_size(), generator=gen).to(DEV)
+    scale = torch.tensor(0.37, device=DEV)
+    got = eng.param_grads(flat, scale, lins)
+    views = eng.grad_views(flat)
+    for lin, (dv, dg, db), (gw, gb) in zip(lins, got, views):
+        if lin.weight_norm:
+            v = lin.weight_v.detach().clone().requires_grad_(True)
+            gg = lin.weight_g.detach().clone().requires_grad_(True)
+            w = torch._weight_norm(v, gg, 0)
+            (w * gw.view_as(w)).sum().mul(scale).backward()
+            assert rel_l2(dv.cpu(), v.grad.cpu()) < 1e-5
+            assert rel_l2(dg.cpu().flatten(), gg.grad.cpu().flatten()) < 1e-5
+        else:
+            assert dg is None and rel_l2(dv.cpu(), (gw.view_as(dv) * scale).cpu()) < 1e-6
+        assert rel_l2(db.cpu(), (gb * scale).cpu()) < 1e-6
