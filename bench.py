@@ -37,6 +37,7 @@ YAML_NET = dict(features=FEATS, hidden_dim=128, num_particles=N_PART, frequencie
                 t_emb="cosine", t_local_cat=True, t_global_cat=True, add_time_to_input=False)
 WORKLOAD = ("EPiC-FM JetNet-150 (150x3, variable-multiplicity masks) midpoint ode_steps=200 generation, "
             "random-init default net (H128 Z10 L6 T32), jets sharded over ranks")
+WORKLOAD_ALL_REAL = WORKLOAD.replace("variable-multiplicity masks", "all 150 particles real")
 # FLOP per real particle per evaluation and per jet per evaluation (hoisted form)
 FLOP_PER_PARTICLE, FLOP_PER_JET = 427_520, 684_096
 
@@ -118,6 +119,27 @@ def oracle_sampler():
         with torch.no_grad():
             return lo.sample(vf, z, mask, SOLVER, ODE_STEPS)
     return run
+
+
+def eager_gpu_leg(dev, n_jets):
+    """The oracle port (the reference's module arithmetic, eager PyTorch ops, fp32) run on the GPU: what a user of the
+    reference gets on one B200 without this library.  Outside every timed region of the product path."""
+    from oracle import epic_oracle as eo, loss_oracle as lo
+    cfg = eo.EpicCfg(feats=FEATS, input_dim=FEATS, hid=128, latent=10, layers=6, t_dim=32, t_local_cat=True, t_global_cat=True)
+    sd = {k: v.to(dev) for k, v in eo.synth_state_dict(cfg, 12345).items()}
+    mask, n_real = synth_masks(n_jets, 9999)
+    z = (torch.randn(n_jets, N_PART, FEATS, generator=torch.Generator().manual_seed(1)) * mask).to(dev)
+    mask = mask.to(dev)
+    vf = lambda t, y: eo.cnf_forward(sd, cfg, t.to(dev), y, None, mask, t_emb="cosine", frequencies=16, add_time_to_input=False)
+    with torch.no_grad():
+        lo.sample(vf, z, mask, SOLVER, 4)                        # warm-up (3 steps)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lo.sample(vf, z, mask, SOLVER, ODE_STEPS)
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_jets / dt, "unit": "jets/s", "kind": "oracle port, eager PyTorch fp32 on cuda:0 (one launch per op)",
+            "sample": f"{n_jets} jets (the reference's eval batch size, jetnet_eval.yaml:16-19), full 398 evaluations, {dt:.2f} s"}
 
 
 def time_cpu(run, n_jets, seed, reps=1):
@@ -214,6 +236,7 @@ def main():
     ap.add_argument("--cpu-baseline-jets", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
+    ap.add_argument("--no-all-real", action="store_true", help="skip the all-real roofline variant")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,12 +275,11 @@ def main():
     mask_d, z_d = mask_h.to(dev), z_h.to(dev)
     gather_buf = [torch.empty(B, N_PART, FEATS, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    from particle_fm_b200.launch import generate_data_sharded, integrate_and_gather
 
     def step():
-        out = cnf.decode(z_d, None, mask_d, ode_solver=SOLVER, ode_steps=ODE_STEPS)
-        if world > 1:
-            dist.gather(out, gather_buf, dst=0)
-        return out
+        # the product launcher's device half: fused reverse pass of this rank's slice + the final gather to rank 0
+        return integrate_and_gather(model, z_d, None, mask_d, B, SOLVER, ODE_STEPS, parts=gather_buf)
 
     for _ in range(args.warmup):
         step()
@@ -287,25 +309,93 @@ def main():
     total_ms = float(t.item())
     value = world * B * args.steps / (total_ms / 1e3)
 
-    # ---- end to end through the public API: CPU noise, H2D of inputs, integration, D2H of the result ----
-    mask_pin = mask_h.pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
-    res_pin = torch.empty(B, N_PART, FEATS).pin_memory()                                # the result lands in pinned host memory
-    res_pin.copy_(model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS))   # warm
+    # ---- multi-GPU correctness, outside the timed region: rank 0 re-integrates every other rank's slice (inputs
+    # regenerated from the rank's seeds) on its own GPU and compares with what the gather delivered: bit-equal ----
+    multi_check = None
+    if world > 1 and rank == 0:
+        bad = 0
+        for r in range(1, world):
+            m_r, _ = synth_masks(B, 9999 + r)
+            if args.all_real:
+                m_r = torch.ones_like(m_r)
+            z_r = torch.randn(B, N_PART, FEATS, generator=torch.Generator().manual_seed(4242 + r)) * m_r
+            ref_r = cnf.decode(z_r.to(dev), None, m_r.to(dev), ode_solver=SOLVER, ode_steps=ODE_STEPS)
+            bad += int(not torch.equal(ref_r, gather_buf[r]))
+        if bad:
+            raise SystemExit(f"multi-GPU check failed: {bad} of {world - 1} gathered slices differ from their single-GPU re-integration")
+        multi_check = {"slices_checked": world - 1, "bit_equal_to_single_gpu": True,
+                       "how": "rank 0 re-integrated every other rank's slice after the timed region and compared with the gathered tensor (torch.equal)"}
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res_pin.copy_(model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS), non_blocking=True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+
+    # ---- end to end through the public API: CPU noise, H2D of inputs, integration, D2H of the result ----
+    e2e_steps = max(1, min(args.steps, 3))
+    latency_ms = None
+    if world == 1:
+        mask_pin = mask_h.pin_memory()
+        res_pin = torch.empty(B, N_PART, FEATS).pin_memory()                            # the result lands in pinned host memory
+        res_pin.copy_(model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS))   # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()                                                        # one isolated call, nothing overlapped
+        res_pin.copy_(model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS))
+        torch.cuda.synchronize()
+        latency_ms = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res_pin.copy_(model.sample(B, mask=mask_pin, ode_solver=SOLVER, ode_steps=ODE_STEPS), non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_api = ("SetFlowMatchingLitModule.sample(n, mask=pinned) copied to a pinned host buffer (CPU noise draw, H2D, "
+                   "integration, D2H inside the timed region); back-to-back calls, the CPU draw of call k+1 overlaps the GPU work of call k")
+    else:
+        # N > 1: the product launcher on host inputs -- every rank draws its noise blocks, copies them and its mask slice
+        # to its GPU, integrates, the slices are gathered to rank 0 and copied into pinned host memory
+        mask_all = torch.cat([synth_masks(B, 9999 + r)[0] for r in range(world)])
+        if args.all_real:
+            mask_all = torch.ones_like(mask_all)
+        mask_all = mask_all.pin_memory()
+        torch.manual_seed(777)
+        generate_data_sharded(model, world * B, mask=mask_all, ode_solver=SOLVER, ode_steps=ODE_STEPS, noise="blocks")   # warm
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            generate_data_sharded(model, world * B, mask=mask_all, ode_solver=SOLVER, ode_steps=ODE_STEPS, noise="blocks")
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_api = ("particle_fm_b200.launch.generate_data_sharded(model, n, mask=host, noise='blocks'): per-rank CPU noise draw, "
+                   "H2D, integration, gather to rank 0, D2H into pinned host memory, all inside the timed region")
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te.item())
     h2d = B * N_PART * FEATS * 4 + B * N_PART * 4 + NFE * 32 * 4 + (ODE_STEPS - 1) * 4
     d2h = B * N_PART * FEATS * 4
+
+    # ---- all-real variant of the same kernel (the variant the roofline fraction is also quoted on) ----
+    all_real = None
+    if world == 1 and not args.all_real and args.precision == "bf16" and not args.no_all_real:
+        B_ar = 148 * 28
+        ones = torch.ones(B_ar, N_PART, 1, device=dev)
+        z_ar = torch.randn(B_ar, N_PART, FEATS, generator=torch.Generator().manual_seed(4243)).to(dev)
+        ms = []
+        for i in range(3):
+            flush.fill_(i)
+            cnf.decode(z_ar, None, ones, ode_solver=SOLVER, ode_steps=ODE_STEPS)
+            torch.cuda.synchronize()
+            ms.append(eng.last_kernel_ms())
+        k_ar = statistics.mean(ms[1:])
+        fl_ar = (B_ar * N_PART * FLOP_PER_PARTICLE + B_ar * FLOP_PER_JET) * NFE
+        all_real = {"jets": B_ar, "kernel_ms": k_ar, "jets_per_s": B_ar / (k_ar * 1e-3), "achieved": fl_ar / (k_ar * 1e-3) / 1e12}
+
+    # ---- the reference's own eager PyTorch arithmetic (oracle port) on this GPU: a GPU comparator for the speed-up ----
+    gpu_eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            gpu_eager = eager_gpu_leg(dev, 1024)
+        except Exception as e:                                   # reported, never fatal: it is a comparator only
+            gpu_eager = {"error": repr(e)[:200]}
 
     train = None
     if not args.no_train:
@@ -319,30 +409,41 @@ def main():
         flops = (float(n_real.sum()) * FLOP_PER_PARTICLE + B * FLOP_PER_JET) * NFE          # per launch, this rank
         k_ms = statistics.mean(kernel_ms)
         achieved = flops / (k_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if args.precision == "bf16" and os.path.exists(tpath):          # DRAM bytes of one ncu --set full capture, scaled per jet
             tj = json.load(open(tpath))["epic_tc_kernel"]
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["jets"] * B
+            traffic_source = (f"static: one ncu --set full capture ({tj.get('capture', 'profiles/')}, {tj['jets']} jets), "
+                              "scaled by jets per launch; not measured in this run")
         peak = peaks["tf_sustained"]
         line = {"metric": "generated_jets_per_s", "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "ode_steps": ODE_STEPS, "solver": SOLVER, "nfe": NFE,
+                "config": {"workload": WORKLOAD_ALL_REAL if args.all_real else WORKLOAD, "batch_per_gpu": B, "ode_steps": ODE_STEPS, "solver": SOLVER, "nfe": NFE,
                            "precision": args.precision, "mean_real_particles": float(n_real.float().mean()),
                            "all_real": bool(args.all_real), "l2": "flushed between timed steps (256 MB write)",
                            "parallelism": f"jets sharded x{world}, final gather to rank 0"},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "SetFlowMatchingLitModule.sample(n, mask=pinned) copied to a pinned host buffer (CPU noise draw, H2D, integration, D2H inside the timed region)"},
+                        "steps": e2e_steps, "api": e2e_api, "single_call_latency_ms": latency_ms},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": traffic,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                              "algorithmic_bytes_per_launch": B * (2 * N_PART * FEATS * 4 + N_PART * 4),
                              "kernel": "epic_tc_kernel" if args.precision == "bf16" else "epic_simt_kernel",
                              "kernel_ms": k_ms, "algorithmic_flop_per_launch": flops,
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)"}}
+        if all_real is not None:
+            line["roofline_all_real"] = {"frac": all_real["achieved"] / peak, "achieved": all_real["achieved"], "peak": peak,
+                                         "unit": "TFLOP/s", "jets_per_s": all_real["jets_per_s"], "jets": all_real["jets"],
+                                         "kernel_ms": all_real["kernel_ms"],
+                                         "workload": "same kernel, every jet 150 real particles (SURVEY 8d all-real variant)"}
+        if multi_check is not None:
+            line["multi_gpu_check"] = multi_check
+        if gpu_eager is not None:
+            line["reference_gpu_eager"] = gpu_eager
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:

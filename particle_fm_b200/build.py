@@ -25,6 +25,21 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libpfm_b200.so cannot be built (there is no CPU fallback)")
 
 
+OBJ_DIR = os.path.join(PKG, "_obj")          # git-ignored; objects are kept so that only changed translation units recompile
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+           [os.path.join(PKG, "..", "include", "pfm_b200.h")]
+
+
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in [src, *_headers()] if os.path.exists(d))
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -34,16 +49,19 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu -> lib/libpfm_b200.so when sources are newer than the library."""
+    """Compile csrc/*.cu -> lib/libpfm_b200.so; only translation units newer than their object are recompiled."""
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
     procs = []
-    for s in srcs:       # compile the translation units in parallel, then link
-        o = os.path.join(LIB_DIR, os.path.basename(s) + ".o")
+    for s in srcs:       # compile the stale translation units in parallel, then link
+        o = os.path.join(OBJ_DIR, os.path.basename(s) + ".o")
         objs.append(o)
+        if not force and not _obj_stale(s, o):
+            continue
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
@@ -51,11 +69,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose or p.returncode != 0:
             sys.stderr.write(out)
         if p.returncode != 0:
+            try:
+                os.remove(cmd[-1])
+            except OSError:
+                pass
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs]
     subprocess.run(link, check=True)
-    for o in objs:
-        os.remove(o)
     return LIB_PATH
 
 

@@ -936,21 +936,27 @@ int tc_pack_weights(pfm_epic* h, cudaStream_t st) {
   const size_t spk_bytes = (size_t)(c.layers + 1) * TC_SPK;
   const size_t bytes = img_bytes + spk_bytes;
   const size_t aux = sizeof(ImgSrc) * n_items + sizeof(SpkSrc) * spk.size();
+  bool upload = false;
   if (h->tc_bytes < bytes + aux) {
     if (h->tc_store) cudaFree(h->tc_store);
     h->tc_store = nullptr; h->tc_bytes = 0;
     PFM_CUDA_CHECK(cudaMalloc(&h->tc_store, bytes + aux));
     h->tc_bytes = bytes + aux;
+    upload = true;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(h->tc_store);
   ImgSrc* dsrc = reinterpret_cast<ImgSrc*>(base + bytes);
   SpkSrc* dspk = reinterpret_cast<SpkSrc*>(base + bytes + sizeof(ImgSrc) * n_items);
-  PFM_CUDA_CHECK(cudaMemcpyAsync(dsrc, src.data(), sizeof(ImgSrc) * n_items, cudaMemcpyHostToDevice, st));
-  PFM_CUDA_CHECK(cudaMemcpyAsync(dspk, spk.data(), sizeof(SpkSrc) * spk.size(), cudaMemcpyHostToDevice, st));
-  PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src / spk are host temporaries
+  if (upload) {      // the source tables only hold pointers into the handle's fp32 weight store: uploaded once per allocation,
+                     // so that a repack (every sample() re-syncs the weights) is two launches and never blocks the host
+    PFM_CUDA_CHECK(cudaMemcpyAsync(dsrc, src.data(), sizeof(ImgSrc) * n_items, cudaMemcpyHostToDevice, st));
+    PFM_CUDA_CHECK(cudaMemcpyAsync(dspk, spk.data(), sizeof(SpkSrc) * spk.size(), cudaMemcpyHostToDevice, st));
+    PFM_CUDA_CHECK(cudaStreamSynchronize(st));     // src / spk are host temporaries
+  }
   pack_images_kernel<<<n_items, 256, 0, st>>>(dsrc, base);
   pack_spk_kernel<<<c.layers + 1, 256, 0, st>>>(dspk, reinterpret_cast<SpkPack*>(base + img_bytes));
   PFM_CUDA_CHECK(cudaGetLastError());
+  h->tc_dirty = false;
   return PFM_OK;
 }
 
@@ -971,7 +977,7 @@ int tc_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
               "use PFM_PREC_FP32 or the sampling entry point, which hoists the time columns", a.Kx, TC_KXMAX);
     return PFM_ERR_UNSUPPORTED;
   }
-  if (!h->tc_store) { int rc = tc_pack_weights(h, st); if (rc != PFM_OK) return rc; }
+  if (!h->tc_store || h->tc_dirty) { int rc = tc_pack_weights(h, st); if (rc != PFM_OK) return rc; }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.F = c.feats; p.Kx = a.Kx; p.x_ld = a.Kx; p.xin_off = a.xin_off; p.Z = c.latent; p.L = c.layers; p.n_lin = h->n_lin;

@@ -284,11 +284,15 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
   const int cond_dim = c.global_cond_dim > c.local_cond_dim ? c.global_cond_dim : c.local_cond_dim;
   if (cond_dim > 0 && cond == nullptr) { set_error("cond is NULL but the net is conditioned"); return PFM_ERR_INVALID; }
   const bool any_t = (c.t_local_cat || c.t_global_cat) && c.t_dim > 0;
-  if ((any_t || t_in > 0) && t_code == nullptr && t_code_in == nullptr) {
+  if ((any_t && t_code == nullptr) || (t_in > 0 && t_code_in == nullptr)) {
     set_error("time code is NULL but the net takes a time code"); return PFM_ERR_INVALID;
   }
   cudaError_t e0 = cudaSetDevice(h->device);
   if (e0 != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e0)); return PFM_ERR_CUDA; }
+  // this call rewrites the handle-wide plan buffers (n_real, ridx, groups, counter): a pfm_epic_forward_train still waiting
+  // for its pfm_epic_backward is invalidated here, so that a stale backward fails with PFM_ERR_STATE instead of running
+  // on a foreign plan
+  h->train_B = 0;
   h->last_launches = 0;
   h->last_groups_host = 0;
   h->ev_used = 0;
@@ -538,7 +542,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->n_lin = 4 + 4 * c.layers + 1;
   h->precision = PFM_PREC_FP32;
   h->weights_set = false;
-  h->lin_dev = nullptr; h->wt_store = nullptr; h->b_store = nullptr; h->tc_store = nullptr; h->tc_bytes = 0;
+  h->lin_dev = nullptr; h->wt_store = nullptr; h->b_store = nullptr; h->tc_store = nullptr; h->tc_bytes = 0; h->tc_dirty = false;
   h->wn_rows = nullptr; h->wn_total_rows = 0; h->wn_goff = nullptr; h->wn_ptrs = nullptr;
   h->wr_store = nullptr; h->wr_floats = 0;
   h->act = nullptr; h->act_cap = 0; h->dact = nullptr; h->dact_cap = 0; h->yact = nullptr; h->yact_cap = 0;
@@ -665,6 +669,7 @@ int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* 
   }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
+  h->tc_dirty = true;
   if (h->precision == PFM_PREC_BF16) {
     int rc = tc_pack_weights(h, st);
     if (rc != PFM_OK) return rc;
@@ -777,6 +782,7 @@ int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* 
   wn_fold_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_ptrs, n);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
+  h->tc_dirty = true;
   if (h->precision == PFM_PREC_BF16) {
     rc = tc_pack_weights(h, st);
     if (rc != PFM_OK) return rc;
@@ -812,10 +818,9 @@ int pfm_epic_set_precision(pfm_epic* h, int precision) {
   }
   int old = h->precision;
   h->precision = precision;
-  if (precision == PFM_PREC_BF16 && h->weights_set && (old != precision || !h->tc_store)) {
-    int rc = tc_pack_weights(h, 0);
-    if (rc != PFM_OK) { h->precision = old; return rc; }
-  }
+  // The bf16 weight images are (re)packed lazily by the next forward / sample ON ITS OWN STREAM (tc_run packs when
+  // tc_store is NULL): packing here on the legacy stream would not be ordered against a non-blocking consumer stream.
+  (void)old;
   return PFM_OK;
 }
 

@@ -63,6 +63,7 @@ struct pfm_epic {
   int bstride;                      // floats per bias-table row
   // bf16 tensor-core path: pre-swizzled shared-memory images of the H x H per-particle weights
   void* tc_store;
+  bool tc_dirty;            // the fp32 weights changed after the bf16 images were packed: tc_run repacks on its own stream
   size_t tc_bytes;
   // workspaces (grown on demand)
   float* tbias; size_t tbias_cap;   // [rows, bstride]  b + W_t . time_code

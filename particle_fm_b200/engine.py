@@ -182,6 +182,7 @@ class EpicEngine:
         else:
             t_code = None
         out = torch.empty(B, N, d.feats, device=self.device, dtype=torch.float32)
+        self._ticket = getattr(self, "_ticket", 0) + 1      # the call rewrites the handle's plan: a pending backward() is stale
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pfm_epic_forward(self._h, _ptr(t_code), t_rows, _ptr(x), _ptr(mask), _ptr(cond),
                                                  _ptr(out), B, N, self._stream()), "pfm_epic_forward")
@@ -203,6 +204,7 @@ class EpicEngine:
             t_codes = _f32c(t_codes, self.device).reshape(n_evals, -1)
         if t_codes_in is not None:
             t_codes_in = _f32c(t_codes_in, self.device).reshape(n_evals, -1)
+        self._ticket = getattr(self, "_ticket", 0) + 1      # the call rewrites the handle's plan: a pending backward() is stale
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pfm_epic_sample(self._h, _ptr(x), _ptr(mask), _ptr(cond), _ptr(t_codes),
                                                 _ptr(t_codes_in), _ptr(dt), code, n_steps, B, N, self._stream()),

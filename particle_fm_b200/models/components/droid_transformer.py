@@ -375,7 +375,12 @@ class _DroidNet(nn.Module):
     def _weights_key(self):
         return tuple((p._version, p.data_ptr()) for p in self.parameters())
 
-    def engine(self, device=None, sync_weights: bool = True) -> _TfEngine:
+    def invalidate_weights(self):
+        """See EPiC_encoder.invalidate_weights: in-place ``.data`` updates are invisible to the change detector."""
+        for eng in self._engines.values():
+            eng.weights_key = None
+
+    def engine(self, device=None, sync_weights: bool = True, force_sync: bool = False) -> _TfEngine:
         p0 = next(self.parameters())
         device = torch.device(device) if device is not None else p0.device
         if device.type != "cuda":
@@ -392,7 +397,7 @@ class _DroidNet(nn.Module):
             eng.set_precision(self.precision)
         if sync_weights:
             key = self._weights_key()
-            if eng.weights_key != key:
+            if force_sync or eng.weights_key != key:
                 eng.set_weights(list(self.parameters()), key=key)
         return eng
 

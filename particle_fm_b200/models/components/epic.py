@@ -146,9 +146,19 @@ class EPiC_encoder(nn.Module):
     def _weights_key(self):
         return tuple((p._version, p.data_ptr()) for p in self.parameters())
 
-    def engine(self, device: Optional[torch.device] = None, sync_weights: bool = True) -> EpicEngine:
+    def invalidate_weights(self):
+        """Force the next engine() call to re-fold and repack the parameters.  The change detector below keys on
+        (``_version``, ``data_ptr``) of every parameter, which in-place updates through ``.data`` (``p.data.mul_()``,
+        manual EMA / clipping / re-initialisation) do NOT bump -- call this after such an update.  Sampling entry points
+        (``CNF.decode``) re-sync unconditionally, so only per-step forward / training callers need it."""
+        for eng in self._engines.values():
+            eng.weights_key = None
+
+    def engine(self, device: Optional[torch.device] = None, sync_weights: bool = True,
+               force_sync: bool = False) -> EpicEngine:
         """The packed copy of this network on ``device`` (default: where the parameters live), refreshed
-        whenever a parameter changed (optimizer step, EMA load_state_dict swap -- ema.py:145-159)."""
+        whenever a parameter changed (optimizer step, EMA load_state_dict swap -- ema.py:145-159) as far as
+        ``_version`` / ``data_ptr`` show it (see invalidate_weights), or unconditionally with ``force_sync``."""
         p0 = next(self.parameters())
         device = torch.device(device) if device is not None else p0.device
         if device.type != "cuda":
@@ -163,7 +173,7 @@ class EPiC_encoder(nn.Module):
             eng.set_precision(self.precision)
         if sync_weights:
             key = self._weights_key()
-            if eng.weights_key != key:
+            if force_sync or eng.weights_key != key:
                 eng.set_params(self.linears(), key=key)      # weight-norm fold + repack inside the library
         return eng
 

@@ -180,7 +180,9 @@ class CNF(nn.Module):
             if dkey not in cache:
                 cache[dkey] = (codes.to(z.device), dt.to(z.device))
             codes, dt = cache[dkey]
-        eng = self.net.engine()
+        # one fold + repack launch is negligible next to a whole integration: re-sync unconditionally, so that in-place
+        # parameter updates the (_version, data_ptr) key cannot see (p.data.mul_(), manual EMA) never sample stale weights
+        eng = self.net.engine(force_sync=True)
         takes = self.net.t_local_cat or self.net.t_global_cat
         return eng.sample(z, mask, cond, codes if takes else None, codes if self.add_time_to_input else None, dt,
                           ode_solver)
@@ -259,6 +261,21 @@ class SetFlowMatchingLitModule(_LightningBase):
             mask = None
         loss = self.loss(x, mask=mask, cond=cond)
         self.log("train/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        # per-jet-type losses every 20 epochs (flow_matching_module.py:526-551, JetClass-cond datamodule option); the extra
+        # loss calls consume the RNG streams exactly like the reference's (rand(B) on the CPU, randn_like on the device)
+        dm = getattr(getattr(self, "trainer", None), "datamodule", None)
+        if dm is not None and self.current_epoch % 20 == 0 and hasattr(dm.hparams, "loss_per_jettype"):
+            if dm.hparams.loss_per_jettype:
+                names = list(dm.names_conditioning)
+                for jet_type in dm.hparams.used_jet_types:
+                    sel = cond[:, names.index(f"jet_type_label_{jet_type}")] == 1
+                    x_t, m_t, c_t = x[sel][:10_000], mask[sel][:10_000], cond[sel][:10_000]
+                    if x_t.shape[0] == 0:              # the reference divides 0 by 0 here
+                        loss_t = torch.full((), float("nan"), device=x.device)
+                    else:
+                        with torch.no_grad():          # logging only: the reference never back-propagates these
+                            loss_t = self.loss(x_t, m_t, cond=c_t)
+                    self.log(f"train/loss_{jet_type}", loss_t, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
         return {"loss": loss}
 
     def on_validation_epoch_start(self) -> None:

@@ -171,3 +171,93 @@ def test_weight_norm_fold_and_chain_rule_in_the_library():
         else:
             assert dg is None and rel_l2(dv.cpu(), (gw.view_as(dv) * scale).cpu()) < 1e-6
         assert rel_l2(db.cpu(), (gb * scale).cpu()) < 1e-6
+
+
+def test_stale_backward_after_inference_call_raises():
+    """ADVICE r1: an inference forward / sample() between forward_train and backward rewrites the handle's plan buffers;
+    the pending backward must fail (ticket + PFM_ERR_STATE) instead of running on a foreign plan."""
+    g = Golden("c1_jetnet30")
+    m = build_module(g.ctor, g.sd, device=DEV)
+    B, N = g.x.shape[:2]
+    t = torch.rand(B, generator=torch.Generator().manual_seed(3)).unsqueeze(-1).repeat_interleave(N, dim=1)
+    xd = g.x.to(DEV).requires_grad_(True)
+    v = m.flows[0](t.to(DEV), xd, cond=None, mask=g.mask.to(DEV))            # generic autograd path: forward_train
+    other_mask = torch.ones_like(g.mask)
+    other_mask[:, 7:] = 0
+    with torch.no_grad():                                                     # inference call with a different mask
+        m.flows[0](torch.tensor(0.3, device=DEV), g.x.to(DEV) * other_mask.to(DEV), cond=None, mask=other_mask.to(DEV))
+    with pytest.raises(RuntimeError, match="overwritten|forward_train|PFM"):
+        v.sum().backward()
+    # and directly at the C ABI: the handle itself refuses (train_B was reset by the inference call)
+    eng = m.flows[0].net.engine()
+    code = m.flows[0].time_code(t[:, 0])
+    out, ticket, saved = eng.forward_train(code.to(DEV), g.x.to(DEV), g.mask.to(DEV), None)
+    eng.forward(code[:1].to(DEV), g.x.to(DEV), other_mask.to(DEV), None)
+    eng._ticket = ticket                                                      # defeat the Python-side guard
+    with pytest.raises(Exception, match="no matching pfm_epic_forward_train"):
+        eng.backward(ticket, saved, torch.ones_like(out), True, True)
+
+
+def test_in_place_data_updates_reach_the_sampler():
+    """p.data.mul_() bumps neither _version nor data_ptr; decode() re-syncs unconditionally and
+    invalidate_weights() covers the per-step forward."""
+    g = Golden("c1_jetnet30")
+    m = build_module(g.ctor, g.sd, device=DEV)
+    z = (g.t("z_euler100") * g.mask).to(DEV)
+    mask = g.mask.to(DEV)
+    a = m.flows[0].decode(z, None, mask, "euler", 5)
+    with torch.no_grad():
+        for p in m.flows[0].net.fc_l3.parameters():
+            p.data.mul_(0.5)
+    b = m.flows[0].decode(z, None, mask, "euler", 5)
+    assert not torch.equal(a, b), "sample() used stale packed weights after an in-place .data update"
+    sd2 = {k[len("flows.0.net."):]: v.detach().cpu() for k, v in m.state_dict().items() if k.startswith("flows.0.net.")}
+    ref = lo.sample(g.oracle_vf(sd=sd2), z.cpu(), g.mask, "euler", 5)
+    assert rel_l2(b.cpu(), ref) < 1e-4
+    t = torch.tensor(0.5, device=DEV)
+    with torch.no_grad():
+        v1 = m.flows[0](t, z, cond=None, mask=mask)
+        for p in m.flows[0].net.fc_l3.parameters():
+            p.data.mul_(2.0)
+        m.flows[0].net.invalidate_weights()
+        v2 = m.flows[0](t, z, cond=None, mask=mask)
+    assert not torch.equal(v1, v2)
+
+
+def test_training_step_loss_per_jettype_branch():
+    """flow_matching_module.py:526-551: with datamodule.hparams.loss_per_jettype the step logs one extra loss per jet type
+    on the slice of that type, consuming the RNG streams like the reference's extra self.loss(...) calls."""
+    import types
+    g = Golden("cond_jetclass_like")
+    m = build_module(g.ctor, g.sd, loss_type="FM-OT", device=DEV)
+    B = g.x.shape[0]
+    C = g.cond.shape[1]
+    cond = g.cond.clone()
+    cond[:, 0] = (torch.arange(B) % 2 == 0).float()                          # one-hot jet-type labels in columns 0 / 1
+    cond[:, 1] = 1 - cond[:, 0]
+    names = ["jet_type_label_A", "jet_type_label_B"] + [f"c{i}" for i in range(C - 2)]
+    dm = types.SimpleNamespace(hparams=types.SimpleNamespace(variable_jet_sizes=True, loss_per_jettype=True,
+                                                             used_jet_types=["A", "B"]), names_conditioning=names)
+    m.trainer = types.SimpleNamespace(datamodule=dm)
+    logged = {}
+    m.log = lambda name, value, **kw: logged.__setitem__(name, value)
+    x, mask = (g.x * 5.0 * g.mask).to(DEV), g.mask.to(DEV)
+    torch.manual_seed(21)
+    out = m.training_step((x, mask, cond.to(DEV)), 0)
+    assert set(logged) == {"train/loss", "train/loss_A", "train/loss_B"}
+    # the same sequence of draws replayed against the oracle
+    torch.manual_seed(21)
+    refs = {}
+    for name, sel in (("train/loss", torch.ones(B, dtype=torch.bool)), ("train/loss_A", cond[:, 0] == 1), ("train/loss_B", cond[:, 1] == 1)):
+        xs = x[sel.to(DEV)]
+        t = torch.rand_like(torch.ones(xs.shape[0]))
+        n0 = torch.randn_like(xs)
+        vf = g.oracle_vf(cond=cond[sel], mask=g.mask[sel])
+        refs[name] = float(lo.fm_loss(vf, "FM-OT", xs.cpu(), g.mask[sel], t, n0.cpu(), None, 1e-4))
+    for k, r in refs.items():
+        assert abs(float(logged[k]) - r) <= 1e-5 * abs(r), (k, float(logged[k]), r)
+    assert out["loss"].requires_grad and not logged["train/loss_A"].requires_grad
+    m.current_epoch = 3                                                       # not a multiple of 20: branch off
+    logged.clear()
+    m.training_step((x, mask, cond.to(DEV)), 0)
+    assert set(logged) == {"train/loss"}

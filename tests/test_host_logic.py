@@ -112,3 +112,22 @@ def test_generate_data_batching_and_postprocessing():
         generate_data(Fake(), 7, variable_set_sizes=True, mask=None, device="cpu")
     with pytest.raises(ValueError):
         generate_data(Fake(), 6, mask=mask, device="cpu")
+
+
+def test_block_noise_is_independent_of_the_partition():
+    """launch.block_noise: the rows a rank draws for its slice equal the same rows of the whole request, whatever the
+    world size (fixed-size blocks with their own seeds), so noise="blocks" results do not depend on the GPU count."""
+    from particle_fm_b200.launch import block_noise, shard_bounds
+    from particle_fm_b200.launch import generate as gen
+    old = gen.NOISE_BLOCK
+    gen.NOISE_BLOCK = 8
+    try:
+        n, N, F, seed = 37, 5, 3, 123456789
+        whole = block_noise(0, n, N, F, seed)
+        assert whole.shape == (n, N, F) and float(whole.std()) > 0.5
+        for world in (1, 2, 3, 8):
+            parts = [block_noise(*shard_bounds(n, world, r), N, F, seed) for r in range(world)]
+            assert torch.equal(torch.cat(parts), whole)
+        assert not torch.equal(block_noise(0, n, N, F, seed + 1), whole)
+    finally:
+        gen.NOISE_BLOCK = old
