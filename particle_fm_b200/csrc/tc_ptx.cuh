@@ -198,6 +198,36 @@ __device__ __forceinline__ void sts128_if(uint32_t addr, uint32_t x, uint32_t y,
       : "memory");
 }
 
+// ---------------------------------------------------------------- warp-level MMA (mma.sync, HMMA.16816.F32.BF16) + ldmatrix
+// Used for the small per-jet chain (masked pooling, global MLP, bias re-injection): M = 16 jets is one fragment row block.
+// Fragment layouts (g = lane >> 2, t = lane & 3):  A(16x16, row): a0 (g, 2t..2t+1) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..)
+//   B(16x8, col): b0 (k 2t..2t+1, n g)  b1 (k 2t+8.., n g)     C/D(16x8): c0,c1 (g, 2t..2t+1)  c2,c3 (g+8, 2t..2t+1)
+__device__ __forceinline__ void hmma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3); register i <- matrix i
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts64_if(uint32_t addr, float x, float y, bool pred) {
+  if (pred) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts32_if(uint32_t addr, uint32_t x, bool pred) {
+  if (pred) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 // pack two fp32 into bf16x2 (round to nearest even): low half = a, high half = b
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
