@@ -13,16 +13,19 @@
 // The per-jet chain between them -- masked mean/sum pooling, fc_global1 (2H+Z -> H), fc_global2 (H -> Z, residual),
 // re-injection of the global vector as a per-jet bias of fc_local1 -- runs on the EPILOGUE warps with warp-level
 // mma.sync (M = 16 jets is exactly one fragment row block), so that it needs no round trip through the tcgen05 pipe:
-//   pooling      S[jet][c] = sum_rows P[jet][row] h[row][c]: every warp reduces its own 32 rows right after it stored them
-//                (A = 0/1 indicator fragments built once per group, B = ldmatrix.trans of the swizzled h tile); the partial
-//                sums go to a slot per (warp, jet) pair and are added in a fixed order (deterministic, no atomics)
-//   fc_global1   [16 jets x 272] . [272 x 128]: warp w owns 16 outputs; B fragments come straight out of the ring images
-//   fc_global2   [16 x 128] . [128 x 16], every warp redundantly (the result stays in registers: no exchange)
-//   re-injection [16 x 16] . [16 x 128]: A fragment = the new global vector, converted in registers
+// all in the "transposed" orientation D^T[feature][jet] (M = 16 features, N = 8 jets per fragment: a typical group has 3-4
+// jets, so one N tile; groups with 9..16 jets take a second one):
+//   pooling      S^T[c][jet] = sum_rows h[row][c] P[jet][row]: warp w owns columns 16w..16w+15 and reduces over all rows of
+//                the group (A = ldmatrix.trans of the swizzled h tiles, B = the 0/1 indicator matrix P) -> complete sums in
+//                one warp, deterministic, scaled (mean, sum) and written as the bf16 operand St of fc_global1
+//   fc_global1   [16 outputs of warp w x 272] . [272 x jets]: A fragments come straight out of the ring images
+//   fc_global2   [16 z x 128] . [128 x jets], every warp redundantly (the result stays in registers: no exchange)
+//   re-injection [16 outputs x 16 z] . [16 z x jets]: B fragment = the new global vector, transposed with movmatrix
 // (Round 1 ran pooling and fc_global1 as N = 16 tcgen05 MMAs and the rest as CUDA-core GEMVs: four dependent hops through
 // mbarriers / TMEM per layer, ~4 k of the ~9 k cycles of a layer.)
-// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one lane), warps 2-5 / 6-9 = epilogue
-// warpgroups of tile A / tile B (TMEM lane quadrant = warp % 4).
+// Warp roles: warps 0 and 10 = weight producers (one thread sustains only one cp.async.bulk per ~690 cycles whatever its size
+// -- tools/bulk_probe.cu -- so the ring is fed by two warps, even / odd items), warp 1 = MMA issuer (one lane),
+// warps 2-5 / 6-9 = epilogue warpgroups of tile A / tile B (TMEM lane quadrant = warp % 4).
 #include <cstdlib>
 
 #include "pfm_internal.cuh"
@@ -51,16 +54,15 @@ struct SpkPack {
 static constexpr uint32_t TC_SPK = sizeof(SpkPack);
 static_assert(sizeof(SpkPack) % 16 == 0, "bulk copies move multiples of 16 bytes");
 static constexpr int TC_SBIAS = 384 + 16;               // one unit's slice of the time-bias table
-static constexpr int TC_THREADS = 320;
+static constexpr int TC_THREADS = 352;
 static constexpr int TC_NSLOT = 3;
 static constexpr uint32_t TC_MAT = 32768;   // one 128x128 bf16 weight image
-static constexpr int TC_PAIRS = 24;         // (32-row block, jet) pairs of a group: jets are contiguous, so at most 16 + 8 - 1
 
 template <int FP>
 struct TcSmem {
   alignas(1024) uint8_t h[2][TC_MAT];          // bf16 h tiles
   alignas(1024) uint8_t w[TC_NSLOT][TC_MAT];   // weight ring
-  alignas(16) float Spart[TC_PAIRS][TCH];      // pooled partial sums: slot (jet + 32-row block) <- that block's rows of the jet
+  alignas(16) __nv_bfloat16 P[TC_J][TC_ST_LD]; // 0/1 indicator P[jet][row] of the group (B operand of the pooling)
   union alignas(16) {
     __nv_bfloat16 St[TC_J][TC_ST_LD];          // A operand of fc_global1: [jet][mean | sum], dead once fc_global1 is done ->
     float bl1[TC_J][TCH];                      //  reused for the per-jet bias of fc_local1 (b + W_t . t + W_glob . g)
@@ -71,7 +73,7 @@ struct TcSmem {
   alignas(16) float w1s[TCH][FP];              // fc_l1 weights of the particle features, [column][feature]
   alignas(16) float w3s[TCH][FP];              // fc_l3 (k-major)
   alignas(16) SpkPack spk;                     // small weights of the current unit
-  alignas(16) float sbias[TC_SBIAS];           // time-bias slice of the current unit (4 consecutive linears)
+  alignas(16) float sbias[2][TC_SBIAS];        // time-bias slice of the current / next unit (4 consecutive linears), cp.async by the epilogue warps
   float inv_n[TC_J];
   int boff[128];                               // bias-table offset of every linear (copied once: no global descriptor loads in the loop)
   int jrow0[TC_J + 1];
@@ -79,8 +81,9 @@ struct TcSmem {
   int group;
   uint32_t tmem_base;
   uint64_t full[TC_NSLOT], empty[TC_NSLOT];
-  uint64_t hready[2], accU_full[2], u_ready[2][2], accH_full[2];      // u_ready[tile][half of the 128 u columns]
+  uint64_t hready[2][4], accU_full[2], u_ready[2][2], accH_full[2];   // hready[tile][32-column chunk of h], u_ready[tile][half of the 128 u columns]
   uint64_t spk_full, spk_empty;
+  uint32_t issued[2];                          // ring positions issued so far by the even / odd producer warp (+1)
 };
 
 static_assert(sizeof(TcSmem<8>) + 1024 <= 232448, "TcSmem exceeds the 227 KB per-block shared-memory limit of sm_100");
@@ -172,10 +175,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s.hready[t], 128); mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t][0], 128); mbar_init(&s.u_ready[t][1], 128);
+      for (int c = 0; c < 4; ++c) mbar_init(&s.hready[t][c], 128);
+      mbar_init(&s.accU_full[t], 1); mbar_init(&s.u_ready[t][0], 128); mbar_init(&s.u_ready[t][1], 128);
       mbar_init(&s.accH_full[t], 1);
     }
     mbar_init(&s.spk_full, 1); mbar_init(&s.spk_empty, 256);
+    s.issued[0] = 0; s.issued[1] = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&s.tmem_base, 512);
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
 
   // running use counters of every barrier (parity = count & 1); each role only advances the ones it uses
   uint32_t ring_it = 0;                                     // producer / MMA: weight items consumed so far
-  uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0};      // MMA side
+  uint32_t c_hready[2] = {0, 0}, c_uready[2] = {0, 0};      // MMA side (one count per tile: its four chunk barriers advance together)
   uint32_t ring_e = 0;                                      // epilogue: mirror of the weight-ring position (it reads the fc_global1 images)
   uint32_t c_accH = 0, c_accU = 0, c_spk = 0;               // epilogue side
   uint32_t spk_it = 0;                                      // producer: small-weight packs issued so far
@@ -215,32 +220,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
     const int2 grp = p.groups[gidx];
     const int j0 = grp.x, nj = grp.y;
 
-    if (warp == 0) {
-      // ================================ weight producer (whole warp, elected lane issues) ================================
+    if (warp == 0 || warp == 10) {
+      // ================================ weight producers (whole warp, elected lane issues) ================================
       // ring order per evaluation:  stem  fc_l2 | fc_g1 mean | fc_g1 sum     layer l  fc_local1 | fc_global1 mean | sum | fc_local2
-      const bool stage_bias = !p.tbias_per_jet;
-      const uint32_t bias_bytes = stage_bias ? (uint32_t)p.bias_chunk_floats * 4u : 0u;
+      // warp 0 issues the even ring positions, warp 10 the odd ones and the small-weight packs
+      const uint32_t mine = warp == 0 ? 0u : 1u;
       for (int ev = 0; ev < p.n_evals; ++ev) {
         for (int it = 0; it < p.n_items; ++it, ++ring_it) {
-          // the small-weight pack + bias slice of unit u travel just before the unit's first image
-          const int u = it == 1 ? 0 : ((it >= 3 && ((it - 3) & 3) == 0) ? 1 + ((it - 3) >> 2) : -1);
-          if (u >= 0) {
+          // the small-weight pack of unit u travels just before the unit's fc_global1 images (after the layer's fc_local1 image,
+          // which is needed much earlier: fc_local1 runs under the residual epilogue, before the previous unit's chain has ended)
+          const int u = it == 1 ? 0 : ((it >= 4 && ((it - 4) & 3) == 0) ? 1 + ((it - 4) >> 2) : -1);
+          if (u >= 0 && mine == 1u) {
             mbar_wait(&s.spk_empty, (spk_it & 1) ^ 1);
             ++spk_it;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&s.spk_full, TC_SPK + bias_bytes);
+              mbar_arrive_expect_tx(&s.spk_full, TC_SPK);
               bulk_copy_g2s(&s.spk, p.spk + (size_t)u * TC_SPK, TC_SPK, &s.spk_full);
-              if (stage_bias)
-                bulk_copy_g2s(s.sbias, p.tbias + (size_t)ev * p.bstride + (u == 0 ? p.boff_stem : p.boff_layer0 + (u - 1) * p.boff_layer_stride),
-                              bias_bytes, &s.spk_full);
             }
             __syncwarp();
           }
+          if ((ring_it & 1u) != mine) continue;
           const uint32_t slot = ring_it % TC_NSLOT, round = ring_it / TC_NSLOT;
+          // The parity test below is only valid while this warp is at most one phase ahead of the slot's barrier.  The slot's
+          // previous user (ring position - 3) belongs to the OTHER producer: wait until it has been issued (its own wait
+          // proved the phase before that complete).
+          if (ring_it >= 3u) {
+            uint32_t seen;
+            do {
+              asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&s.issued[mine ^ 1u])) : "memory");
+            } while (seen < ring_it - 2u);
+          }
           mbar_wait(&s.empty[slot], (round & 1) ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&s.full[slot], TC_MAT);
             bulk_copy_g2s(s.w[slot], p.wimg + (size_t)it * TC_MAT, TC_MAT, &s.full[slot]);
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s.issued[mine])), "r"(ring_it + 1u) : "memory");
           }
           __syncwarp();
         }
@@ -254,17 +268,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       auto wait_full = [&](uint32_t it) { mbar_wait(&s.full[it % TC_NSLOT], (it / TC_NSLOT) & 1); };
       auto wslot = [&](uint32_t it) { return wdesc0 + (uint64_t)((it % TC_NSLOT) * (TC_MAT >> 4)); };
       for (int ev = 0; ev < p.n_evals; ++ev) {
-        // ---- stem fc_l2: accH[t] (holds h1) += h1 . W_l2^T
+        // ---- stem fc_l2: accH[t] (holds h1) += h1 . W_l2^T.  Every version of h is handed over in four 32-column chunks
+        // (two K steps each); the stem arrives on all four at once (its TMEM stores must be complete before the first MMA
+        // accumulates onto them), the layers chunk by chunk so that fc_local1 runs WHILE the residual epilogue still works.
         const uint32_t it_l2 = ring_it++;
-        for (int t = 0; t < 2; ++t) {
-          PROF_T(0);
-          mbar_wait(&s.hready[t], c_hready[t]++ & 1);
-          tc_fence_after();
-          PROF_T(1);
-          if (t == 0) wait_full(it_l2);
-          PROF_T(2);
-          issue_ss_128(t ? accH1 : accH0, t ? hB : hA, wslot(it_l2), idesc, true);
-          commit_to(&s.accH_full[t]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            PROF_T(0);
+            mbar_wait(&s.hready[t][c], c_hready[t] & 1);
+            tc_fence_after();
+            PROF_T(1);
+            if (t == 0 && c == 0) wait_full(it_l2);
+            PROF_T(2);
+            const uint64_t ad = t ? hB : hA, wd = wslot(it_l2);
+            if (elect_one()) {
+              mma_ss(t ? accH1 : accH0, ad + kstep16(2 * c), wd + kstep16(2 * c), idesc, 1u);
+              mma_ss(t ? accH1 : accH0, ad + kstep16(2 * c + 1), wd + kstep16(2 * c + 1), idesc, 1u);
+            }
+            __syncwarp();
+            if (c == 3) { commit_to(&s.accH_full[t]); ++c_hready[t]; }
+          }
         }
         commit_to(&s.empty[it_l2 % TC_NSLOT]);
         ring_it += 2;                                  // fc_g1 images: read (and released) by the epilogue warps
@@ -272,17 +297,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           const uint32_t it_w1 = ring_it++;
           ring_it += 2;                                // fc_global1 images
           const uint32_t it_w2 = ring_it++;
-          // ---- fc_local1: accU[t] = h_l . W1^T as soon as the tile's new h is in shared memory; its result is only needed
-          // once the per-jet chain has produced the bias, so these MMAs hide under the chain
-          for (int t = 0; t < 2; ++t) {
-            PROF_T(0);
-            mbar_wait(&s.hready[t], c_hready[t]++ & 1);
-            tc_fence_after();
-            PROF_T(3);
-            if (t == 0) wait_full(it_w1);
-            PROF_T(4);
-            issue_ss_128(t ? accU1 : accU0, t ? hB : hA, wslot(it_w1), idesc, false);
-            commit_to(&s.accU_full[t]);
+          // ---- fc_local1: accU[t] = h_l . W1^T, two K steps per 32-column chunk of h as the residual epilogue stores them:
+          // the GEMM runs under the (ALU-bound) epilogue, so the tensor pipe is free for the mma.sync of the per-jet chain
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              PROF_T(0);
+              mbar_wait(&s.hready[t][c], c_hready[t] & 1);
+              tc_fence_after();
+              PROF_T(3);
+              if (t == 0 && c == 0) wait_full(it_w1);
+              PROF_T(4);
+              const uint64_t ad = t ? hB : hA, wd = wslot(it_w1);
+              if (elect_one()) {
+                mma_ss(t ? accU1 : accU0, ad + kstep16(2 * c), wd + kstep16(2 * c), idesc, c ? 1u : 0u);
+                mma_ss(t ? accU1 : accU0, ad + kstep16(2 * c + 1), wd + kstep16(2 * c + 1), idesc, 1u);
+              }
+              __syncwarp();
+              if (c == 3) { commit_to(&s.accU_full[t]); ++c_hready[t]; }
+            }
           }
           commit_to(&s.empty[it_w1 % TC_NSLOT]);
           // ---- fc_local2: accH[t] += u[t] (bf16 in TMEM) . W2^T.  The fc_local1 epilogue hands over u in two halves of 64
@@ -317,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const int q = warp & 3;                    // TMEM lane quadrant this warp may access
       const int r = q * 32 + lane;               // row in tile = TMEM lane
       const int row = wg * 128 + r;
-      const int w8 = wg * 4 + q;                 // 32-row block of the group owned by this warp
+      const int w8 = wg * 4 + q;                 // this warp's slice of the per-jet chain: features 16 w8 .. 16 w8 + 15
       const int g8 = lane >> 2, t4 = lane & 3;   // mma.sync fragment coordinates
       const uint32_t lane_base = tm + ((uint32_t)(q * 32) << 16);
       const uint32_t accH = lane_base + wg * 128, accU = lane_base + 256 + wg * 128;
@@ -337,8 +371,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       }
       // h = 0: rows without a particle are never written afterwards, so they stay finite (0) in every operand the
       // pooling fragments read; their TMEM lanes hold finite junk that no real row ever sees.  The per-jet operand
-      // arrays are zeroed once so that the fragment rows of jets the group does not have hold finite values too.
+      // arrays are zeroed once so that the fragment columns of jets the group does not have hold finite values too.
       for (int i = et; i < 2 * (int)TC_MAT / 16; i += 256) reinterpret_cast<uint4*>(&s.h[0][0])[i] = make_uint4(0, 0, 0, 0);
+      for (int i = et; i < (int)sizeof(s.P) / 16; i += 256) reinterpret_cast<uint4*>(&s.P[0][0])[i] = make_uint4(0, 0, 0, 0);
       for (int i = et; i < (int)sizeof(s.sb) / 16; i += 256) reinterpret_cast<uint4*>(&s.sb)[i] = make_uint4(0, 0, 0, 0);
       for (int i = et; i < (int)sizeof(s.g1) / 16; i += 256) reinterpret_cast<uint4*>(&s.g1[0][0])[i] = make_uint4(0, 0, 0, 0);
       for (int i = et; i < (int)sizeof(s.Sg) / 16; i += 256) reinterpret_cast<uint4*>(&s.Sg[0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -348,30 +383,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       int myjet = 0;
       for (int j = 1; j < nj; ++j) myjet += (row >= s.jrow0[j]) ? 1 : 0;
       if (!valid) myjet = 0;
+      if (valid) s.P[myjet][row] = __float2bfloat16(1.0f);
       const int jg = s.jid[myjet];
-      // pooling A fragments: 0/1 indicators P[jet][row] of this warp's 32 rows (two K = 16 steps), and which of this lane's
-      // two fragment rows (jets g8, g8 + 8) have particles in the warp's rows at all
-      uint32_t ind[2][4];
-      {
-        auto in_jet = [&](int j, int rr) -> uint32_t { return (rr >= s.jrow0[j] && rr < s.jrow0[j + 1]) ? 0x3F80u : 0u; };   // bf16 1.0
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const int rb = w8 * 32 + kk * 16 + 2 * t4;
-          ind[kk][0] = in_jet(g8, rb) | (in_jet(g8, rb + 1) << 16);
-          ind[kk][1] = in_jet(g8 + 8, rb) | (in_jet(g8 + 8, rb + 1) << 16);
-          ind[kk][2] = in_jet(g8, rb + 8) | (in_jet(g8, rb + 9) << 16);
-          ind[kk][3] = in_jet(g8 + 8, rb + 8) | (in_jet(g8 + 8, rb + 9) << 16);
-        }
-      }
-      const bool pres_lo = s.jrow0[g8] < w8 * 32 + 32 && s.jrow0[g8 + 1] > w8 * 32;
-      const bool pres_hi = s.jrow0[g8 + 8] < w8 * 32 + 32 && s.jrow0[g8 + 9] > w8 * 32;
-      const bool jet_lo = g8 < nj, jet_hi = g8 + 8 < nj;         // fragment rows that are jets of this group
-      const int jg_lo = s.jid[g8], jg_hi = s.jid[g8 + 8];
+      const int NB = (nj + 7) >> 3;              // 8-jet fragment column blocks of the per-jet chain (1 or 2)
+      const int pool_ks = (R + 15) >> 4;         // 16-row K steps of the pooling that hold particles
       // bias of a linear of the CURRENT unit: staged slice of the time table (+ per-jet cond table), or the
       // slow direct path when every jet has its own time (training-style forward)
+      // time-bias slices: unit k of the running count lives in sbias[k & 1]; the epilogue threads fetch the next unit's slice
+      // with cp.async while the current unit runs
+      const bool stage_bias = !p.tbias_per_jet;
+      const int bias_n16 = (p.bias_chunk_floats * 4 + 15) >> 4;
+      uint32_t c_unit = 0;                       // units completed so far by this CTA (selects the sbias buffer)
+      auto fetch_bias = [&](int ev_, int u_, uint32_t buf) {
+        if (stage_bias && et < bias_n16) {
+          const float* src = p.tbias + (size_t)ev_ * p.bstride + (u_ == 0 ? p.boff_stem : p.boff_layer0 + (u_ - 1) * p.boff_layer_stride) + et * 4;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.sbias[buf][et * 4])), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      const float* sbias_cur = &s.sbias[0][0];
       auto unit_bias = [&](int lin_idx, int voff, int jet_global, int o) -> float {
-        if (SIMPLE) return s.sbias[voff + o];
-        float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o] : s.sbias[voff + o];
+        if (SIMPLE) return sbias_cur[voff + o];
+        float b = p.tbias_per_jet ? p.tbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o] : sbias_cur[voff + o];
         if (p.cbias) b += p.cbias[(size_t)jet_global * p.bstride + s.boff[lin_idx] + o];
         return b;
       };
@@ -392,24 +425,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
       const unsigned long long slope2 = ((unsigned long long)__float_as_uint(p.slope) << 32) | __float_as_uint(p.slope);
       const int ZP = (Z + 3) & ~3;
       const uint32_t w3_addr = smem_u32(&s.w3s[0][0]);
-      // per-lane ldmatrix row addresses (see tc_ptx.cuh for the fragment layouts)
-      const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;            // A operands [jet][k]: matrices (rows 0-7 | 8-15) x (k lo | hi)
-      const int akh = lane >> 4;
-      const int brow = (lane & 7) + (lane >> 4) * 8;                  // B operands [n][k]: matrices (n 0-7, k lo | hi), (n 8-15, k lo | hi)
-      const int bkh = (lane >> 3) & 1;
-      const int o_b = w8 * 16 + brow;                                 // this warp's 16 outputs of fc_global1 / the re-injection
-      const uint32_t st_lane = smem_u32(&s.sb.St[0][0]) + (uint32_t)(arow * TC_ST_LD * 2 + akh * 16);
-      const uint32_t sg_lane = smem_u32(&s.Sg[0][0]) + (uint32_t)(arow * TC_GG_LD * 2 + akh * 16);
-      const uint32_t g1_lane = smem_u32(&s.g1[0][0]) + (uint32_t)(arow * TC_G2_LD * 2 + akh * 16);
-      const uint32_t wg2_lane = smem_u32(&s.spk.g2[0][0]) + (uint32_t)(brow * TC_G2_LD * 2 + bkh * 16);
-      const uint32_t wgg_lane = smem_u32(&s.spk.gg[0][0]) + (uint32_t)(o_b * TC_GG_LD * 2 + bkh * 16);
-      const uint32_t wgl_lane = smem_u32(&s.spk.gl[0][0]) + (uint32_t)(o_b * TC_GG_LD * 2 + bkh * 16);
-      const uint32_t img_row = (uint32_t)((o_b >> 3) * 1024 + (o_b & 7) * 128);     // row o_b of a K-major SW128 image
-      const uint32_t img_swz = (uint32_t)(o_b & 7);
-      // pooling B operand: this warp's rows of the h tile through ldmatrix.trans; matrices (rows lo | hi) x (8-column unit lo | hi)
-      const uint32_t pool_lane = smem_u32(s.h[wg]) + (uint32_t)((q * 4 + ((lane >> 3) & 1)) * 1024 + (lane & 7) * 128);
-      const uint32_t pool_swz = (uint32_t)(lane & 7), pool_cu = (uint32_t)(lane >> 4);
-      const uint32_t spart_lane = smem_u32(&s.Spart[0][0]) + (uint32_t)(((g8 + w8) * TCH + 2 * t4) * 4);
+      // ---- per-lane ldmatrix row addresses (fragment layouts: tc_ptx.cuh).  The chain runs transposed: M = 16 features.
+      //  A operands [m][k] row-major (weights): matrices (m lo, k lo) (m hi, k lo) (m lo, k hi) (m hi, k hi)
+      //  B operands [n = jet][k] row-major, one 8-jet block, TWO K steps per x4: matrices (k0 lo) (k0 hi) (k1 lo) (k1 hi)
+      const int l7 = lane & 7, mi = lane >> 3;
+      const int a_m = l7 + (mi & 1) * 8, a_kh = mi >> 1;
+      const int o_a = w8 * 16 + a_m;                                  // this lane's weight row in fc_global1 / the re-injection
+      const uint32_t img_row = (uint32_t)((o_a >> 3) * 1024 + (o_a & 7) * 128);     // row o_a of a K-major SW128 image
+      const uint32_t img_swz = (uint32_t)(o_a & 7);
+      const uint32_t wgg_lane = smem_u32(&s.spk.gg[0][0]) + (uint32_t)(o_a * TC_GG_LD * 2 + a_kh * 16);
+      const uint32_t wgl_lane = smem_u32(&s.spk.gl[0][0]) + (uint32_t)(o_a * TC_GG_LD * 2 + a_kh * 16);
+      const uint32_t wg2_lane = smem_u32(&s.spk.g2[0][0]) + (uint32_t)(a_m * TC_G2_LD * 2 + a_kh * 16);
+      const uint32_t st_lane = smem_u32(&s.sb.St[0][0]) + (uint32_t)(l7 * TC_ST_LD * 2 + mi * 16);
+      const uint32_t p_lane = smem_u32(&s.P[0][0]) + (uint32_t)(l7 * TC_ST_LD * 2 + mi * 16);
+      const uint32_t g1_lane = smem_u32(&s.g1[0][0]) + (uint32_t)(l7 * TC_G2_LD * 2 + mi * 16);
+      const uint32_t sg_lane = smem_u32(&s.Sg[0][0]) + (uint32_t)(l7 * TC_GG_LD * 2 + (mi & 1) * 16);
+      // pooling A operand = h^T through ldmatrix.trans: stored 8x8 blocks are (8 rows) x (8 columns); matrices
+      // (c lo, rows lo) (c hi, rows lo) (c lo, rows hi) (c hi, rows hi) of the warp's 16 columns and a 16-row K step
+      const uint32_t pool_cu = (uint32_t)(2 * w8 + (mi & 1));         // 8-column unit (16 bytes) inside the 128-byte row
+      const uint32_t pool_lane = (pool_cu >> 3) * 16384u + (uint32_t)((mi >> 1) * 1024 + l7 * 128) + (((pool_cu & 7u) ^ (uint32_t)l7) << 4);
+      const uint32_t h_base = smem_u32(&s.h[0][0]);
 
       // store 32 fp32 columns [32c, 32c+32) of this particle's row as bf16 into the swizzled h tile
       auto store_h_bf16 = [&](const uint32_t (&v)[32], int c, uint32_t pred) {
@@ -424,31 +459,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           sts128_if(hrow_addr + (uint32_t)((c16 >> 3) * 16384) + ((uint32_t)((c16 & 7) << 4) ^ rx16), pk.x, pk.y, pk.z, pk.w, pred);
         }
       };
-      // masked pooling of columns [32c, 32c+32) over this warp's 32 rows (just stored): 8 mma.sync, partial sums -> Spart
-      auto pool_chunk = [&](int c) {
-        float pa[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { pa[i][0] = 0.f; pa[i][1] = 0.f; pa[i][2] = 0.f; pa[i][3] = 0.f; }
-        __syncwarp();
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-          for (int np = 0; np < 2; ++np) {
-            const uint32_t cu = (uint32_t)(c * 4 + np * 2) + pool_cu;            // 8-column unit (16 bytes) inside the row
-            uint32_t fb[4];
-            ldsm_x4_trans(pool_lane + (uint32_t)(kk * 2048) + (cu >> 3) * 16384u + (((cu & 7u) ^ pool_swz) << 4), fb);
-            hmma_bf16(pa[np * 2], ind[kk][0], ind[kk][1], ind[kk][2], ind[kk][3], fb[0], fb[1]);
-            hmma_bf16(pa[np * 2 + 1], ind[kk][0], ind[kk][1], ind[kk][2], ind[kk][3], fb[2], fb[3]);
-          }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const uint32_t a = spart_lane + (uint32_t)((c * 32 + nt * 8) * 4);
-          sts64_if(a, pa[nt][0], pa[nt][1], pres_lo);
-          sts64_if(a + 8u * TCH * 4u, pa[nt][2], pa[nt][3], pres_hi);
-        }
-      };
-      // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16 (+ pooling)
+      // one 32-column chunk of the residual update: h = lrelu(acc + bias) -> TMEM fp32 (in place) + shared bf16, then the
+      // chunk (two K steps of fc_local1) is handed to the MMA warp
       auto epi_h_chunk = [&](uint32_t (&v)[32], int c, bool last) {
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -456,10 +468,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           bias_lrelu2(v[i4 * 4 + 0], v[i4 * 4 + 1], b.x, b.y, slope2);
           bias_lrelu2(v[i4 * 4 + 2], v[i4 * 4 + 3], b.z, b.w, slope2);
         }
+        // hand chunk c-1 over now: its shared-memory stores were issued a whole chunk of ALU work ago, so the proxy fence
+        // does not wait (a fence right behind the stores costs ~200 cycles per chunk)
+        if (!last && c > 0) { fence_proxy_async(); mbar_arrive(&s.hready[wg][c - 1]); }
         tmem_st32(accH + c * 32, v);
         if (!last) {
           store_h_bf16(v, c, vpred);
-          pool_chunk(c);
+          if (c == 3) { fence_proxy_async(); mbar_arrive(&s.hready[wg][3]); }
         }
       };
       // one 32-column chunk of the fc_local1 epilogue: u = lrelu(acc + bias) -> bf16 pairs in place in TMEM
@@ -476,11 +491,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         tmem_st16(accU + c * 16, u16);        // columns [16c, 16c+16) were already read (16c+16 <= 32c+32)
       };
 
-      float greg[2][4];                          // global vectors of the group in C-fragment layout: [z tile][jet g8: z 2t4, 2t4+1 | jet g8+8: same]
+      // global vectors of the group, fp32, in the D^T fragment layout: greg[jet block][z g8: jets 2t4, 2t4+1 | z g8+8: same]
+      float greg[2][4];
+      fetch_bias(0, 0, 0);
       for (int ev = 0; ev < p.n_evals; ++ev) {
         // ---------------- unit 0 pack (stem biases + fc_g2) has landed; per-jet stem biases ----------------
         PROF_T(0);
         mbar_wait(&s.spk_full, c_spk++ & 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ebar();                                    // unit 0's bias slice (every thread waited for its own pieces) is visible
+        sbias_cur = &s.sbias[c_unit & 1][0];
+        fetch_bias(ev, 1, (c_unit + 1) & 1);
         PROF_T(1);
         float b3[FP];                              // head bias and step size: loaded now, used at the end of the evaluation
 #pragma unroll
@@ -523,10 +544,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           tmem_st32(accH + c * 32, v);
           store_h_bf16(v, c, vpred);
         }
-        tmem_wait_st();
+        tmem_wait_st();                            // fc_l2 accumulates onto h1 in TMEM: all of it must be there first
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&s.hready[wg]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mbar_arrive(&s.hready[wg][c]);
         PROF_T(2);
         ++ring_e;                                  // the stem's fc_l2 image
 
@@ -553,22 +575,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
               epi_h_chunk(vb, 2 * cc + 1, last);
             }
             PROF_T(4);
-            tmem_wait_st();
-            if (last) break;
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&s.hready[wg]);           // MMA warp: fc_local1 of this tile may start
-            ebar();                               // every warp's partial sums are in Spart; bl1 of the previous unit is dead
+            if (last) { tmem_wait_st(); break; }
+            ebar();                               // the whole new h is in shared memory; bl1 of the previous unit is dead
             PROF_T(5);
-            // ---- pooled sums -> pre-scaled bf16 A operand of fc_global1:  St[j][0:128) = S/n (mean), St[j][128:256) = S*s (sum)
-            for (int i = et; i < nj * TCH; i += 256) {
-              const int j = i >> 7, c = i & 127;
-              const int r0 = s.jrow0[j], r1 = s.jrow0[j + 1];
-              float S = 0.f;
-              if (r1 > r0)
-                for (int w = r0 >> 5; w <= ((r1 - 1) >> 5); ++w) S += s.Spart[j + w][c];
-              s.sb.St[j][c] = __float2bfloat16(S * s.inv_n[j]);
-              s.sb.St[j][TCH + c] = __float2bfloat16(S * p.sum_scale);
+            // ---- masked pooling, this warp's 16 columns over all rows of the group:  S^T[c][jet] = sum_rows h[row][c] P[jet][row]
+            // -> pre-scaled bf16 B operand of fc_global1:  St[jet][0:128) = S/n (mean), St[jet][128:256) = S*s (sum)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              if (nb < NB) {
+                // batches of 4 K steps (64 rows), 4 independent accumulators; the fragments of batch b+1 are requested before
+                // the mma.sync of batch b are issued (the volatile asm keeps program order: no compiler pipelining)
+                float pa[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pa[i][0] = 0.f; pa[i][1] = 0.f; pa[i][2] = 0.f; pa[i][3] = 0.f; }
+                uint32_t fA[2][4][4], fB[2][2][4];
+                const int nbatch = (pool_ks + 3) >> 2;
+                auto load_batch = [&](int bb, uint32_t (&A)[4][4], uint32_t (&Bf)[2][4]) {
+                  const uint32_t hk = h_base + pool_lane + (uint32_t)((bb >> 1) * (int)TC_MAT + (bb & 1) * 8192);   // 64 rows = 8 KB inside a tile's 64-column block
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) ldsm_x4_trans(hk + (uint32_t)(i * 2048), A[i]);
+                  ldsm_x4(p_lane + (uint32_t)(nb * 8 * TC_ST_LD * 2 + bb * 128), Bf[0]);
+                  ldsm_x4(p_lane + (uint32_t)(nb * 8 * TC_ST_LD * 2 + bb * 128 + 64), Bf[1]);
+                };
+                load_batch(0, fA[0], fB[0]);
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                  if (bb < nbatch) {
+                    if (bb + 1 < nbatch) load_batch(bb + 1, fA[(bb + 1) & 1], fB[(bb + 1) & 1]);
+                    uint32_t (&A)[4][4] = fA[bb & 1];
+                    uint32_t (&Bf)[2][4] = fB[bb & 1];
+                    hmma_bf16(pa[0], A[0][0], A[0][1], A[0][2], A[0][3], Bf[0][0], Bf[0][1]);
+                    hmma_bf16(pa[1], A[1][0], A[1][1], A[1][2], A[1][3], Bf[0][2], Bf[0][3]);
+                    hmma_bf16(pa[2], A[2][0], A[2][1], A[2][2], A[2][3], Bf[1][0], Bf[1][1]);
+                    hmma_bf16(pa[3], A[3][0], A[3][1], A[3][2], A[3][3], Bf[1][2], Bf[1][3]);
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = nb * 8 + 2 * t4 + e;
+                  const float inv = s.inv_n[j];
+                  const float slo = (pa[0][e] + pa[1][e]) + (pa[2][e] + pa[3][e]);                   // column 16 w8 + g8
+                  const float shi = (pa[0][2 + e] + pa[1][2 + e]) + (pa[2][2 + e] + pa[3][2 + e]);   // column 16 w8 + g8 + 8
+                  const uint32_t a = smem_u32(&s.sb.St[j][w8 * 16 + g8]);
+                  sts16_if(a, __float2bfloat16(slo * inv), j < nj);
+                  sts16_if(a + 16u, __float2bfloat16(shi * inv), j < nj);
+                  sts16_if(a + 2u * TCH, __float2bfloat16(slo * p.sum_scale), j < nj);
+                  sts16_if(a + 2u * TCH + 16u, __float2bfloat16(shi * p.sum_scale), j < nj);
+                }
+              }
             }
             PROF_T(6);
           }
@@ -578,108 +632,134 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           if (gi >= 1) ++ring_e;                   // fc_local2 image
           const int Ga = gi == 0 ? LIN_G1 : LIN_LAYER0 + 4 * (gi - 1) + 0, off_ga = gi == 0 ? 256 : 0;
           const int Gb = gi == 0 ? LIN_G2 : LIN_LAYER0 + 4 * (gi - 1) + 1, off_gb = gi == 0 ? 384 : 128;
-          if (gi >= 1) mbar_wait(&s.spk_full, c_spk++ & 1);       // unit gi's pack + bias slice (unit 0: waited at eval start)
-          ebar();                                  // St (and the previous unit's Sg) complete
+          if (gi >= 1) {                           // unit gi's pack + bias slice (unit 0: waited at eval start)
+            mbar_wait(&s.spk_full, c_spk++ & 1);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+          }
+          ebar();                                  // St (and the previous unit's Sg), this unit's bias slice complete
+          if (gi >= 1) {
+            sbias_cur = &s.sbias[c_unit & 1][0];
+            if (gi < L) fetch_bias(ev, gi + 1, (c_unit + 1) & 1);
+            else if (ev + 1 < p.n_evals) fetch_bias(ev + 1, 0, (c_unit + 1) & 1);
+          }
           PROF_T(7);
-          // ---- fc_g1 / fc_global1:  g1[j][o] = lrelu(W_mean . mean + W_sum . sum (+ W_gg . g) + bias), this warp: 16 outputs
+          // ---- fc_g1 / fc_global1, this warp's 16 outputs:  g1[j][o] = lrelu(W_mean . mean + W_sum . sum (+ W_gg . g) + bias)
           // (epic.py:180-182, :375-377)
           {
-            float acc[2][4];
+            mbar_wait(&s.full[it_gm % TC_NSLOT], (it_gm / TC_NSLOT) & 1);
+            mbar_wait(&s.full[it_gs % TC_NSLOT], (it_gs / TC_NSLOT) & 1);
+            const uint32_t img_m = smem_u32(s.w[it_gm % TC_NSLOT]) + img_row, img_s = smem_u32(s.w[it_gs % TC_NSLOT]) + img_row;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+            for (int nb = 0; nb < 2; ++nb) {
+              if (nb < NB) {
+                // 16 K steps over the two images in batches of 4, 4 independent accumulators, loads one batch ahead
+                float acc[4][4];
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {          // mean image, then sum image
-              const uint32_t itw = m ? it_gs : it_gm;
-              mbar_wait(&s.full[itw % TC_NSLOT], (itw / TC_NSLOT) & 1);
-              const uint32_t img = smem_u32(s.w[itw % TC_NSLOT]) + img_row;
+                for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+                uint32_t fA[2][4][4], fB[2][2][4];
+                auto load_batch = [&](int bb, uint32_t (&A)[4][4], uint32_t (&Bf)[2][4]) {   // K steps 4 bb .. 4 bb + 3 of the 16
+                  const uint32_t img = (bb >> 1) ? img_s : img_m;
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t kc = (uint32_t)(ks * 2 + bkh);      // 16-byte unit (8 k values) inside the 128-k image row
-                uint32_t fa[4], fb[4];
-                ldsm_x4(st_lane + (uint32_t)((m * 8 + ks) * 32), fa);
-                ldsm_x4(img + (kc >> 3) * 16384u + (((kc & 7u) ^ img_swz) << 4), fb);
-                hmma_bf16(acc[0], fa[0], fa[1], fa[2], fa[3], fb[0], fb[1]);
-                hmma_bf16(acc[1], fa[0], fa[1], fa[2], fa[3], fb[2], fb[3]);
+                  for (int i = 0; i < 4; ++i) {
+                    const uint32_t kc = (uint32_t)(((bb & 1) * 4 + i) * 2 + a_kh);      // 16-byte unit (8 k values) inside the image row
+                    ldsm_x4(img + (kc >> 3) * 16384u + (((kc & 7u) ^ img_swz) << 4), A[i]);
+                  }
+                  ldsm_x4(st_lane + (uint32_t)(nb * 8 * TC_ST_LD * 2 + bb * 128), Bf[0]);
+                  ldsm_x4(st_lane + (uint32_t)(nb * 8 * TC_ST_LD * 2 + bb * 128 + 64), Bf[1]);
+                };
+                load_batch(0, fA[0], fB[0]);
+                uint32_t fga[4], fgb[2];
+                if (gi >= 1) {                     // the 16 global-vector columns (17th K step)
+                  ldsm_x4(wgg_lane, fga);
+                  ldsm_x2(sg_lane + (uint32_t)(nb * 8 * TC_GG_LD * 2), fgb);
+                }
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                  if (bb < 3) load_batch(bb + 1, fA[(bb + 1) & 1], fB[(bb + 1) & 1]);
+                  uint32_t (&A)[4][4] = fA[bb & 1];
+                  uint32_t (&Bf)[2][4] = fB[bb & 1];
+                  hmma_bf16(acc[0], A[0][0], A[0][1], A[0][2], A[0][3], Bf[0][0], Bf[0][1]);
+                  hmma_bf16(acc[1], A[1][0], A[1][1], A[1][2], A[1][3], Bf[0][2], Bf[0][3]);
+                  hmma_bf16(acc[2], A[2][0], A[2][1], A[2][2], A[2][3], Bf[1][0], Bf[1][1]);
+                  hmma_bf16(acc[3], A[3][0], A[3][1], A[3][2], A[3][3], Bf[1][2], Bf[1][3]);
+                }
+                if (gi >= 1) hmma_bf16(acc[0], fga[0], fga[1], fga[2], fga[3], fgb[0], fgb[1]);
+                const int o = w8 * 16 + g8;        // D^T rows of this lane: o, o + 8; columns: jets 2 t4, 2 t4 + 1 of the block
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = nb * 8 + 2 * t4 + e;
+                  const int jgl = SIMPLE ? 0 : s.jid[j];
+                  const float v0 = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]) + unit_bias(Ga, off_ga, jgl, o);
+                  const float v1 = (acc[0][2 + e] + acc[1][2 + e]) + (acc[2][2 + e] + acc[3][2 + e]) + unit_bias(Ga, off_ga, jgl, o + 8);
+                  const uint32_t a = smem_u32(&s.g1[j][o]);
+                  sts16_if(a, __float2bfloat16(lrelu_tc(v0, p.slope)), j < nj);
+                  sts16_if(a + 16u, __float2bfloat16(lrelu_tc(v1, p.slope)), j < nj);
+                }
               }
-            }
-            if (gi >= 1) {                         // the 16 global-vector columns
-              uint32_t fa[4], fb[4];
-              ldsm_x4(sg_lane, fa);
-              ldsm_x4(wgg_lane, fb);
-              hmma_bf16(acc[0], fa[0], fa[1], fa[2], fa[3], fb[0], fb[1]);
-              hmma_bf16(acc[1], fa[0], fa[1], fa[2], fa[3], fb[2], fb[3]);
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int o = w8 * 16 + nt * 8 + 2 * t4;
-              const float b0 = unit_bias(Ga, off_ga, jg_lo, o), b1 = unit_bias(Ga, off_ga, jg_lo, o + 1);
-              const float c0 = SIMPLE ? b0 : unit_bias(Ga, off_ga, jg_hi, o), c1 = SIMPLE ? b1 : unit_bias(Ga, off_ga, jg_hi, o + 1);
-              sts32_if(smem_u32(&s.g1[g8][o]), pack_bf16x2(lrelu_tc(acc[nt][0] + b0, p.slope), lrelu_tc(acc[nt][1] + b1, p.slope)), jet_lo);
-              sts32_if(smem_u32(&s.g1[g8 + 8][o]), pack_bf16x2(lrelu_tc(acc[nt][2] + c0, p.slope), lrelu_tc(acc[nt][3] + c1, p.slope)), jet_hi);
             }
           }
           ebar();                                  // g1 complete; St and the two ring images are dead
           PROF_T(8);
           if (et == 0) { mbar_arrive(&s.empty[it_gm % TC_NSLOT]); mbar_arrive(&s.empty[it_gs % TC_NSLOT]); }
-          // ---- fc_g2 / fc_global2 (+ residual for the layers), every warp redundantly: the new global vectors stay in registers
-          {
-            float acc[2][4];
+          // ---- fc_g2 / fc_global2 (+ residual for the layers), every warp redundantly: the new global vectors stay in
+          // registers; then the re-injection for this warp's 16 outputs: per-jet biases of fc_local1 (b + W_t . t + W_glob . g)
+          // and fc_local2
 #pragma unroll
-            for (int i = 0; i < 2; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+          for (int nb = 0; nb < 2; ++nb) {
+            if (nb < NB) {
+              float acc[4][4];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              uint32_t fa[4], fb[4];
-              ldsm_x4(g1_lane + (uint32_t)(ks * 32), fa);
-              ldsm_x4(wg2_lane + (uint32_t)(ks * 32), fb);
-              hmma_bf16(acc[0], fa[0], fa[1], fa[2], fa[3], fb[0], fb[1]);
-              hmma_bf16(acc[1], fa[0], fa[1], fa[2], fa[3], fb[2], fb[3]);
-            }
+              for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+              uint32_t fA[8][4], fB[4][4];         // all 8 K steps requested up front
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
+              for (int ks = 0; ks < 8; ++ks) ldsm_x4(wg2_lane + (uint32_t)(ks * 32), fA[ks]);
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) ldsm_x4(g1_lane + (uint32_t)(nb * 8 * TC_G2_LD * 2 + k2 * 64), fB[k2]);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                hmma_bf16(acc[ks & 3], fA[ks][0], fA[ks][1], fA[ks][2], fA[ks][3], fB[ks >> 1][(ks & 1) * 2], fB[ks >> 1][(ks & 1) * 2 + 1]);
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int z = nt * 8 + 2 * t4 + e, zc = z < Z ? z : Z - 1;
-                const float blo = unit_bias(Gb, off_gb, jg_lo, zc), bhi = SIMPLE ? blo : unit_bias(Gb, off_gb, jg_hi, zc);
-                float vlo = acc[nt][e] + blo, vhi = acc[nt][2 + e] + bhi;
-                if (gi >= 1) { vlo += greg[nt][e]; vhi += greg[nt][2 + e]; }
-                greg[nt][e] = z < Z ? lrelu_tc(vlo, p.slope) : 0.f;
-                greg[nt][2 + e] = z < Z ? lrelu_tc(vhi, p.slope) : 0.f;
+                const int j = nb * 8 + 2 * t4 + e;
+                const int jgl = SIMPLE ? 0 : s.jid[j];
+                const int z0 = g8 < Z ? g8 : Z - 1, z1 = g8 + 8 < Z ? g8 + 8 : Z - 1;
+                float v0 = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]) + unit_bias(Gb, off_gb, jgl, z0);
+                float v1 = (acc[0][2 + e] + acc[1][2 + e]) + (acc[2][2 + e] + acc[3][2 + e]) + unit_bias(Gb, off_gb, jgl, z1);
+                if (gi >= 1) { v0 += greg[nb][e]; v1 += greg[nb][2 + e]; }
+                greg[nb][e] = g8 < Z ? lrelu_tc(v0, p.slope) : 0.f;
+                greg[nb][2 + e] = g8 + 8 < Z ? lrelu_tc(v1, p.slope) : 0.f;
+              }
+              // bf16 copy, transposed to [jet g8][z 2t4, 2t4+1 | 8 + 2t4, ...]: B fragment of the re-injection, and the
+              // global-vector columns of the next unit's fc_global1 operand
+              const uint32_t gt0 = movmatrix_trans(pack_bf16x2(greg[nb][0], greg[nb][1]));
+              const uint32_t gt1 = movmatrix_trans(pack_bf16x2(greg[nb][2], greg[nb][3]));
+              if (w8 == 0) {
+                sts32_if(smem_u32(&s.Sg[nb * 8 + g8][2 * t4]), gt0, true);
+                sts32_if(smem_u32(&s.Sg[nb * 8 + g8][8 + 2 * t4]), gt1, true);
+              }
+              if (gi >= 1) {
+                const int La = LIN_LAYER0 + 4 * (gi - 1) + 2, Lb = LIN_LAYER0 + 4 * (gi - 1) + 3;
+                float bb[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t fa[4];
+                ldsm_x4(wgl_lane, fa);
+                hmma_bf16(bb, fa[0], fa[1], fa[2], fa[3], gt0, gt1);
+                const int o = w8 * 16 + g8;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = nb * 8 + 2 * t4 + e;
+                  const int jgl = SIMPLE ? 0 : s.jid[j];
+                  if (j < nj) {
+                    s.sb.bl1[j][o] = bb[e] + unit_bias(La, 128 + ZP, jgl, o);
+                    s.sb.bl1[j][o + 8] = bb[2 + e] + unit_bias(La, 128 + ZP, jgl, o + 8);
+                    s.bl2[j][o] = unit_bias(Lb, 256 + ZP, jgl, o);
+                    s.bl2[j][o + 8] = unit_bias(Lb, 256 + ZP, jgl, o + 8);
+                  }
+                }
               }
             }
           }
-          const uint32_t ga0 = pack_bf16x2(greg[0][0], greg[0][1]), ga1 = pack_bf16x2(greg[0][2], greg[0][3]);
-          const uint32_t ga2 = pack_bf16x2(greg[1][0], greg[1][1]), ga3 = pack_bf16x2(greg[1][2], greg[1][3]);
-          if (w8 == 0) {                           // bf16 copy for the next unit's fc_global1 (read after that unit's barrier)
-            sts32_if(smem_u32(&s.Sg[g8][2 * t4]), ga0, true);
-            sts32_if(smem_u32(&s.Sg[g8 + 8][2 * t4]), ga1, true);
-            sts32_if(smem_u32(&s.Sg[g8][8 + 2 * t4]), ga2, true);
-            sts32_if(smem_u32(&s.Sg[g8 + 8][8 + 2 * t4]), ga3, true);
-          }
-          PROF_T(9);
-          if (gi >= 1) {
-            // ---- re-injection: per-jet biases of fc_local1 (b + W_t . t + W_glob . g) and fc_local2, this warp's 16 outputs
-            const int La = LIN_LAYER0 + 4 * (gi - 1) + 2, Lb = LIN_LAYER0 + 4 * (gi - 1) + 3;
-            float acc[2][4];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-            uint32_t fb[4];
-            ldsm_x4(wgl_lane, fb);
-            hmma_bf16(acc[0], ga0, ga1, ga2, ga3, fb[0], fb[1]);
-            hmma_bf16(acc[1], ga0, ga1, ga2, ga3, fb[2], fb[3]);
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int o = w8 * 16 + nt * 8 + 2 * t4;
-              const float a0 = unit_bias(La, 128 + ZP, jg_lo, o), a1 = unit_bias(La, 128 + ZP, jg_lo, o + 1);
-              const float d0 = unit_bias(Lb, 256 + ZP, jg_lo, o), d1 = unit_bias(Lb, 256 + ZP, jg_lo, o + 1);
-              sts64_if(smem_u32(&s.sb.bl1[g8][o]), acc[nt][0] + a0, acc[nt][1] + a1, jet_lo);
-              sts64_if(smem_u32(&s.bl2[g8][o]), d0, d1, jet_lo);
-              const float a2 = SIMPLE ? a0 : unit_bias(La, 128 + ZP, jg_hi, o), a3 = SIMPLE ? a1 : unit_bias(La, 128 + ZP, jg_hi, o + 1);
-              const float d2 = SIMPLE ? d0 : unit_bias(Lb, 256 + ZP, jg_hi, o), d3 = SIMPLE ? d1 : unit_bias(Lb, 256 + ZP, jg_hi, o + 1);
-              sts64_if(smem_u32(&s.sb.bl1[g8 + 8][o]), acc[nt][2] + a2, acc[nt][3] + a3, jet_hi);
-              sts64_if(smem_u32(&s.bl2[g8 + 8][o]), d2, d3, jet_hi);
-            }
-          }
-          mbar_arrive(&s.spk_empty);               // pack + bias slice of this unit are dead: the producer may refill
+          mbar_arrive(&s.spk_empty);               // the pack of this unit is dead: the producer may refill
+          ++c_unit;
           PROF_T(10);
           if (gi >= 1) {
             ebar();                                // bl1 / bl2 complete
