@@ -231,6 +231,84 @@ int pfm_tf_loss_fwd_bwd(pfm_tf* h, const float* x1, const float* t, const float*
                         const float* noise1, const float* mask, const float* cond, int loss_kind, float sigma,
                         float* loss_out, float* grad_flat, int B, int N, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diffusion family on the same network (loss_type="diffusion"): the samplers of
+ *   components/solver.py:23-143 (ddim_sampler, euler_maruyama_sampler) and the probability-flow ODE of
+ *   flow_matching_module.py:62-69 (ode_wrapper, loss_type == "diffusion") behind CNF.decode :279-287, :304-327,
+ * as per-evaluation update rules of the SAME single-launch integrator (state resident on chip).
+ *   coef [n_evals, 4]  host-computed fp32 schedule values of every network evaluation (device memory):
+ *     PFM_STEP_PF_ODE : {beta(t), noise_rate(t), -, -}   drift f = -0.5*beta*(x - v/noise_rate), stepped with `solver`
+ *                       (Euler / midpoint in reversed time, dt as in pfm_epic_sample)
+ *     PFM_STEP_DDIM   : {signal_rate, noise_rate, next_signal_rate, next_noise_rate}
+ *                       pred = (x - nr*v)/sr;  x <- nsr*pred + nnr*v;  the result is pred of the last step
+ *     PFM_STEP_EM     : {beta, noise_rate, delta_t, sqrt(beta*delta_t)}
+ *                       x += 0.5*beta*(x + 2*(-v/nr))*delta_t;  x += sqrt(beta*delta_t) * noise[step]
+ *   noise [n_steps, B, N, feats]  (PFM_STEP_EM only) the caller's per-step normal draws (the reference draws
+ *                       torch.randn_like(x_t) on the device at every step, solver.py:131)
+ * fp32 path only (PFM_PREC_FP32). */
+typedef enum { PFM_STEP_PF_ODE = 1, PFM_STEP_DDIM = 2, PFM_STEP_EM = 3 } pfm_step_kind;
+int pfm_epic_sample_diffusion(pfm_epic* h, float* x_inout, const float* mask, const float* cond, const float* t_codes,
+                              const float* t_codes_in, const float* coef, const float* noise, const float* dt, int step_kind,
+                              int solver, int n_steps, int B, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * generate_data post-processing on the device  <- particle_fm/utils/data_generation.py:105-123
+ *   out[b,n,f] = post(x[b,n,f]) (* mask[b,n] if mask != NULL), with
+ *   post(v) = v * scale[f] + shift[f]        (inverse_normalize_tensor, data/components/utils.py:183-200;
+ *                                             scale = std/sigma, shift = mean; two roundings like the eager ops)
+ *             then 1 - exp(.) on column log_col (log_pt, :116-117; log_col < 0: none);  scale == shift == NULL: identity.
+ *   first_only_col >= 0: on that column the affine part is applied to particle 0 of every jet only -- what the
+ *             reference's pt_standardization branch does (:111-113 passes the 2-D slice batch[..., 2] to
+ *             inverse_normalize_tensor, whose ``tensor[..., 0]`` then indexes particles); -1 otherwise.
+ * x, mask: device memory.  scale / shift: HOST arrays of F floats (passed by value to the kernel).  out: device memory
+ * OR pinned (page-locked) host memory -- the kernel writes the final values straight into the caller's host buffer,
+ * there is no separate device -> host copy.  F <= PFM_POST_MAX_FEATS. */
+#define PFM_POST_MAX_FEATS 16
+int pfm_postprocess(const float* x, const float* mask, float* out, long long B, int N, int F, const float* scale,
+                    const float* shift, int log_col, int first_only_col, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CFM-OT mini-batch coupling  <- ConditionalFlowMatchingOTLoss.forward, losses.py:165-189
+ * pfm_ot_assign: for every jet k the exact optimal assignment between the N noise points x0[k] and the N data points
+ *   x1[k] under the squared Euclidean cost (what POT's ot.emd returns for uniform marginals, as a permutation):
+ *   sigma[k, i] = j.  cost[k] (optional, double) = sum_i |x0[k,i] - x1[k,sigma(i)]|^2.  One warp per jet, N <= 320.
+ * pfm_ot_gather: the resampled pairs of losses.py:183-189 for host-drawn row picks pick[k, m] in [0, N):
+ *   x0p[k,m] = x0[k,pick], x1p[k,m] = x1[k,sigma[pick]], mask_ot[k,m] = mask[k,sigma[pick]] (mask NULL = ones). */
+int pfm_ot_assign(const float* x0, const float* x1, int B, int N, int F, int32_t* sigma, double* cost, void* stream);
+int pfm_ot_gather(const float* x0, const float* x1, const float* mask, const int32_t* sigma, const int32_t* pick, int B, int N,
+                  int F, float* x0p, float* x1p, float* mask_ot, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Jet-feature flow  <- CNF of particle_fm/models/flow_matching_no_sets.py:41-93 around
+ *                      small_cond_MLP_model, components/mlp.py:24-68 (blocks of nn.Linear + activation; every block's
+ *                      input is torch.cat([t, x, cond]))
+ * A chain of n_linears dense layers on rows (one row = one event).  For linear i: out_widths[i] outputs,
+ * concat[i] != 0: its input is [time code | previous output | cond] (K = t_dim + prev + cond_dim), else the previous
+ * output; act[i] != 0: the activation follows it.  The last linear maps back to `features`.
+ * pfm_mlp_sample integrates dx/dt = v(t, x, cond) from t = 1 to 0 exactly like pfm_epic_sample (one launch, the state
+ * of a row tile resident in shared memory, weights streamed from L2); pfm_mlp_forward is one evaluation. */
+typedef enum { PFM_ACT_ELU = 0, PFM_ACT_TANH = 1, PFM_ACT_RELU = 2, PFM_ACT_LEAKY_RELU = 3, PFM_ACT_SILU = 4 } pfm_act;
+typedef struct {
+  int32_t features;   /* row width in and out                         */
+  int32_t t_dim;      /* width of the time code (2 * freqs)           */
+  int32_t cond_dim;   /* width of cond (1: m_jj)                      */
+  int32_t n_linears;
+  int32_t act;        /* pfm_act                                      */
+} pfm_mlp_cfg;
+typedef struct pfm_mlp pfm_mlp;
+int pfm_mlp_create(const pfm_mlp_cfg* cfg, const int32_t* out_widths, const int32_t* concat, const int32_t* act, int device,
+                   pfm_mlp** out);
+void pfm_mlp_destroy(pfm_mlp* h);
+int pfm_mlp_linear_shape(const pfm_mlp* h, int i, int32_t* out_features, int32_t* in_features);
+/* weights[i]: row-major [out, in] fp32 (nn.Linear.weight), biases[i]: [out]; device pointers, host pointer arrays */
+int pfm_mlp_set_weights(pfm_mlp* h, const float* const* weights, const float* const* biases, int n, void* stream);
+/* t_code [1|B, t_dim], x [B, features], cond [B, cond_dim] -> out [B, features] */
+int pfm_mlp_forward(pfm_mlp* h, const float* t_code, int t_rows, const float* x, const float* cond, float* out, int B,
+                    void* stream);
+/* x_inout [B, features]; t_codes [n_evals, t_dim]; dt [n_steps] (see pfm_epic_sample) */
+int pfm_mlp_sample(pfm_mlp* h, float* x_inout, const float* cond, const float* t_codes, const float* dt, int solver,
+                   int n_steps, int B, void* stream);
+
 /* Introspection for tests / bench: kernels launched by the last call on this handle and the
  * number of CTA work groups the last plan produced. */
 int pfm_epic_last_launches(const pfm_epic* h);

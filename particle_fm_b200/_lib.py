@@ -12,6 +12,9 @@ LIB_PATH = os.path.join(_PKG, "lib", "libpfm_b200.so")
 PFM_PREC_FP32, PFM_PREC_BF16 = 0, 1
 PFM_SOLVER_EULER, PFM_SOLVER_MIDPOINT = 0, 1
 PFM_LOSS_FM_OT, PFM_LOSS_CFM, PFM_LOSS_DROID = 0, 1, 2
+PFM_STEP_PF_ODE, PFM_STEP_DDIM, PFM_STEP_EM = 1, 2, 3
+PFM_ACT = {"ELU": 0, "Tanh": 1, "ReLU": 2, "LeakyReLU": 3, "SiLU": 4}
+PFM_POST_MAX_FEATS = 16
 
 
 class PfmError(RuntimeError):
@@ -22,6 +25,10 @@ class EpicCfgC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("feats", "input_dim", "hid", "latent", "layers", "t_dim", "t_local_cat",
                                          "t_global_cat", "global_cond_dim", "local_cond_dim")] + \
                [("sum_scale", C.c_float), ("neg_slope", C.c_float)]
+
+
+class MlpCfgC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("features", "t_dim", "cond_dim", "n_linears", "act")]
 
 
 class TfCfgC(C.Structure):
@@ -66,6 +73,18 @@ _SIGNATURES = {
     "pfm_tf_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfm_tf_loss_fwd_bwd": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p]),
+    "pfm_epic_sample_diffusion": (C.c_int, [C.c_void_p] + [_F] * 8 + [C.c_int] * 5 + [C.c_void_p]),
+    "pfm_postprocess": (C.c_int, [_F, _F, _F, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                  C.c_int, C.c_void_p]),
+    "pfm_ot_assign": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, _F, _F, C.c_void_p]),
+    "pfm_ot_gather": (C.c_int, [_F] * 5 + [C.c_int] * 3 + [_F] * 3 + [C.c_void_p]),
+    "pfm_mlp_create": (C.c_int, [C.POINTER(MlpCfgC), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                                 C.POINTER(C.c_void_p)]),
+    "pfm_mlp_destroy": (None, [C.c_void_p]),
+    "pfm_mlp_linear_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pfm_mlp_set_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "pfm_mlp_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, C.c_int, C.c_void_p]),
+    "pfm_mlp_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_last_launches": (C.c_int, [C.c_void_p]),
     "pfm_epic_last_groups": (C.c_int, [C.c_void_p]),
     "pfm_epic_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -26,6 +26,7 @@ struct SimtParams {
   const int* jetmap;           // position -> jet (inference plan; nullptr = identity, training)
   const float* x_in; float* x_out; int B, N;
   int n_evals, solver, n_steps; const float* dt;
+  int step_kind; const float* coef; const float* noise; long long noise_step_stride; int jet0;   // diffusion step program (RunArgs)
   // training forward (TRAIN instantiation): interpolation inputs, saved activations, loss
   const float* x1; const float* tjet; const float* noise0; const float* noise1; int loss_kind; float sigma;
   float* act; size_t act_stage_stride; int Hp_act;          // act[stage][row][Hp_act]
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
         __syncthreads();
       }
       // ---------------- integrator (torchdyn fixed step, restated in oracle/ode_oracle.py) ----------------
-      if (p.solver >= 0) {
+      if (p.solver >= 0 && (TRAIN || p.step_kind == 0)) {
         const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
         const int step = mid ? (ev >> 1) : ev;
         const float dt = p.dt[step];
@@ -361,6 +362,56 @@ __global__ void __launch_bounds__(kThreads, 1) epic_simt_kernel(const SimtParams
             xs[row * LDX + f] = __fadd_rn(x0[i], __fmul_rn(hdt, k));     // x + 0.5*dt*k1
           } else {
             const float xn = __fadd_rn(x0[i], __fmul_rn(dt, k));         // x + dt*f_(...)
+            x0[i] = xn;
+            xs[row * LDX + f] = xn;
+          }
+        }
+        __syncthreads();
+      } else if (!TRAIN && p.solver >= 0) {
+        // ---------------- diffusion step programs (components/solver.py, flow_matching_module.py:62-69) ----------------
+        const float4 cf = *reinterpret_cast<const float4*>(p.coef + (size_t)ev * 4);
+        if (p.step_kind == PFM_STEP_PF_ODE) {
+          // f(t, x) = -0.5 * beta * (x - v / noise_rate); reversed time: k = -f; x is the state the net was evaluated at
+          const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
+          const float dt = p.dt[mid ? (ev >> 1) : ev];
+          const bool first_stage = mid && ((ev & 1) == 0);
+          const float hdt = __fmul_rn(0.5f, dt);
+          const float mhb = __fmul_rn(-0.5f, cf.x);
+          for (int i = tid; i < R * F; i += kThreads) {
+            const int row = i / F, f = i - row * F;
+            const float xin = xs[row * LDX + f];
+            const float k = -__fmul_rn(mhb, __fadd_rn(xin, -__fdiv_rn(vbuf[i], cf.y)));
+            if (first_stage) {
+              xs[row * LDX + f] = __fadd_rn(x0[i], __fmul_rn(hdt, k));
+            } else {
+              const float xn = __fadd_rn(x0[i], __fmul_rn(dt, k));
+              x0[i] = xn;
+              xs[row * LDX + f] = xn;
+            }
+          }
+        } else if (p.step_kind == PFM_STEP_DDIM) {
+          // pred = (x - nr * v) / sr;  x <- next_sr * pred + next_nr * v;  the last step returns pred  (solver.py:16-19, :79-92)
+          const bool last = ev == p.n_evals - 1;
+          for (int i = tid; i < R * F; i += kThreads) {
+            const int row = i / F, f = i - row * F;
+            const float v = vbuf[i];
+            const float pred = __fdiv_rn(__fadd_rn(x0[i], -__fmul_rn(cf.y, v)), cf.x);
+            const float xn = last ? pred : __fadd_rn(__fmul_rn(cf.z, pred), __fmul_rn(cf.w, v));
+            x0[i] = xn;
+            xs[row * LDX + f] = xn;
+          }
+        } else {
+          // Euler-Maruyama (solver.py:122-131): s = -v / nr; x += 0.5*beta*(x + 2 s)*delta_t; x += sqrt(beta*delta_t) * noise
+          const float hb = __fmul_rn(0.5f, cf.x);
+          const float* nz = p.noise + (size_t)ev * p.noise_step_stride;
+          for (int i = tid; i < R * F; i += kThreads) {
+            const int row = i / F, f = i - row * F;
+            const int j = rjet[row];
+            const int part = p.ridx[(size_t)jid[j] * p.N + (row - jrow0[j])];
+            const float sc = __fdiv_rn(-vbuf[i], cf.y);
+            float xn = x0[i];
+            xn = __fadd_rn(xn, __fmul_rn(__fmul_rn(hb, __fadd_rn(xn, __fmul_rn(2.f, sc))), cf.z));
+            xn = __fadd_rn(xn, __fmul_rn(cf.w, nz[((size_t)(p.jet0 + jid[j]) * p.N + part) * F + f]));
             x0[i] = xn;
             xs[row * LDX + f] = xn;
           }
@@ -548,6 +599,7 @@ int simt_run(pfm_epic* h, const RunArgs& a, cudaStream_t st) {
   p.counter = h->plan.counter; p.jetmap = a.jetmap;
   p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
   p.n_evals = a.n_evals; p.solver = a.solver; p.n_steps = a.n_steps; p.dt = a.dt;
+  p.step_kind = a.step_kind; p.coef = a.coef; p.noise = a.noise; p.noise_step_stride = a.noise_step_stride; p.jet0 = a.jet0;
   // persistent CTAs: one per SM, but never more than there can be groups (every group has >= 1 jet)
   int grid = h->sm_count < a.B ? h->sm_count : a.B;
   rc = ensure_spill(h, s, grid);
@@ -571,6 +623,7 @@ int simt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   p.counter = h->plan.counter;
   p.x_in = a.x_in; p.x_out = a.x_out; p.B = a.B; p.N = a.N;
   p.n_evals = 1; p.solver = -1; p.n_steps = 0; p.dt = nullptr;
+  p.step_kind = 0; p.coef = nullptr; p.noise = nullptr; p.noise_step_stride = 0; p.jet0 = 0;
   p.x1 = a.x_in; p.tjet = a.t; p.noise0 = a.noise0; p.noise1 = a.noise1; p.loss_kind = a.loss_kind; p.sigma = a.sigma;
   p.act = h->act; p.act_stage_stride = a.lay.stage_stride; p.Hp_act = a.lay.Hp;
   p.yact = h->yact;

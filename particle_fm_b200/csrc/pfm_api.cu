@@ -343,6 +343,8 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
     a.n_evals = n_evals; a.solver = solver; a.n_steps = n_steps; a.dt = dt;
     a.tbias_per_jet = per_jet_t ? 1 : 0;
     a.has_cbias = cond_dim > 0;
+    a.step_kind = h->step_kind; a.coef = h->step_coef; a.noise = h->step_noise;
+    a.noise_step_stride = (long long)B * N * c.feats; a.jet0 = b0;
     // per-jet tables are indexed by the jet index inside this chunk
     float* tb_save = h->tbias; float* cb_save = h->cbias;
     if (per_jet_t) h->tbias += (size_t)b0 * h->bstride;
@@ -555,6 +557,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   memset(&h->plan, 0, sizeof(h->plan));
   h->last_launches = 0; h->last_groups_host = 0;
   h->timing = false; h->ev_used = 0;
+  h->step_kind = 0; h->step_coef = nullptr; h->step_noise = nullptr;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   h->lin_host.resize(h->n_lin);
@@ -844,6 +847,31 @@ int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float*
   const int n_evals = n_steps * (solver == PFM_SOLVER_MIDPOINT ? 2 : 1);
   return run_chunked(h, t_codes, n_evals, false, t_codes_in, t_in, x_inout, x_inout, mask, cond, B, N, h->cfg.feats,
                      t_in, n_evals, solver, n_steps, dt, (cudaStream_t)stream);
+}
+
+int pfm_epic_sample_diffusion(pfm_epic* h, float* x_inout, const float* mask, const float* cond, const float* t_codes,
+                              const float* t_codes_in, const float* coef, const float* noise, const float* dt, int step_kind,
+                              int solver, int n_steps, int B, int N, void* stream) {
+  if (!h || !x_inout || !coef) { set_error("null argument"); return PFM_ERR_INVALID; }
+  if (step_kind != PFM_STEP_PF_ODE && step_kind != PFM_STEP_DDIM && step_kind != PFM_STEP_EM) { set_error("unknown step kind %d", step_kind); return PFM_ERR_INVALID; }
+  if (step_kind == PFM_STEP_PF_ODE) {
+    if (solver != PFM_SOLVER_EULER && solver != PFM_SOLVER_MIDPOINT) { set_error("unknown solver %d", solver); return PFM_ERR_INVALID; }
+    if (!dt) { set_error("the probability-flow ODE needs the step sizes dt"); return PFM_ERR_INVALID; }
+  } else {
+    solver = PFM_SOLVER_EULER;       // one network evaluation per step
+  }
+  if (step_kind == PFM_STEP_EM && !noise) { set_error("the Euler-Maruyama sampler needs the per-step noise"); return PFM_ERR_INVALID; }
+  if (n_steps <= 0) { set_error("n_steps must be positive"); return PFM_ERR_INVALID; }
+  if (h->precision != PFM_PREC_FP32) { set_error("the diffusion samplers run on the fp32 path (PFM_PREC_FP32)"); return PFM_ERR_UNSUPPORTED; }
+  const int t_in = h->cfg.input_dim - h->cfg.feats;
+  if (t_in < 0) { set_error("input_dim < feats"); return PFM_ERR_INVALID; }
+  if (t_in > 0 && !t_codes_in) { set_error("input_dim > feats needs t_codes_in (add_time_to_input)"); return PFM_ERR_INVALID; }
+  const int n_evals = n_steps * (solver == PFM_SOLVER_MIDPOINT ? 2 : 1);
+  h->step_kind = step_kind; h->step_coef = coef; h->step_noise = noise;
+  const int rc = run_chunked(h, t_codes, n_evals, false, t_codes_in, t_in, x_inout, x_inout, mask, cond, B, N, h->cfg.feats,
+                             t_in, n_evals, solver, n_steps, dt, (cudaStream_t)stream);
+  h->step_kind = 0; h->step_coef = nullptr; h->step_noise = nullptr;
+  return rc;
 }
 
 int pfm_epic_last_launches(const pfm_epic* h) { return h ? h->last_launches : PFM_ERR_INVALID; }

@@ -92,6 +92,8 @@ struct pfm_epic {
   int wn_total_rows;
   long long* wn_goff;               // [2 n_lin] offsets of W_i and b_i in the flat gradient
   const float** wn_ptrs;            // [8 n_lin] device copy of the caller's pointer tables
+  // diffusion step program of the next sampling call (pfm_epic_sample_diffusion; 0 = plain flow-matching ODE)
+  int step_kind; const float* step_coef; const float* step_noise;
   bool timing;
   std::vector<cudaEvent_t> ev_pool;   // start/stop pairs of the main kernel, one pair per chunk of a call
   int ev_used;
@@ -122,6 +124,11 @@ struct RunArgs {
   int tbias_per_jet;      // 0: bias-table row = evaluation index; 1: row = jet index
   bool has_cbias;
   const int* jetmap;      // position -> jet (nullptr: identity)
+  int step_kind;          // 0: dx/dt = v (flow matching); else pfm_step_kind (diffusion samplers, fp32 path only)
+  const float* coef;      // [n_evals, 4] schedule values of the step program
+  const float* noise;     // PFM_STEP_EM: [n_steps, B_total, N, feats]
+  long long noise_step_stride;   // B_total * N * feats
+  int jet0;               // index of this launch's first jet inside the whole request (noise addressing)
 };
 
 // fp32 CUDA-core path (epic_simt.cu)

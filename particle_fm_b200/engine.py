@@ -330,3 +330,178 @@ class EpicEngine:
 
     def last_groups(self) -> int:
         return int(self.lib.pfm_epic_last_groups(self._h))
+
+    # -- diffusion samplers ---------------------------------------------------------
+    def sample_diffusion(self, z: Tensor, mask: Optional[Tensor], cond: Optional[Tensor], t_codes: Optional[Tensor],
+                         t_codes_in: Optional[Tensor], coef: Tensor, step_kind: str, solver: str = "euler",
+                         dt: Optional[Tensor] = None, noise: Optional[Tensor] = None) -> Tensor:
+        """Single-launch DDIM / Euler-Maruyama / probability-flow-ODE sampling (pfm_epic_sample_diffusion).
+        coef [n_evals, 4] schedule values per evaluation, noise [n_steps, B, N, feats] for 'em'."""
+        B, N = int(z.shape[0]), int(z.shape[1])
+        x = z.detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+        mask = None if mask is None else _f32c(mask.reshape(B, N), self.device)
+        cond = self._cond(cond, B)
+        kind = {"pf_ode": _lib.PFM_STEP_PF_ODE, "ddim": _lib.PFM_STEP_DDIM, "em": _lib.PFM_STEP_EM}[step_kind]
+        code = {"euler": _lib.PFM_SOLVER_EULER, "midpoint": _lib.PFM_SOLVER_MIDPOINT}[solver]
+        coef = _f32c(coef, self.device).reshape(-1, 4)
+        n_evals = int(coef.shape[0])
+        n_steps = n_evals // (2 if (step_kind == "pf_ode" and solver == "midpoint") else 1)
+        dt = None if dt is None else _f32c(dt, self.device).reshape(-1)
+        noise = None if noise is None else _f32c(noise, self.device)
+        if noise is not None and tuple(noise.shape) != (n_steps, B, N, self.dims.feats):
+            raise ValueError(f"noise must be [n_steps={n_steps}, B={B}, N={N}, feats={self.dims.feats}], got {tuple(noise.shape)}")
+        if t_codes is not None:
+            t_codes = _f32c(t_codes, self.device).reshape(n_evals, -1)
+        if t_codes_in is not None:
+            t_codes_in = _f32c(t_codes_in, self.device).reshape(n_evals, -1)
+        self._ticket = getattr(self, "_ticket", 0) + 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_epic_sample_diffusion(self._h, _ptr(x), _ptr(mask), _ptr(cond), _ptr(t_codes),
+                                                          _ptr(t_codes_in), _ptr(coef), _ptr(noise), _ptr(dt), kind, code,
+                                                          n_steps, B, N, self._stream()), "pfm_epic_sample_diffusion")
+        return x
+
+
+# ----------------------------------------------------------------------------------------------
+# generate_data post-processing (SURVEY 8f2)
+# ----------------------------------------------------------------------------------------------
+def postprocess_into(x: Tensor, mask: Optional[Tensor], out: Tensor, scale=None, shift=None, log_col: int = -1,
+                     first_only_col: int = -1):
+    """out[...] = post(x) (* mask): inverse normalisation / log-pt / masking of data_generation.py:105-123 in one kernel
+    that writes straight into ``out`` -- a CUDA tensor or a PINNED host tensor (no separate device -> host copy).
+    x [B,N,F] on a CUDA device, mask [B,N(,1)] or None, scale / shift sequences of F python floats or None."""
+    if x.device.type != "cuda":
+        raise _lib.PfmError("postprocess_into needs a CUDA tensor (no CPU fallback)")
+    lib = _lib.load()
+    B, N, F = (int(s) for s in x.shape)
+    x = x.detach().to(torch.float32).contiguous()
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (B, N, F):
+        raise ValueError("out must be a contiguous float32 tensor of x's shape")
+    if out.device.type == "cpu" and not out.is_pinned():
+        raise ValueError("a host output buffer must be pinned (page-locked): the kernel writes into it directly")
+    if mask is not None:
+        mask = mask.detach().to(device=x.device, dtype=torch.float32).reshape(B, N).contiguous()
+    sc = sh = None
+    if scale is not None:
+        sc = (C.c_float * F)(*[float(v) for v in scale])
+        sh = (C.c_float * F)(*[float(v) for v in shift])
+    with torch.cuda.device(x.device):
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.pfm_postprocess(_ptr(x), _ptr(mask), C.c_void_p(out.data_ptr()), B, N, F, sc, sh, int(log_col),
+                                       int(first_only_col), st),
+                   "pfm_postprocess")
+    if out.device.type == "cuda":
+        return out
+    x.record_stream(torch.cuda.current_stream(x.device))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CFM-OT coupling (SURVEY 8f1)
+# ----------------------------------------------------------------------------------------------
+def ot_assign(x0: Tensor, x1: Tensor, want_cost: bool = False):
+    """sigma [B,N] int32: exact optimal assignment of noise particle i to data particle sigma[i] per jet
+    (squared Euclidean cost; = POT's ot.emd plan for uniform marginals, losses.py:171-180)."""
+    if x0.device.type != "cuda":
+        raise _lib.PfmError("ot_assign needs CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    B, N, F = (int(s) for s in x0.shape)
+    a, b = _f32c(x0, x0.device), _f32c(x1, x0.device)
+    sigma = torch.empty(B, N, device=x0.device, dtype=torch.int32)
+    cost = torch.empty(B, device=x0.device, dtype=torch.float64) if want_cost else None
+    with torch.cuda.device(x0.device):
+        st = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+        _lib.check(lib.pfm_ot_assign(_ptr(a), _ptr(b), B, N, F, _ptr(sigma), _ptr(cost), st), "pfm_ot_assign")
+    return (sigma, cost) if want_cost else sigma
+
+
+def ot_gather(x0: Tensor, x1: Tensor, mask: Optional[Tensor], sigma: Tensor, pick: Tensor):
+    """(x0[k, pick], x1[k, sigma[pick]], mask[k, sigma[pick]]) -- the resampled pairs of losses.py:183-189."""
+    lib = _lib.load()
+    B, N, F = (int(s) for s in x0.shape)
+    a, b = _f32c(x0, x0.device), _f32c(x1, x0.device)
+    m = None if mask is None else _f32c(mask.reshape(B, N), x0.device)
+    pick = pick.to(device=x0.device, dtype=torch.int32).contiguous()
+    x0p, x1p = torch.empty_like(a), torch.empty_like(b)
+    mo = torch.empty(B, N, device=x0.device, dtype=torch.float32)
+    with torch.cuda.device(x0.device):
+        st = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+        _lib.check(lib.pfm_ot_gather(_ptr(a), _ptr(b), _ptr(m), _ptr(sigma), _ptr(pick), B, N, F, _ptr(x0p), _ptr(x1p), _ptr(mo), st),
+                   "pfm_ot_gather")
+    return x0p, x1p, mo
+
+
+# ----------------------------------------------------------------------------------------------
+# jet-feature flow (SURVEY 8f3)
+# ----------------------------------------------------------------------------------------------
+class MlpFlowEngine:
+    """Packed copy of a conditional MLP vector field (components/mlp.py small_cond_MLP_model) on one GPU."""
+
+    def __init__(self, features: int, t_dim: int, cond_dim: int, out_widths, concat, act_flags, activation: str,
+                 device: torch.device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.PfmError(f"particle_fm_b200 runs on CUDA devices only (got {device}); there is no CPU fallback")
+        if activation not in _lib.PFM_ACT:
+            raise NotImplementedError(f"activation={activation!r}: the CUDA path implements {sorted(_lib.PFM_ACT)}")
+        self.lib = _lib.load()
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.features, self.t_dim, self.cond_dim, self.n = features, t_dim, cond_dim, len(out_widths)
+        cfg = _lib.MlpCfgC(features, t_dim, cond_dim, self.n, _lib.PFM_ACT[activation])
+        arr = lambda v: (C.c_int32 * self.n)(*[int(i) for i in v])
+        h = C.c_void_p()
+        _lib.check(self.lib.pfm_mlp_create(C.byref(cfg), arr(out_widths), arr(concat), arr(act_flags), self.index, C.byref(h)),
+                   "pfm_mlp_create")
+        self._h = h
+        self.weights_key = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pfm_mlp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_weights(self, weights: Sequence[Tensor], biases: Sequence[Tensor], key=None):
+        ws = [_f32c(w, self.device) for w in weights]
+        bs = [_f32c(b, self.device) for b in biases]
+        o, i = C.c_int32(), C.c_int32()
+        for k, (w, b) in enumerate(zip(ws, bs)):
+            _lib.check(self.lib.pfm_mlp_linear_shape(self._h, k, C.byref(o), C.byref(i)), "pfm_mlp_linear_shape")
+            if tuple(w.shape) != (o.value, i.value) or tuple(b.shape) != (o.value,):
+                raise ValueError(f"linear {k}: expected weight {(o.value, i.value)}, got {tuple(w.shape)}")
+        wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in ws])
+        bp = (C.c_void_p * self.n)(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_mlp_set_weights(self._h, wp, bp, self.n, self._stream()), "pfm_mlp_set_weights")
+        self._keepalive = (ws, bs)
+        self.weights_key = key
+
+    def forward(self, t_code: Tensor, x: Tensor, cond: Optional[Tensor]) -> Tensor:
+        B = int(x.shape[0])
+        x = _f32c(x, self.device).reshape(B, self.features)
+        t_code = _f32c(t_code, self.device).reshape(-1, self.t_dim)
+        cond = None if cond is None else _f32c(cond, self.device).reshape(B, self.cond_dim)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_mlp_forward(self._h, _ptr(t_code), int(t_code.shape[0]), _ptr(x), _ptr(cond), _ptr(out), B,
+                                                self._stream()), "pfm_mlp_forward")
+        return out
+
+    def sample(self, z: Tensor, cond: Optional[Tensor], t_codes: Tensor, dt: Tensor, solver: str) -> Tensor:
+        B = int(z.shape[0])
+        x = z.detach().to(device=self.device, dtype=torch.float32).contiguous().clone()
+        cond = None if cond is None else _f32c(cond, self.device).reshape(B, self.cond_dim)
+        code = {"euler": _lib.PFM_SOLVER_EULER, "midpoint": _lib.PFM_SOLVER_MIDPOINT}[solver]
+        dt = _f32c(dt, self.device).reshape(-1)
+        t_codes = _f32c(t_codes, self.device).reshape(-1, self.t_dim)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pfm_mlp_sample(self._h, _ptr(x), _ptr(cond), _ptr(t_codes), _ptr(dt), code, int(dt.numel()), B,
+                                               self._stream()), "pfm_mlp_sample")
+        return x

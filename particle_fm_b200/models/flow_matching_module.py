@@ -88,11 +88,17 @@ class ode_wrapper(nn.Module):
     def __init__(self, model: nn.Module, mask: Tensor = None, cond: Tensor = None, loss_type: str = "FM-OT",
                  diff_config: Mapping = {"max_sr": 0.999, "min_sr": 0.02}):
         super().__init__()
-        if loss_type == "diffusion":
-            raise NotImplementedError("loss_type='diffusion' is out of scope of the B200 hot path")
         self.model, self.mask, self.cond, self.loss_type = model, mask, cond, loss_type
+        if loss_type == "diffusion":
+            from .components.diffusion import VPDiffusionSchedule
+            self.diff_sched = VPDiffusionSchedule(**diff_config)
 
     def forward(self, t, x, *args, **kwargs):
+        if self.loss_type == "diffusion":      # probability-flow ODE drift (:62-69); sampling uses the fused program instead
+            shape = [-1] + [1] * (x.dim() - 1)
+            _, noise_rates = self.diff_sched(t.view(shape))
+            betas = self.diff_sched.get_betas(t.view(shape))
+            return -0.5 * betas * (x - self.model(t, x, mask=self.mask, cond=self.cond) / noise_rates)
         return self.model(t, x, mask=self.mask, cond=self.cond)
 
 
@@ -164,11 +170,13 @@ class CNF(nn.Module):
     def decode(self, z: Tensor, cond: Tensor, mask: Tensor = None, ode_solver: str = "dopri5_zuko",
                ode_steps: int = 100) -> Tensor:
         """Integrate from t=1 (noise) to t=0 (data) -- one fused CUDA launch for all steps."""
+        if self.loss_type == "diffusion":
+            return self._decode_diffusion(z, cond, mask, ode_solver, ode_steps)
+        if ode_solver in ("em", "ddim"):
+            raise SyntaxError(f"Solver {ode_solver} is only implemented for diffusion loss")      # :328-329
         if ode_solver not in FIXED_STEP_SOLVERS:
             raise NotImplementedError(f"ode_solver={ode_solver!r}: the B200 path implements the fixed-step "
                                       f"{FIXED_STEP_SOLVERS} solvers (the reference's generation configs use midpoint)")
-        if self.loss_type == "diffusion":
-            raise NotImplementedError("loss_type='diffusion' is out of scope of the B200 hot path")
         key = (ode_steps, ode_solver)
         cache = self.__dict__.setdefault("_grid_cache", {})
         if key not in cache:
@@ -186,6 +194,78 @@ class CNF(nn.Module):
         takes = self.net.t_local_cat or self.net.t_global_cat
         return eng.sample(z, mask, cond, codes if takes else None, codes if self.add_time_to_input else None, dt,
                           ode_solver)
+
+
+def _diffusion_program(cnf, ode_solver: str, ode_steps: int):
+    """Per-evaluation (times, coefficient rows, dt) of the diffusion samplers, computed on the CPU in fp32 with the
+    reference's own recurrences so that the time codes and schedule values round the same way:
+      ddim  solver.py:60-92   diff_times = 1, then ``diff_times - step_size`` per step; rates at t and at t - step
+      em    solver.py:112-133 t = 1, ``t -= delta_t``; betas(t), noise_rate(t), delta_t, sqrt(betas * delta_t)
+      euler / midpoint        the torchdyn grid of ``fixed_step_grid`` with the drift of ode_wrapper.forward :62-69"""
+    from .components.diffusion import VPDiffusionSchedule
+    sched = VPDiffusionSchedule(**cnf.diff_config)
+    if ode_solver == "ddim":
+        step = 1 / ode_steps
+        t = torch.ones(1)
+        nsr, nnr = sched(t.view(-1, 1, 1))
+        times, rows = [], []
+        for _ in range(ode_steps):
+            sr, nr = nsr, nnr
+            times.append(t[0].clone())
+            t = t - step
+            nsr, nnr = sched(t.view(-1, 1, 1))
+            rows.append(torch.stack([sr.reshape(()), nr.reshape(()), nsr.reshape(()), nnr.reshape(())]))
+        return torch.stack(times), torch.stack(rows), None
+    if ode_solver == "em":
+        delta_t = 1 / ode_steps
+        t = torch.ones(1)
+        times, rows = [], []
+        for _ in range(ode_steps):
+            times.append(t[0].clone())
+            _, nr = sched(t.view(-1, 1, 1))
+            betas = sched.get_betas(t.view(-1, 1, 1))
+            rows.append(torch.stack([betas.reshape(()), nr.reshape(()), torch.tensor(delta_t, dtype=torch.float32),
+                                     (betas * delta_t).sqrt().reshape(())]))
+            t = t - delta_t                      # the reference's in-place ``t -= delta_t``: same fp32 arithmetic
+        return torch.stack(times), torch.stack(rows), None
+    t_eval, dt = fixed_step_grid(ode_steps, ode_solver)
+    tv = t_eval.view(-1, 1, 1)
+    _, nr = sched(tv)
+    betas = sched.get_betas(tv)
+    z = torch.zeros_like(t_eval)
+    return t_eval, torch.stack([betas.reshape(-1), nr.reshape(-1), z, z], dim=1), dt
+
+
+def _cnf_decode_diffusion(self, z, cond, mask, ode_solver, ode_steps):
+    """CNF.decode for loss_type == 'diffusion' (flow_matching_module.py:245-329): DDIM / Euler-Maruyama samplers and the
+    probability-flow ODE (euler / midpoint) as step programs of the single-launch integrator."""
+    if ode_solver not in ("em", "ddim") + FIXED_STEP_SOLVERS:
+        raise NotImplementedError(f"ode_solver={ode_solver!r} with the diffusion loss: the B200 path implements "
+                                  f"'em', 'ddim' and the fixed-step {FIXED_STEP_SOLVERS} probability-flow ODE")
+    from .components.epic import EPiC_encoder
+    if not isinstance(self.net, EPiC_encoder):
+        raise NotImplementedError("the diffusion samplers of the B200 path run on the EPiC vector field")
+    key = ("diffusion", ode_steps, ode_solver)
+    cache = self.__dict__.setdefault("_grid_cache", {})
+    if key not in cache:
+        t_eval, coef, dt = _diffusion_program(self, ode_solver, ode_steps)
+        cache[key] = (self.time_code(t_eval), coef, dt)
+    codes, coef, dt = cache[key]
+    eng = self.net.engine(force_sync=True)
+    if eng.precision != "fp32":
+        eng.set_precision("fp32")             # the step programs live in the fp32 kernel
+        self.net.precision = "fp32"
+    takes = self.net.t_local_cat or self.net.t_global_cat
+    noise = None
+    if ode_solver == "em":
+        # solver.py:131 draws torch.randn_like(x_t) on the device at every step: same generator, same call sequence
+        noise = torch.stack([torch.randn_like(z) for _ in range(ode_steps)])
+    kind = {"em": "em", "ddim": "ddim"}.get(ode_solver, "pf_ode")
+    return eng.sample_diffusion(z, mask, cond, codes if takes else None, codes if self.add_time_to_input else None, coef,
+                                kind, solver=ode_solver if kind == "pf_ode" else "euler", dt=dt, noise=noise)
+
+
+CNF._decode_diffusion = _cnf_decode_diffusion
 
 
 class SetFlowMatchingLitModule(_LightningBase):

@@ -76,14 +76,16 @@ def test_unsupported_options_raise():
     from particle_fm_b200.models.flow_matching_module import SetFlowMatchingLitModule as M
     small = dict(hidden_dim=8, layers=1, latent=4, frequencies=2)
     for kw in (dict(model="mdma"), dict(model="droid_fulltransformer"), dict(use_normaliser=True),
-               dict(t_emb="gaussian"), dict(dropout=0.1), dict(loss_type="diffusion"), dict(loss_type="CFM-OT"),
+               dict(t_emb="gaussian"), dict(dropout=0.1), dict(loss_type="no_such_loss"),
                dict(n_transforms=2), dict(activation="relu"), dict(wrapper_func="spectral_norm")):
         with pytest.raises(NotImplementedError):
             M(optimizer=None, **{**small, **kw})
     m = M(optimizer=None, **small)
-    for solver in ("dopri5_zuko", "rk4", "dopri5", "tsit5", "em"):
+    for solver in ("dopri5_zuko", "rk4", "dopri5", "tsit5"):
         with pytest.raises(NotImplementedError):
             m.forward(torch.zeros(1, 3, 3), reverse=True, ode_solver=solver)
+    with pytest.raises(SyntaxError):       # "em" / "ddim" without the diffusion loss: flow_matching_module.py:328-329
+        m.forward(torch.zeros(1, 3, 3), reverse=True, ode_solver="em")
     assert m.hparams.num_particles == 150 and m.hparams.loss_type == "FM-OT" and m.conditioned is False
 
 
