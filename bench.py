@@ -331,6 +331,7 @@ def main():
     # ---- end to end through the public API: CPU noise, H2D of inputs, integration, D2H of the result ----
     e2e_steps = max(1, min(args.steps, 3))
     latency_ms = None
+    gen_data = None
     if world == 1:
         mask_pin = mask_h.pin_memory()
         res_pin = torch.empty(B, N_PART, FEATS).pin_memory()                            # the result lands in pinned host memory
@@ -347,6 +348,19 @@ def main():
         e2e_s = time.perf_counter() - t0
         e2e_api = ("SetFlowMatchingLitModule.sample(n, mask=pinned) copied to a pinned host buffer (CPU noise draw, H2D, "
                    "integration, D2H inside the timed region); back-to-back calls, the CPU draw of call k+1 overlaps the GPU work of call k")
+        # the caller one level up: generate_data (batching + inverse normalisation + masking), post-processing on the device,
+        # results written by the kernel into one pinned host buffer
+        from particle_fm_b200.utils.data_generation import generate_data
+        gd_kw = dict(batch_size=B // 4, device=str(dev), variable_set_sizes=True, mask=mask_pin, normalized_data=True, normalize_sigma=5,
+                     means=[0.0, 0.0, 0.02], stds=[0.1, 0.1, 0.03], verbose=False, ode_solver=SOLVER, ode_steps=ODE_STEPS)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gd_out, _ = generate_data(model, B, **gd_kw)
+        gd_s = time.perf_counter() - t0
+        gen_data = {"value": B / gd_s, "unit": "jets/s", "jets": B, "batch_size": B // 4,
+                    "api": "particle_fm_b200.utils.data_generation.generate_data(model, n, batch_size, mask, normalized_data=True, ...): "
+                           "4 batches, device post-processing straight into one pinned host buffer, whole call timed on the host clock"}
+        assert gd_out.shape == (B, N_PART, FEATS)
     else:
         # N > 1: the product launcher on host inputs -- every rank draws its noise blocks, copies them and its mask slice
         # to its GPU, integrates, the slices are gathered to rank 0 and copied into pinned host memory
@@ -427,7 +441,7 @@ def main():
                            "parallelism": f"jets sharded x{world}, final gather to rank 0"},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": e2e_api, "single_call_latency_ms": latency_ms},
+                        "steps": e2e_steps, "api": e2e_api, "single_call_latency_ms": latency_ms, "generate_data": gen_data},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
