@@ -153,7 +153,7 @@ def time_cpu(run, n_jets, seed, reps=1):
     return n_jets / dt, dt, float(n_real.float().mean())
 
 
-def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
+def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024, mode="auto"):
     """Secondary metric (BASELINE.json: "train jets/s"): full training steps of the default JetNet-150 net --
     fused FM-OT loss forward+backward (fp32 kernels), flat-gradient all-reduce over the ranks, global-norm clip 0.5,
     AdamW(1e-3, wd 5e-5) (configs/model/flow_matching.yaml:3-7, experiment gradient_clip_val 0.5).  Weak scaling:
@@ -167,6 +167,7 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
     x = (5.0 * torch.randn(B, N_PART, FEATS, generator=g) * mask_h).to(dev)
     mask = mask_h.to(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-5)
+    model.flows[0].net.engine().set_train_mode(mode)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -193,7 +194,10 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024):
     ms = float(ms.item())
     return {"value": world * B * steps / (ms / 1e3), "unit": "jets/s", "batch_per_gpu": B, "steps": steps,
             "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss.detach()),
-            "step": "fused loss fwd+bwd (fp32 CUDA cores; weight gradients on tcgen05, 3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + clip 0.5 + AdamW",
+            "step": ("loss fwd+bwd with the per-particle GEMMs and their transposes on tcgen05 (3-term bf16 split, fp32-accurate), per-jet "
+                     "MLPs on CUDA cores" if mode == "auto" else "fused loss fwd+bwd on fp32 CUDA cores") +
+                    "; weight gradients on tcgen05 (3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + clip 0.5 + AdamW",
+            "kernels": mode,
             "mean_real_particles": float(n_real.float().mean())}
 
 
@@ -414,6 +418,10 @@ def main():
     train = None
     if not args.no_train:
         train = train_bench(model, dev, world, rank)
+        if world == 1:         # A/B: the fused fp32 CUDA-core kernels of round 1
+            cc = train_bench(model, dev, world, rank, mode="cuda_cores")
+            train["cuda_core_kernels"] = {k: cc[k] for k in ("value", "unit", "ms_per_step")}
+            model.flows[0].net.engine().set_train_mode("auto")
         if world > 1:          # also the strong-scaling figure, global batch 1024 split over the ranks
             strong = train_bench(model, dev, world, rank, B=max(1, 1024 // world))
             train["strong_scaling"] = {k: strong[k] for k in ("value", "unit", "batch_per_gpu", "ms_per_step")}

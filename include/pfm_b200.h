@@ -136,6 +136,20 @@ int pfm_epic_sample(pfm_epic* h, float* x_inout, const float* mask, const float*
  * --------------------------------------------------------------------------------------------- */
 long long pfm_epic_grad_size(const pfm_epic* h);
 
+/* Arithmetic of the training kernels (results are fp32-accurate in both modes: loss 1e-5, gradients 1e-4 against autograd).
+ * PFM_TRAIN_AUTO (default): with hid == 128 the 128 x 128 per-particle linears and their transposes run on tcgen05 tensor
+ * cores with the 3-term bf16 split (x = hi + lo; the dropped lo*lo term is 2^-16 relative), fp32 accumulation in TMEM,
+ * as a program of kernels over the packed real particles of the batch (csrc/epic_train_tc.cu); other widths use the
+ * fused fp32 CUDA-core kernels.  PFM_TRAIN_CUDA_CORES forces the latter (A/B runs, strict comparisons). */
+typedef enum { PFM_TRAIN_AUTO = 0, PFM_TRAIN_CUDA_CORES = 1 } pfm_train_mode;
+int pfm_epic_set_train_mode(pfm_epic* h, int mode /* pfm_train_mode */);
+/* Test hook: synchronise the device and copy n floats of a training array of the last forward / backward to HOST memory.
+ * which: 0 saved post-activations act[stage][row][hid_p], 1 pre-activation gradients dact (same shape), 2 per-jet
+ * effective-bias gradients [B][bias row], 3 saved per-jet vectors, 4 head gradient seed [row][feats], 5 network input
+ * [row][Kx]; rows = packed real particles in batch order.  Used by the parity tests to tell apart arithmetic error from
+ * a leaky_relu kink taken on different sides by two fp32 evaluation orders. */
+int pfm_epic_debug_copy(pfm_epic* h, int which, float* host, long long n);
+
 /* Data-parallel overlap: the weight gradients of the last backward are produced in pfm_epic_grad_chunks() consecutive
  * slices of the flat buffer (offset / count in floats).  pfm_epic_stream_wait_grad_chunk makes `stream` wait until slice
  * i is complete, so the host can enqueue the all-reduce of slice i on a side stream while later slices are still being

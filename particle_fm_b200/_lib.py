@@ -47,6 +47,8 @@ _SIGNATURES = {
     "pfm_epic_linear_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pfm_epic_set_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "pfm_epic_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "pfm_epic_set_train_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "pfm_epic_debug_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]),
     "pfm_epic_forward": (C.c_int, [C.c_void_p, _F, C.c_int, _F, _F, _F, _F, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_sample": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pfm_epic_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -600,8 +600,8 @@ static int launch_bwd(const BwdShape& s, int grid, cudaStream_t st) {
 
 __global__ void reset_counter_kernel(int* counter) { *counter = 0; }
 
-int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
-  const pfm_epic_cfg& c = h->cfg;
+// per-particle / per-jet pre-activation gradients on the fp32 CUDA-core kernel
+static int train_backward_simt(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   int R_f, J_f, TC, RB, KC;
   int rc = simt_caps_for_train(h, a.N, &R_f, &J_f, &TC, &RB, &KC);
   if (rc != PFM_OK) return rc;
@@ -636,6 +636,13 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   else rc = launch_bwd<10, 8>(s, grid, st);
   if (rc != PFM_OK) return rc;
   h->last_launches += 2;
+  return PFM_OK;
+}
+
+int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  int rc = tt_enabled(h) ? tt_train_backward(h, a, st) : train_backward_simt(h, a, st);     // tensor-core path: epic_train_tc.cu
+  if (rc != PFM_OK) return rc;
   if (!a.grad_flat) return PFM_OK;
 
   // ---- weight-gradient job table ----

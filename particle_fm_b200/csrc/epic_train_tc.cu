@@ -1,0 +1,756 @@
+// Training forward / backward of the EPiC vector field with the per-particle GEMMs on the tensor cores (hid == 128).
+//
+// In training every activation has to reach HBM anyway (the backward needs it), so unlike the sampler the network is NOT
+// kept resident in one CTA: it runs as a short program of kernels over the PACKED real particles of the whole batch,
+//   rowlin_tc_kernel   Y[rows,128] = epi( pro(X)[rows,128] . W^T )            every 128 x 128 per-particle linear and its
+//                      transpose (dX = dY . W), tcgen05.mma with fp32 accumulation in TMEM.  fp32 accuracy is kept with the
+//                      3-term split x = hi + lo (two bf16): X W^T ~ Xh Wh^T + Xh Wl^T + Xl Wh^T (the dropped Xl Wl^T term is
+//                      2^-16 relative), so loss and gradients stay inside the fp32 gates (1e-5 / 1e-4) of the CUDA-core path.
+//                      Prologue (fused into the operand load): + per-jet broadcast vector, * leaky_relu'(saved activation),
+//                      write-back of the masked gradient.  Epilogue: + per-jet effective bias, + residual, leaky_relu,
+//                      * leaky_relu'(saved activation).
+//   per-jet kernels    pooling + global MLP + effective biases (forward) and their backward, one CTA per jet, CUDA cores
+//                      (1% of the FLOPs), plus the K = 3 stem / N = 3 head.
+// Bound: HBM.  One 128-row tile moves 64 KB in and 64 KB out per operand array against 24 MMAs (1.5 k cycles).
+// The kernels fill the SAME saved-activation / gradient arrays as the fp32 CUDA-core kernels (epic_simt.cu TRAIN,
+// epic_train.cu), so the weight-gradient jobs (xty_tc.cu) and the weight-norm chain rule are shared.
+// Reference: autograd over EPiC_encoder.forward / EPiC_layer.forward (epic.py:304-391, 85-203) and the flow-matching
+// losses (losses.py:38-77, 101-136, 308-342).
+#include <cstdlib>
+#include <cstring>
+
+#include "pfm_internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace pfm {
+
+using namespace tc;
+
+static constexpr int TT_H = 128;
+static constexpr uint32_t TT_IMG = 32768;          // one bf16 128 x 128 K-major SW128 image
+
+__device__ __forceinline__ float tt_lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+__device__ __forceinline__ float tt_dlrelu(float post, float s) { return post > 0.f ? 1.f : s; }
+
+// ---------------------------------------------------------------------------------------------
+// weight images: for GEMM g (0 = fc_l2, 1 + 2l = fc_local1 main block, 2 + 2l = fc_local2)
+//   [g][0] forward  B[n = o][k]     = W[o][m_off + k]     (Y = X . W^T)
+//   [g][1] backward B[n = k][K = o] = W[o][m_off + k]     (dX = dY . W)
+// each as a hi image followed by a lo image (W = hi + lo in bf16)
+// ---------------------------------------------------------------------------------------------
+struct TtImgSrc { const float* Wt; int ldo; int k0; };   // W[o][k] = Wt[(k0 + k) * ldo + o]
+
+__global__ void tt_pack_kernel(const TtImgSrc* __restrict__ src, uint8_t* __restrict__ img) {
+  const TtImgSrc S = src[blockIdx.x >> 1];
+  const int transposed = blockIdx.x & 1;
+  uint8_t* hi = img + (size_t)blockIdx.x * 2 * TT_IMG;
+  uint8_t* lo = hi + TT_IMG;
+  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) {
+    const int k = i >> 7, o = i & 127;                   // consecutive threads -> consecutive o: coalesced reads
+    const float w = S.Wt[(size_t)(S.k0 + k) * S.ldo + o];
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const uint32_t off = transposed ? sw128_offset(k, o, 16384) : sw128_offset(o, k, 16384);
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rowlin_tc_kernel
+// ---------------------------------------------------------------------------------------------
+struct RowLinP {
+  const float* X;          // [rows][128]
+  const float* bc;         // [B][128] per-jet vector added to X (nullptr: none)
+  const float* S;          // [rows][128] saved post-activation: X' = (X + bc) * leaky_relu'(S) (nullptr: none)
+  float* Xout;             // [rows][128] X' written back (nullptr: none)
+  const uint8_t* Wimg;     // hi | lo
+  const float* bias;       // per-jet effective bias rows, already offset to the linear's slice (nullptr: none)
+  int bias_ld;
+  const float* R;          // [rows][128] residual added before the activation (nullptr: none)
+  int r_is_xout;           // the residual is this launch's own Xout
+  const float* E;          // [rows][128] saved post-activation: Y *= leaky_relu'(E) (nullptr: none)
+  int act;                 // leaky_relu on the result
+  float* Y;                // [rows][128]
+  const int* rowjet;       // [rows]
+  const int* n_total;
+  float slope;
+};
+
+struct RowLinSmem {
+  alignas(1024) uint8_t W[2][TT_IMG];
+  alignas(1024) uint8_t A[2][2][TT_IMG];        // [buffer][hi, lo]
+  uint64_t mbar_w, mbar[2];
+  uint32_t tmem;
+};
+
+__global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
+  extern __shared__ uint8_t smem_raw[];
+  RowLinSmem& s = *reinterpret_cast<RowLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = *p.n_total;
+  const int n_tiles = (rows + 127) >> 7;
+  if ((int)blockIdx.x >= n_tiles) return;                 // uniform, before any barrier / allocation
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) tmem_alloc(&s.tmem, 256);
+  if (tid == 0) {
+    mbar_init(&s.mbar_w, 1); mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&s.mbar_w, 2 * TT_IMG);
+    bulk_copy_g2s(s.W[0], p.Wimg, TT_IMG, &s.mbar_w);
+    bulk_copy_g2s(s.W[1], p.Wimg + TT_IMG, TT_IMG, &s.mbar_w);
+  }
+  const uint32_t tm = s.tmem;
+  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+
+  // unit = half a tile (64 rows): 8 float4 of X (and of S) per thread in flight
+  float4 xv[8], sv[8];
+  auto fetch = [&](int u) {
+    const int tile = (int)blockIdx.x + (u >> 1) * (int)gridDim.x;
+    const int r0 = tile * 128 + (u & 1) * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + 256 * i, r = r0 + (idx >> 5), c = (idx & 31) * 4;
+      if (r < rows) {
+        xv[i] = __ldcg(reinterpret_cast<const float4*>(p.X + (size_t)r * TT_H + c));
+        if (p.S) sv[i] = __ldcg(reinterpret_cast<const float4*>(p.S + (size_t)r * TT_H + c));
+      } else {
+        xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sv[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    }
+  };
+  auto store = [&](int u) {
+    const int t_local = u >> 1;
+    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+    const int r0 = tile * 128 + (u & 1) * 64;
+    uint8_t* hi = s.A[t_local & 1][0];
+    uint8_t* lo = s.A[t_local & 1][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + 256 * i, rl = (u & 1) * 64 + (idx >> 5), r = r0 + (idx >> 5), c = (idx & 31) * 4;
+      float4 v = xv[i];
+      if (r < rows) {
+        if (p.bc) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bc + (size_t)p.rowjet[r] * TT_H + c));
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (p.S) {
+          v.x *= tt_dlrelu(sv[i].x, p.slope); v.y *= tt_dlrelu(sv[i].y, p.slope);
+          v.z *= tt_dlrelu(sv[i].z, p.slope); v.w *= tt_dlrelu(sv[i].w, p.slope);
+        }
+        if (p.Xout) __stcg(reinterpret_cast<float4*>(p.Xout + (size_t)r * TT_H + c), v);
+      }
+      const uint32_t off = sw128_offset(rl, c, 16384);
+      const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z),
+                          hw = __float2bfloat16_rn(v.w);
+      uint2 h2, l2;
+      h2.x = pack_bf16x2(v.x, v.y); h2.y = pack_bf16x2(v.z, v.w);
+      l2.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
+      l2.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
+      *reinterpret_cast<uint2*>(hi + off) = h2;
+      *reinterpret_cast<uint2*>(lo + off) = l2;
+    }
+  };
+  auto epilogue = [&](int t_local) {
+    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+    mbar_wait(&s.mbar[t_local & 1], (uint32_t)((t_local >> 1) & 1));
+    tc_fence_after();
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = tile * 128 + q * 32 + lane;
+    const bool ok = r < rows;
+    const int jet = ok ? p.rowjet[r] : 0;
+    const float* res = p.r_is_xout ? p.Xout : p.R;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t v[32];
+      const int o0 = hf * 64 + j * 32;
+      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 a = make_float4(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]), __uint_as_float(v[i4 * 4 + 2]),
+                                 __uint_as_float(v[i4 * 4 + 3]));
+          const int o = o0 + i4 * 4;
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (res) {
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(res + (size_t)r * TT_H + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
+          if (p.E) {
+            const float4 e = __ldcg(reinterpret_cast<const float4*>(p.E + (size_t)r * TT_H + o));
+            a.x *= tt_dlrelu(e.x, p.slope); a.y *= tt_dlrelu(e.y, p.slope); a.z *= tt_dlrelu(e.z, p.slope); a.w *= tt_dlrelu(e.w, p.slope);
+          }
+          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+        }
+      }
+    }
+    tc_fence_before();
+  };
+
+  const int n_units = 2 * my_tiles;
+  fetch(0);
+  mbar_wait(&s.mbar_w, 0);                                 // weights have landed (async proxy write: visible to the MMAs)
+  for (int u = 0; u < n_units; ++u) {
+    store(u);
+    if (u + 1 < n_units) fetch(u + 1);
+    if (u & 1) {
+      const int t_local = u >> 1;
+      fence_proxy_async();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ah = desc_kmajor(smem_u32(s.A[t_local & 1][0])), al = desc_kmajor(smem_u32(s.A[t_local & 1][1]));
+          const uint64_t wh = desc_kmajor(smem_u32(s.W[0])), wl = desc_kmajor(smem_u32(s.W[1]));
+          const uint32_t acc = tm + (uint32_t)((t_local & 1) * 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t d = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+            mma_ss(acc, ah + d, wh + d, idesc, k ? 1u : 0u);
+            mma_ss(acc, ah + d, wl + d, idesc, 1u);
+            mma_ss(acc, al + d, wh + d, idesc, 1u);
+          }
+          mma_commit(&s.mbar[t_local & 1]);
+        }
+        __syncwarp();
+      }
+      if (t_local >= 1) epilogue(t_local - 1);             // overlaps the MMAs of this tile and the loads of the next
+    }
+  }
+  epilogue(my_tiles - 1);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+// rowjet[rowoff[j] + r] = j
+__global__ void tt_rowjet_kernel(const int* __restrict__ n_real, const int* __restrict__ rowoff, int B, int* __restrict__ rowjet) {
+  const int j = blockIdx.x;
+  if (j >= B) return;
+  const int n = n_real[j], r0 = rowoff[j];
+  for (int r = threadIdx.x; r < n; r += blockDim.x) rowjet[r0 + r] = j;
+}
+
+// beff[j][:] = tbias[row(j)][:] + cbias[j][:]      (effective bias of every linear before the global-vector term)
+__global__ void tt_beff_kernel(const float* __restrict__ tbias, int per_jet, const float* __restrict__ cbias, int bstride,
+                               float* __restrict__ beff) {
+  const int j = blockIdx.x;
+  const float* tb = tbias + (size_t)(per_jet ? j : 0) * bstride;
+  for (int i = threadIdx.x; i < bstride; i += blockDim.x)
+    beff[(size_t)j * bstride + i] = tb[i] + (cbias ? cbias[(size_t)j * bstride + i] : 0.f);
+}
+
+struct TtCommon {
+  const Lin* lin; int n_lin, L, H, Z, F, Kx, xin_off, N, B, bstride;
+  float sum_scale, slope;
+  const int* n_real; const uint16_t* ridx; const int* rowoff; const int* n_total; const int* rowjet;
+  float* act; float* dact; size_t stage_stride;
+  float* yact; float* jact; int junit, jstride, LDP, Hp, Zp;
+  float* dpre3; float* dbeff; float* beff; float* bc; float* dGc; float* dhbuf; float* dxs;
+  float* loss_acc;
+  // loss inputs
+  const float* x_in; float* x_out; const float* tjet; const float* noise0; const float* noise1; int loss_kind; float sigma;
+};
+
+// stem: y (flow-matching interpolation or the given input) -> yact;  h1 = lrelu(fc_l1(y)) -> act[0].  One warp per row.
+__global__ void __launch_bounds__(256) tt_stem_kernel(const TtCommon p) {
+  const int lane = threadIdx.x & 31;
+  const int rows = *p.n_total;
+  const Lin L1 = p.lin[LIN_L1];
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+    const int j = p.rowjet[r];
+    const int part = p.ridx[(size_t)j * p.N + (r - p.rowoff[j])];
+    float4 a = *reinterpret_cast<const float4*>(p.beff + (size_t)j * p.bstride + L1.bias_off + lane * 4);
+    for (int c = 0; c < p.Kx; ++c) {
+      const size_t gi = ((size_t)j * p.N + part) * p.Kx + c;
+      float y;
+      if (p.loss_kind >= 0) {                                  // losses.py:56, :115-116, :320
+        const float x = p.x_in[gi], t = p.tjet[j], z = p.noise0[gi];
+        if (p.loss_kind == PFM_LOSS_FM_OT) y = (1.f - t) * x + (p.sigma + (1.f - p.sigma) * t) * z;
+        else if (p.loss_kind == PFM_LOSS_CFM) y = ((1.f - t) * x + t * z) + p.sigma * p.noise1[gi];
+        else y = x + t * z;
+      } else {
+        y = p.x_in[gi];
+      }
+      if (lane == 0) p.yact[(size_t)r * p.Kx + c] = y;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(L1.Wt + (size_t)(L1.m_off + p.xin_off + c) * L1.ldo + lane * 4));
+      a.x = fmaf(w.x, y, a.x); a.y = fmaf(w.y, y, a.y); a.z = fmaf(w.z, y, a.z); a.w = fmaf(w.w, y, a.w);
+    }
+    a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope);
+    *reinterpret_cast<float4*>(p.act + (size_t)r * TT_H + lane * 4) = a;
+  }
+}
+
+// Forward of one per-jet unit (unit 0 = stem fc_g1 / fc_g2, unit l+1 = EPiC layer l): pooling of the unit's input h,
+// global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).  One CTA (128 threads) per jet.
+__global__ void __launch_bounds__(128) tt_jet_fwd_kernel(const TtCommon p, int unit) {
+  __shared__ float pool[2 * TT_H + 32];
+  __shared__ float g1s[TT_H];
+  __shared__ float gs[32];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int H = p.H, Z = p.Z;
+  const int n = p.n_real[j], r0 = p.rowoff[j];
+  const int l = unit - 1;
+  const Lin Ga = p.lin[unit == 0 ? LIN_G1 : LIN_LAYER0 + 4 * l + 0];
+  const Lin Gb = p.lin[unit == 0 ? LIN_G2 : LIN_LAYER0 + 4 * l + 1];
+  float* ja = p.jact + (size_t)j * p.jstride + (size_t)unit * p.junit;
+  const float* h = p.act + (size_t)(unit == 0 ? 1 : 1 + 2 * l) * p.stage_stride;
+  {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= n; r += 4) {
+      s0 += __ldcg(h + (size_t)(r0 + r) * TT_H + tid);     s1 += __ldcg(h + (size_t)(r0 + r + 1) * TT_H + tid);
+      s2 += __ldcg(h + (size_t)(r0 + r + 2) * TT_H + tid); s3 += __ldcg(h + (size_t)(r0 + r + 3) * TT_H + tid);
+    }
+    for (; r < n; ++r) s0 += __ldcg(h + (size_t)(r0 + r) * TT_H + tid);
+    const float sum = (s0 + s1) + (s2 + s3);
+    const float mean = sum / (float)n, ssum = sum * p.sum_scale;
+    if (unit == 0) { pool[tid] = ssum; pool[H + tid] = mean; }       // (sum, mean) in the stem, epic.py:373
+    else { pool[tid] = mean; pool[H + tid] = ssum; }                 // (mean, sum, global) in the layers, :164-171
+    ja[tid] = pool[tid]; ja[H + tid] = pool[H + tid];
+    if (unit > 0 && tid < Z) {
+      const float g = p.jact[(size_t)j * p.jstride + (size_t)(unit - 1) * p.junit + p.LDP + p.Hp + tid];   // previous unit's output
+      pool[2 * H + tid] = g; ja[2 * H + tid] = g;
+    }
+  }
+  __syncthreads();
+  {
+    const int K = 2 * H + (unit > 0 ? Z : 0);
+    const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + tid;
+    float a0 = p.beff[(size_t)j * p.bstride + Ga.bias_off + tid], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+      a0 = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], a0);           a1 = fmaf(__ldg(w + (size_t)(k + 1) * Ga.ldo), pool[k + 1], a1);
+      a2 = fmaf(__ldg(w + (size_t)(k + 2) * Ga.ldo), pool[k + 2], a2); a3 = fmaf(__ldg(w + (size_t)(k + 3) * Ga.ldo), pool[k + 3], a3);
+    }
+    for (; k < K; ++k) a0 = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], a0);
+    const float g1 = tt_lrelu((a0 + a1) + (a2 + a3), p.slope);
+    g1s[tid] = g1;
+    ja[p.LDP + tid] = g1;
+  }
+  __syncthreads();
+  {   // fc_g2 / fc_global2: warp w handles outputs z = w, w + 4, ...; lanes split K
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int z = warp; z < Z; z += 4) {
+      float a = 0.f;
+      for (int k = lane; k < H; k += 32) a = fmaf(__ldg(Gb.Wt + (size_t)(Gb.m_off + k) * Gb.ldo + z), g1s[k], a);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+      if (lane == 0) {
+        a += p.beff[(size_t)j * p.bstride + Gb.bias_off + z];
+        if (unit > 0) a += pool[2 * H + z];                              // residual, epic.py:184-186
+        a = tt_lrelu(a, p.slope);
+        gs[z] = a;
+        ja[p.LDP + p.Hp + z] = a;
+      }
+    }
+  }
+  __syncthreads();
+  if (unit > 0) {   // effective bias of fc_local1: + W_glob . g   (the broadcast global vector, epic.py:189-196)
+    const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2];
+    float a = p.beff[(size_t)j * p.bstride + La.bias_off + tid];
+    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(La.Wt + (size_t)(La.g_off + z) * La.ldo + tid), gs[z], a);
+    p.beff[(size_t)j * p.bstride + La.bias_off + tid] = a;
+  }
+}
+
+// head: v = lrelu(fc_l3(h_L)); flow-matching target, squared error, gradient seed (losses.py:61-62, :75-76).  One warp per row.
+__global__ void __launch_bounds__(256) tt_head_kernel(const TtCommon p) {
+  const int lane = threadIdx.x & 31;
+  const int rows = *p.n_total;
+  const Lin L3 = p.lin[p.n_lin - 1];
+  const float* hL = p.act + (size_t)(1 + 2 * p.L) * p.stage_stride;
+  const float inv_n = 1.f / (float)rows;
+  float part = 0.f;
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+    const int j = p.rowjet[r];
+    const int pidx = p.ridx[(size_t)j * p.N + (r - p.rowoff[j])];
+    const float4 hv = __ldcg(reinterpret_cast<const float4*>(hL + (size_t)r * TT_H + lane * 4));
+    for (int f = 0; f < p.F; ++f) {
+      const float* w = L3.Wt + (size_t)(L3.m_off + lane * 4) * L3.ldo + f;
+      float a = hv.x * __ldg(w) + hv.y * __ldg(w + L3.ldo) + hv.z * __ldg(w + 2 * L3.ldo) + hv.w * __ldg(w + 3 * L3.ldo);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+      if (lane == 0) {
+        const float v = tt_lrelu(a + p.beff[(size_t)j * p.bstride + L3.bias_off + f], p.slope);
+        const size_t gi = ((size_t)j * p.N + pidx) * p.F + f;
+        if (p.loss_kind >= 0) {
+          const float x = p.x_in[gi], z = p.noise0[gi];
+          float u;
+          if (p.loss_kind == PFM_LOSS_FM_OT) u = (1.f - p.sigma) * z - x;
+          else if (p.loss_kind == PFM_LOSS_CFM) u = z - x;
+          else u = z;
+          const float d = v - u;
+          part += d * d;
+          p.dpre3[(size_t)r * p.F + f] = 2.f * d * inv_n * tt_dlrelu(v, p.slope);
+        } else {
+          p.x_out[gi] = v;
+          p.dpre3[(size_t)r * p.F + f] = tt_dlrelu(v, p.slope);      // the backward entry multiplies by the incoming gradient
+        }
+      }
+    }
+  }
+  if (p.loss_kind >= 0 && lane == 0 && part != 0.f) atomicAdd(p.loss_acc, part);
+}
+
+// head backward: dh_L[r][c] = sum_f dpre3[r][f] W3[f][c]
+__global__ void __launch_bounds__(256) tt_head_bwd_kernel(const TtCommon p) {
+  const int lane = threadIdx.x & 31;
+  const int rows = *p.n_total;
+  const Lin L3 = p.lin[p.n_lin - 1];
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f = 0; f < p.F; ++f) {
+      const float d = p.dpre3[(size_t)r * p.F + f];
+      const float* w = L3.Wt + (size_t)(L3.m_off + lane * 4) * L3.ldo + f;
+      a.x = fmaf(__ldg(w), d, a.x); a.y = fmaf(__ldg(w + L3.ldo), d, a.y);
+      a.z = fmaf(__ldg(w + 2 * L3.ldo), d, a.z); a.w = fmaf(__ldg(w + 3 * L3.ldo), d, a.w);
+    }
+    *reinterpret_cast<float4*>(p.dhbuf + (size_t)r * TT_H + lane * 4) = a;
+  }
+}
+
+// column sums over the rows of jet j of a [rows][128] array (thread = column)
+__device__ __forceinline__ float tt_colsum(const float* __restrict__ a, int r0, int n, int tid) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= n; r += 4) {
+    s0 += __ldcg(a + (size_t)(r0 + r) * TT_H + tid);     s1 += __ldcg(a + (size_t)(r0 + r + 1) * TT_H + tid);
+    s2 += __ldcg(a + (size_t)(r0 + r + 2) * TT_H + tid); s3 += __ldcg(a + (size_t)(r0 + r + 3) * TT_H + tid);
+  }
+  for (; r < n; ++r) s0 += __ldcg(a + (size_t)(r0 + r) * TT_H + tid);
+  return (s0 + s1) + (s2 + s3);
+}
+
+// Backward of one per-jet unit (mirrors epic_train.cu::global_backward and the code around it).  One CTA per jet.
+//   unit l+1: db1 / db2 = per-jet sums of the pre-activation gradients of fc_local1 / fc_local2 (-> dbeff),
+//             dG = carry + W_glob^T db1, then the global MLP backward; bc[j] = pooled gradient broadcast (overwritten)
+//   unit 0  : stem global MLP backward from the carry; bc[j] += broadcast (both units pool h0); also the head's bias gradient
+__global__ void __launch_bounds__(128) tt_jet_bwd_kernel(const TtCommon p, int unit, int with_head) {
+  __shared__ float db1[TT_H];
+  __shared__ float pg1[TT_H];
+  __shared__ float pg2[32];
+  __shared__ float dG[32];
+  __shared__ float din[2 * TT_H + 32];
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, Z = p.Z;
+  const int n = p.n_real[j], r0 = p.rowoff[j];
+  const int l = unit - 1;
+  const Lin Ga = p.lin[unit == 0 ? LIN_G1 : LIN_LAYER0 + 4 * l + 0];
+  const Lin Gb = p.lin[unit == 0 ? LIN_G2 : LIN_LAYER0 + 4 * l + 1];
+  const float* ja = p.jact + (size_t)j * p.jstride + (size_t)unit * p.junit;
+  float* dbe = p.dbeff + (size_t)j * p.bstride;
+  if (with_head) {
+    const Lin L3 = p.lin[p.n_lin - 1];
+    for (int f = warp; f < p.F; f += 4) {
+      float a = 0.f;
+      for (int r = lane; r < n; r += 32) a += p.dpre3[(size_t)(r0 + r) * p.F + f];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+      if (lane == 0) dbe[L3.bias_off + f] = a;
+    }
+  }
+  if (unit > 0) {
+    const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2], Lb = p.lin[LIN_LAYER0 + 4 * l + 3];
+    const float s1 = tt_colsum(p.dact + (size_t)(2 + 2 * l) * p.stage_stride, r0, n, tid);
+    const float s2 = tt_colsum(p.dact + (size_t)(3 + 2 * l) * p.stage_stride, r0, n, tid);
+    db1[tid] = s1;
+    dbe[La.bias_off + tid] = s1;
+    dbe[Lb.bias_off + tid] = s2;
+    __syncthreads();
+    for (int z = warp; z < Z; z += 4) {          // gradient w.r.t. the unit's new global vector: carry + W_glob^T . db1
+      const float* w = La.Wt + (size_t)(La.g_off + z) * La.ldo;
+      float a = 0.f;
+      for (int o = lane; o < H; o += 32) a = fmaf(__ldg(w + o), db1[o], a);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+      if (lane == 0) dG[z] = a + p.dGc[(size_t)j * p.Zp + z];
+    }
+  } else if (tid < Z) {
+    dG[tid] = p.dGc[(size_t)j * p.Zp + tid];
+  }
+  __syncthreads();
+  if (tid < Z) {
+    const float g = ja[p.LDP + p.Hp + tid];
+    const float v = dG[tid] * tt_dlrelu(g, p.slope);
+    pg2[tid] = v;
+    dbe[Gb.bias_off + tid] = v;
+  }
+  __syncthreads();
+  {
+    float a = 0.f;
+    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(Gb.Wr + (size_t)z * Gb.ldr + tid), pg2[z], a);
+    const float v = a * tt_dlrelu(ja[p.LDP + tid], p.slope);
+    pg1[tid] = v;
+    dbe[Ga.bias_off + tid] = v;
+  }
+  __syncthreads();
+  for (int k = tid; k < Ga.m_len; k += 128) {     // din[k] = sum_o W_a[o][m_off + k] pg1[o]
+    const float* wk = Ga.Wr + k;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int o = 0; o < H; o += 4) {
+      a0 = fmaf(__ldg(wk + (size_t)o * Ga.ldr), pg1[o], a0);           a1 = fmaf(__ldg(wk + (size_t)(o + 1) * Ga.ldr), pg1[o + 1], a1);
+      a2 = fmaf(__ldg(wk + (size_t)(o + 2) * Ga.ldr), pg1[o + 2], a2); a3 = fmaf(__ldg(wk + (size_t)(o + 3) * Ga.ldr), pg1[o + 3], a3);
+    }
+    din[k] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  {
+    const int o_mean = unit == 0 ? H : 0, o_sum = unit == 0 ? 0 : H;
+    const float v = din[o_mean + tid] / (float)n + p.sum_scale * din[o_sum + tid];
+    float* b = p.bc + (size_t)j * TT_H + tid;
+    *b = unit == 0 ? *b + v : v;
+  }
+  if (unit > 0 && tid < Z) p.dGc[(size_t)j * p.Zp + tid] = din[2 * H + tid] + pg2[tid];     // through fc_global1's global columns + residual
+}
+
+// stem tail: per-jet sums of the fc_l1 / fc_l2 pre-activation gradients, gradient w.r.t. the per-particle input columns
+__global__ void __launch_bounds__(128) tt_stem_bwd_kernel(const TtCommon p) {
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = p.n_real[j], r0 = p.rowoff[j];
+  const Lin L1 = p.lin[LIN_L1], L2 = p.lin[LIN_L2];
+  float* dbe = p.dbeff + (size_t)j * p.bstride;
+  dbe[L1.bias_off + tid] = tt_colsum(p.dact, r0, n, tid);
+  dbe[L2.bias_off + tid] = tt_colsum(p.dact + p.stage_stride, r0, n, tid);
+  if (p.dxs) {
+    for (int r = warp; r < n; r += 4) {
+      const float4 d = __ldcg(reinterpret_cast<const float4*>(p.dact + (size_t)(r0 + r) * TT_H + lane * 4));
+      for (int c = 0; c < p.Kx; ++c) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(L1.Wt + (size_t)(L1.m_off + p.xin_off + c) * L1.ldo + lane * 4));
+        float a = w.x * d.x + w.y * d.y + w.z * d.z + w.w * d.w;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+        if (lane == 0) p.dxs[(size_t)(r0 + r) * p.Kx + c] = a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool tt_enabled(const pfm_epic* h) {
+  static const int force_simt = getenv("PFM_TRAIN_SIMT") ? atoi(getenv("PFM_TRAIN_SIMT")) : 0;
+  const pfm_epic_cfg& c = h->cfg;
+  return !force_simt && h->train_mode != PFM_TRAIN_CUDA_CORES && c.hid == TT_H && c.latent <= 32 && c.feats <= 32;
+}
+
+static int tt_gemm_index_fwd(int g) { return 2 * g; }
+static int tt_gemm_index_bwd(int g) { return 2 * g + 1; }
+
+static int tt_pack(pfm_epic* h, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  const int n_gemm = 1 + 2 * c.layers;
+  const size_t bytes = (size_t)n_gemm * 2 * 2 * TT_IMG;
+  const size_t aux = sizeof(TtImgSrc) * n_gemm;
+  if (h->tt_bytes < bytes + aux) {
+    if (h->tt_store) cudaFree(h->tt_store);
+    h->tt_store = nullptr; h->tt_bytes = 0;
+    PFM_CUDA_CHECK(cudaMalloc(&h->tt_store, bytes + aux));
+    h->tt_bytes = bytes + aux;
+    std::vector<TtImgSrc> src(n_gemm);
+    auto mk = [&](int lin_idx) { const Lin& L = h->lin_host[lin_idx]; TtImgSrc s; s.Wt = L.Wt; s.ldo = L.ldo; s.k0 = L.m_off; return s; };
+    src[0] = mk(LIN_L2);
+    for (int l = 0; l < c.layers; ++l) { src[1 + 2 * l] = mk(LIN_LAYER0 + 4 * l + 2); src[2 + 2 * l] = mk(LIN_LAYER0 + 4 * l + 3); }
+    PFM_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->tt_store) + bytes, src.data(), aux, cudaMemcpyHostToDevice, st));
+    PFM_CUDA_CHECK(cudaStreamSynchronize(st));          // src is a host temporary (pointers into the handle's weight store: once per allocation)
+  }
+  tt_pack_kernel<<<n_gemm * 2, 256, 0, st>>>(reinterpret_cast<const TtImgSrc*>(reinterpret_cast<uint8_t*>(h->tt_store) + bytes),
+                                             reinterpret_cast<uint8_t*>(h->tt_store));
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->tt_dirty = false;
+  h->last_launches++;
+  return PFM_OK;
+}
+
+static int tt_workspace(pfm_epic* h, int B, int N) {
+  const int Zp = (h->cfg.latent + 3) & ~3;
+  const size_t rows = (size_t)B * N;
+  const size_t need = (size_t)B * h->bstride + (size_t)B * TT_H + (size_t)B * Zp + rows * TT_H + rows + 64;
+  if (h->tt_ws_cap < need) {
+    if (h->tt_ws) cudaFree(h->tt_ws);
+    h->tt_ws = nullptr; h->tt_ws_cap = 0;
+    PFM_CUDA_CHECK(cudaMalloc(&h->tt_ws, need * sizeof(float)));
+    h->tt_ws_cap = need;
+  }
+  return PFM_OK;
+}
+
+static void tt_common(pfm_epic* h, int B, int N, int Kx, int xin_off, const TrainLayout& lay, TtCommon* p) {
+  const pfm_epic_cfg& c = h->cfg;
+  memset(p, 0, sizeof(*p));
+  const int Zp = (c.latent + 3) & ~3;
+  p->lin = h->lin_dev; p->n_lin = h->n_lin; p->L = c.layers; p->H = c.hid; p->Z = c.latent; p->F = c.feats; p->Kx = Kx;
+  p->xin_off = xin_off; p->N = N; p->B = B; p->bstride = h->bstride; p->sum_scale = c.sum_scale; p->slope = c.neg_slope;
+  p->n_real = h->plan.n_real; p->ridx = h->plan.ridx; p->rowoff = h->plan.rowoff; p->n_total = h->plan.n_total;
+  p->act = h->act; p->dact = h->dact; p->stage_stride = lay.stage_stride;
+  p->yact = h->yact; p->jact = h->jact; p->junit = lay.junit; p->jstride = lay.jstride; p->LDP = lay.LDP; p->Hp = lay.Hp; p->Zp = lay.Zp;
+  p->dpre3 = h->dpre3; p->dbeff = h->dbeff; p->loss_acc = h->loss_acc;
+  float* w = h->tt_ws;
+  p->beff = w; w += (size_t)B * h->bstride;
+  p->bc = w; w += (size_t)B * TT_H;
+  p->dGc = w; w += (size_t)B * Zp;
+  p->dhbuf = w; w += (size_t)B * N * TT_H;
+  p->rowjet = reinterpret_cast<const int*>(w);
+}
+
+// Debug (PFM_TT_CHECK=1): recompute a rowlin launch on CUDA cores in fp32 from the raw fp32 weights and report the largest deviation.
+__global__ void rowlin_check_kernel(const RowLinP p, const float* __restrict__ Wt, int ldo, int k0, int transposed, float* __restrict__ maxerr) {
+  const int rows = *p.n_total;
+  const int r = blockIdx.x, o = threadIdx.x;
+  if (r >= rows) return;
+  const int jet = p.rowjet[r];
+  float a = 0.f;
+  for (int k = 0; k < 128; ++k) {
+    float x = p.X[(size_t)r * 128 + k];
+    if (p.bc) x += p.bc[(size_t)jet * 128 + k];
+    if (p.S) x *= tt_dlrelu(p.S[(size_t)r * 128 + k], p.slope);
+    // forward: W[o][k] = Wt[(k0 + k) * ldo + o];  transposed: contraction over the linear's outputs: W[k][o]
+    const float w = transposed ? Wt[(size_t)(k0 + o) * ldo + k] : Wt[(size_t)(k0 + k) * ldo + o];
+    a = fmaf(x, w, a);
+  }
+  if (p.bias) a += p.bias[(size_t)jet * p.bias_ld + o];
+  const float* res = p.r_is_xout ? p.Xout : p.R;
+  if (res) a += res[(size_t)r * 128 + o];
+  if (p.act) a = tt_lrelu(a, p.slope);
+  if (p.E) a *= tt_dlrelu(p.E[(size_t)r * 128 + o], p.slope);
+  const float d = fabsf(a - p.Y[(size_t)r * 128 + o]);
+  atomicMax(reinterpret_cast<int*>(maxerr), __float_as_int(d));
+  atomicMax(reinterpret_cast<int*>(maxerr + 1), __float_as_int(fabsf(a)));
+}
+
+static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const TtCommon& c, int grid, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = (int)sizeof(RowLinSmem) + 1024;
+  if (!attr) {
+    PFM_CUDA_CHECK(cudaFuncSetAttribute(rowlin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  q.Wimg = reinterpret_cast<const uint8_t*>(h->tt_store) + (size_t)(transposed ? tt_gemm_index_bwd(gemm) : tt_gemm_index_fwd(gemm)) * 2 * TT_IMG;
+  q.rowjet = c.rowjet; q.n_total = c.n_total; q.slope = c.slope;
+  rowlin_tc_kernel<<<grid, 256, smem, st>>>(q);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->last_launches++;
+  static const bool sync_each = getenv("PFM_TT_SYNC") != nullptr;
+  if (sync_each) PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+  static const bool check = getenv("PFM_TT_CHECK") != nullptr;
+  if (check) {
+    static float* dm = nullptr;
+    if (!dm) PFM_CUDA_CHECK(cudaMalloc(&dm, 8));
+    PFM_CUDA_CHECK(cudaMemsetAsync(dm, 0, 8, st));
+    const int lin_idx = gemm == 0 ? LIN_L2 : (LIN_LAYER0 + 4 * ((gemm - 1) >> 1) + 2 + ((gemm - 1) & 1));
+    const Lin& L = h->lin_host[lin_idx];
+    rowlin_check_kernel<<<c.B * c.N, 128, 0, st>>>(q, L.Wt, L.ldo, L.m_off, transposed, dm);
+    float hm[2];
+    PFM_CUDA_CHECK(cudaMemcpyAsync(hm, dm, 8, cudaMemcpyDeviceToHost, st));
+    PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[pfm tt check] gemm %2d %s max|err| %.3e  max|ref| %.3e\n", gemm, transposed ? "bwd" : "fwd", hm[0], hm[1]);
+  }
+  return PFM_OK;
+}
+
+// forward with saved activations (+ fused flow-matching loss): fills act / yact / jact / dpre3 / loss_acc like
+// epic_simt.cu's TRAIN instantiation
+int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  int rc = tt_workspace(h, a.B, a.N);
+  if (rc != PFM_OK) return rc;
+  if (!h->tt_store || h->tt_dirty) { rc = tt_pack(h, st); if (rc != PFM_OK) return rc; }
+  TtCommon p;
+  tt_common(h, a.B, a.N, a.Kx, a.xin_off, a.lay, &p);
+  p.x_in = a.x_in; p.x_out = a.x_out; p.tjet = a.t; p.noise0 = a.noise0; p.noise1 = a.noise1; p.loss_kind = a.loss_kind; p.sigma = a.sigma;
+  const size_t SS = a.lay.stage_stride;
+  const int grid_rows = 4 * h->sm_count;
+  const int grid_gemm = h->sm_count;
+  tt_rowjet_kernel<<<a.B, 64, 0, st>>>(h->plan.n_real, h->plan.rowoff, a.B, const_cast<int*>(p.rowjet));
+  tt_beff_kernel<<<a.B, 256, 0, st>>>(h->tbias, a.tbias_per_jet, a.has_cbias ? h->cbias : nullptr, h->bstride, p.beff);
+  if (a.loss_kind < 0) PFM_CUDA_CHECK(cudaMemsetAsync(a.x_out, 0, sizeof(float) * (size_t)a.B * a.N * c.feats, st));
+  tt_stem_kernel<<<grid_rows, 256, 0, st>>>(p);
+  h->last_launches += 3;
+  {   // fc_l2: h0 = lrelu(h1 . W^T + b + h1)     (epic.py:364-367)
+    RowLinP q; memset(&q, 0, sizeof(q));
+    q.X = h->act; q.R = h->act; q.bias = p.beff + h->lin_host[LIN_L2].bias_off; q.bias_ld = h->bstride; q.act = 1; q.Y = h->act + SS;
+    if ((rc = tt_rowlin(h, q, 0, 0, p, grid_gemm, st)) != PFM_OK) return rc;
+  }
+  tt_jet_fwd_kernel<<<a.B, 128, 0, st>>>(p, 0);
+  h->last_launches++;
+  for (int l = 0; l < c.layers; ++l) {
+    tt_jet_fwd_kernel<<<a.B, 128, 0, st>>>(p, l + 1);
+    h->last_launches++;
+    RowLinP q; memset(&q, 0, sizeof(q));      // fc_local1: u = lrelu(h . W1^T + beff1[jet])     (epic.py:194-196)
+    q.X = h->act + (size_t)(1 + 2 * l) * SS; q.bias = p.beff + h->lin_host[LIN_LAYER0 + 4 * l + 2].bias_off; q.bias_ld = h->bstride;
+    q.act = 1; q.Y = h->act + (size_t)(2 + 2 * l) * SS;
+    if ((rc = tt_rowlin(h, q, 1 + 2 * l, 0, p, grid_gemm, st)) != PFM_OK) return rc;
+    memset(&q, 0, sizeof(q));                 // fc_local2: h' = lrelu(u . W2^T + beff2[jet] + h)  (epic.py:198-200)
+    q.X = h->act + (size_t)(2 + 2 * l) * SS; q.R = h->act + (size_t)(1 + 2 * l) * SS;
+    q.bias = p.beff + h->lin_host[LIN_LAYER0 + 4 * l + 3].bias_off; q.bias_ld = h->bstride; q.act = 1; q.Y = h->act + (size_t)(3 + 2 * l) * SS;
+    if ((rc = tt_rowlin(h, q, 2 + 2 * l, 0, p, grid_gemm, st)) != PFM_OK) return rc;
+  }
+  tt_head_kernel<<<grid_rows, 256, 0, st>>>(p);
+  h->last_launches++;
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+// backward: fills dact / dbeff (/ dxs) like epic_train.cu::epic_bwd_kernel
+int tt_train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
+  const pfm_epic_cfg& c = h->cfg;
+  // independent of which path produced the saved forward (same arrays): workspace, images and the row -> jet map are
+  // (re)made here, so a forward of the CUDA-core kernels can be differentiated by this path and vice versa
+  int rc = tt_workspace(h, a.B, a.N);
+  if (rc != PFM_OK) return rc;
+  if (!h->tt_store || h->tt_dirty) { rc = tt_pack(h, st); if (rc != PFM_OK) return rc; }
+  TtCommon p;
+  tt_common(h, a.B, a.N, a.Kx, a.xin_off, a.lay, &p);
+  tt_rowjet_kernel<<<a.B, 64, 0, st>>>(h->plan.n_real, h->plan.rowoff, a.B, const_cast<int*>(p.rowjet));
+  h->last_launches++;
+  p.dxs = a.want_dx ? h->dxs : nullptr;
+  const size_t SS = a.lay.stage_stride;
+  const int Zp = a.lay.Zp;
+  const int grid_rows = 4 * h->sm_count;
+  const int grid_gemm = h->sm_count;
+  PFM_CUDA_CHECK(cudaMemsetAsync(p.bc, 0, sizeof(float) * ((size_t)a.B * TT_H + (size_t)a.B * Zp), st));      // bc and dGc are adjacent
+  tt_head_bwd_kernel<<<grid_rows, 256, 0, st>>>(p);
+  h->last_launches++;
+  for (int l = c.layers - 1; l >= 0; --l) {
+    const bool first = l == c.layers - 1;
+    RowLinP q; memset(&q, 0, sizeof(q));
+    // dz2 = (dh + bc[jet]) * lrelu'(h_{l+1}) -> dact[3+2l];  du = dz2 . W2;  dz1 = du * lrelu'(u_l) -> dact[2+2l]
+    q.X = p.dhbuf; q.bc = first ? nullptr : p.bc; q.S = h->act + (size_t)(3 + 2 * l) * SS; q.Xout = h->dact + (size_t)(3 + 2 * l) * SS;
+    q.E = h->act + (size_t)(2 + 2 * l) * SS; q.Y = h->dact + (size_t)(2 + 2 * l) * SS;
+    if ((rc = tt_rowlin(h, q, 2 + 2 * l, 1, p, grid_gemm, st)) != PFM_OK) return rc;
+    // dh = dz2 (residual) + dz1 . W1(main)
+    memset(&q, 0, sizeof(q));
+    q.X = h->dact + (size_t)(2 + 2 * l) * SS; q.R = h->dact + (size_t)(3 + 2 * l) * SS; q.Y = p.dhbuf;
+    if ((rc = tt_rowlin(h, q, 1 + 2 * l, 1, p, grid_gemm, st)) != PFM_OK) return rc;
+    tt_jet_bwd_kernel<<<a.B, 128, 0, st>>>(p, l + 1, first ? 1 : 0);
+    h->last_launches++;
+  }
+  tt_jet_bwd_kernel<<<a.B, 128, 0, st>>>(p, 0, c.layers == 0 ? 1 : 0);
+  h->last_launches++;
+  {   // stem: dz_l2 = (dh + bc) * lrelu'(h0) -> dact[1];  dz_l1 = (dz_l2 . W_l2 + dz_l2) * lrelu'(h1) -> dact[0]
+    RowLinP q; memset(&q, 0, sizeof(q));
+    q.X = p.dhbuf; q.bc = p.bc; q.S = h->act + SS; q.Xout = h->dact + SS; q.r_is_xout = 1; q.E = h->act; q.Y = h->dact;
+    if ((rc = tt_rowlin(h, q, 0, 1, p, grid_gemm, st)) != PFM_OK) return rc;
+  }
+  tt_stem_bwd_kernel<<<a.B, 128, 0, st>>>(p);
+  h->last_launches++;
+  PFM_CUDA_CHECK(cudaGetLastError());
+  return PFM_OK;
+}
+
+}  // namespace pfm

@@ -467,9 +467,15 @@ static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, co
   a.x_in = x; a.x_out = out; a.t = t_jet; a.noise0 = noise0; a.noise1 = noise1; a.loss_kind = loss_kind; a.sigma = sigma;
   a.B = B; a.N = N; a.Kx = Kx; a.xin_off = xin_off; a.has_cbias = cond_dim > 0; a.tbias_per_jet = per_jet ? 1 : 0;
   a.lay = *lay;
-  rc = simt_train_forward(h, a, st);
-  if (rc != PFM_OK) return rc;
-  h->last_launches++;
+  h->train_tc = tt_enabled(h);
+  if (h->train_tc) {
+    rc = tt_train_forward(h, a, st);
+    if (rc != PFM_OK) return rc;
+  } else {
+    rc = simt_train_forward(h, a, st);
+    if (rc != PFM_OK) return rc;
+    h->last_launches++;
+  }
   h->train_B = B; h->train_N = N; h->train_Kx = Kx; h->train_xin_off = xin_off;
   return PFM_OK;
 }
@@ -558,6 +564,7 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->last_launches = 0; h->last_groups_host = 0;
   h->timing = false; h->ev_used = 0;
   h->step_kind = 0; h->step_coef = nullptr; h->step_noise = nullptr;
+  h->tt_store = nullptr; h->tt_bytes = 0; h->tt_dirty = true; h->tt_ws = nullptr; h->tt_ws_cap = 0; h->train_tc = false; h->train_mode = PFM_TRAIN_AUTO;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   h->lin_host.resize(h->n_lin);
@@ -614,6 +621,8 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->wt_store) cudaFree(h->wt_store);
   if (h->b_store) cudaFree(h->b_store);
   if (h->tc_store) cudaFree(h->tc_store);
+  if (h->tt_store) cudaFree(h->tt_store);
+  if (h->tt_ws) cudaFree(h->tt_ws);
   if (h->wr_store) cudaFree(h->wr_store);
   if (h->act) cudaFree(h->act);
   if (h->dact) cudaFree(h->dact);
@@ -672,7 +681,7 @@ int pfm_epic_set_weights(pfm_epic* h, const float* const* weights, const float* 
   }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
-  h->tc_dirty = true;
+  h->tc_dirty = true; h->tt_dirty = true;
   if (h->precision == PFM_PREC_BF16) {
     int rc = tc_pack_weights(h, st);
     if (rc != PFM_OK) return rc;
@@ -785,7 +794,7 @@ int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* 
   wn_fold_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_ptrs, n);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
-  h->tc_dirty = true;
+  h->tc_dirty = true; h->tt_dirty = true;
   if (h->precision == PFM_PREC_BF16) {
     rc = tc_pack_weights(h, st);
     if (rc != PFM_OK) return rc;
@@ -824,6 +833,22 @@ int pfm_epic_set_precision(pfm_epic* h, int precision) {
   // The bf16 weight images are (re)packed lazily by the next forward / sample ON ITS OWN STREAM (tc_run packs when
   // tc_store is NULL): packing here on the legacy stream would not be ordered against a non-blocking consumer stream.
   (void)old;
+  return PFM_OK;
+}
+
+// test hook: copy n floats of an internal training array to the host (which: 0 act, 1 dact, 2 dbeff, 3 jact, 4 dpre3, 5 yact)
+int pfm_epic_debug_copy(pfm_epic* h, int which, float* host, long long n) {
+  if (!h || !host || which < 0 || which > 5) { set_error("bad argument"); return PFM_ERR_INVALID; }
+  const float* src = which == 0 ? h->act : which == 1 ? h->dact : which == 2 ? h->dbeff : which == 3 ? h->jact : which == 4 ? h->dpre3 : h->yact;
+  if (!src) { set_error("no such array"); return PFM_ERR_STATE; }
+  PFM_CUDA_CHECK(cudaDeviceSynchronize());
+  PFM_CUDA_CHECK(cudaMemcpy(host, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+  return PFM_OK;
+}
+
+int pfm_epic_set_train_mode(pfm_epic* h, int mode) {
+  if (!h || (mode != PFM_TRAIN_AUTO && mode != PFM_TRAIN_CUDA_CORES)) { set_error("bad train mode %d", mode); return PFM_ERR_INVALID; }
+  h->train_mode = mode;
   return PFM_OK;
 }
 

@@ -92,6 +92,12 @@ struct pfm_epic {
   int wn_total_rows;
   long long* wn_goff;               // [2 n_lin] offsets of W_i and b_i in the flat gradient
   const float** wn_ptrs;            // [8 n_lin] device copy of the caller's pointer tables
+  // tensor-core training path (epic_train_tc.cu): hi / lo bf16 images of the 128 x 128 per-particle weights and their
+  // transposes, workspace (effective biases, per-jet broadcast / carry vectors, dh, row -> jet map)
+  void* tt_store; size_t tt_bytes; bool tt_dirty;
+  float* tt_ws; size_t tt_ws_cap;
+  bool train_tc;                    // the saved forward was produced by the tensor-core path
+  int train_mode;                   // pfm_train_mode requested by the host
   // diffusion step program of the next sampling call (pfm_epic_sample_diffusion; 0 = plain flow-matching ODE)
   int step_kind; const float* step_coef; const float* step_noise;
   bool timing;
@@ -176,6 +182,10 @@ int xty_tc_launch_one(const float* Y, int ldy, const float* X, int ldx, float* d
 int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, int ldw, int out, int K, int col0, int rows,
                    cudaStream_t st);
 int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);
+// training with the per-particle GEMMs on tcgen05, fp32-accurate 3-term bf16 split (epic_train_tc.cu); hid == 128
+bool tt_enabled(const pfm_epic* h);
+int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st);
+int tt_train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st);
 // bf16 tcgen05 path (epic_tc.cu)
 int tc_supported(const pfm_epic* h, int N);
 int tc_plan_caps(const pfm_epic* h, int N, int* R_cap, int* J_cap);

@@ -85,6 +85,20 @@ class EpicEngine:
         _lib.check(self.lib.pfm_epic_set_precision(self._h, code), "pfm_epic_set_precision")
         self.precision = precision
 
+    def set_train_mode(self, mode: str):
+        """'auto' (tensor-core training kernels when hid == 128) or 'cuda_cores' (fused fp32 CUDA-core kernels)."""
+        code = {"auto": 0, "cuda_cores": 1}[mode]
+        _lib.check(self.lib.pfm_epic_set_train_mode(self._h, code), "pfm_epic_set_train_mode")
+
+    def debug_array(self, which: str, n: int):
+        """Host copy (numpy float32) of the first n floats of an internal training array: 'act', 'dact', 'dbeff', 'jact',
+        'dpre3' or 'yact' (test hook, pfm_epic_debug_copy)."""
+        import numpy as np
+        code = {"act": 0, "dact": 1, "dbeff": 2, "jact": 3, "dpre3": 4, "yact": 5}[which]
+        buf = np.zeros(n, dtype=np.float32)
+        _lib.check(self.lib.pfm_epic_debug_copy(self._h, code, buf.ctypes.data_as(C.c_void_p), n), "pfm_epic_debug_copy")
+        return buf
+
     def linear_shapes(self):
         out = []
         o, i = C.c_int32(), C.c_int32()

@@ -32,9 +32,10 @@ def module_grads(m):
     return {k[len("flows.0.net."):]: p.grad.detach().cpu() for k, p in m.named_parameters() if k.startswith("flows.0.net.")}
 
 
-def run_fused(m, kind, x, mask, cond, t, n0, n1, sigma):
+def run_fused(m, kind, x, mask, cond, t, n0, n1, sigma, mode="cuda_cores"):
     from particle_fm_b200.training import fm_loss_autograd
     m.zero_grad(set_to_none=True)
+    m.flows[0].net.engine().set_train_mode(mode)
     c = None if cond is None else cond.to(DEV)
     loss = fm_loss_autograd(m.flows[0], kind, x.to(DEV), mask.to(DEV), c, t.to(DEV), n0.to(DEV),
                             None if n1 is None else n1.to(DEV), sigma)
@@ -64,6 +65,33 @@ def test_loss_and_gradients_vs_oracle_autograd(name, kind):
     for k, v in ref_g.items():
         if v is not None and float(v.norm()) == 0:
             assert float(got[k].norm()) == 0, k
+    if g.cfg.hid != 128:
+        return
+    # hid == 128: the default training path is the tensor-core program (csrc/epic_train_tc.cu).  Same gates -- unless the two
+    # CUDA evaluations of the forward put a pre-activation on different sides of leaky_relu's kink (|z| within fp32 rounding
+    # of 0: a measure-zero discontinuity of the derivative, not an arithmetic error); that is detected from the saved
+    # activations of both paths and then the draw is repeated with the next seed.
+    rows = int(g.mask.sum())
+    N = x.shape[1]
+    for seed in (31, 32, 33, 34):
+        gen = torch.Generator().manual_seed(seed)
+        t = torch.rand(B, generator=gen)
+        n0 = torch.randn(x.shape, generator=gen)
+        n1 = torch.randn(x.shape, generator=gen) if kind == "CFM" else None
+        run_fused(m, kind, x, g.mask, g.cond, t, n0, n1, sigma, mode="cuda_cores")
+        a_cc = _act_arrays(m.flows[0].net.engine(), B, N, rows)
+        loss, got = run_fused(m, kind, x, g.mask, g.cond, t, n0, n1, sigma, mode="auto")
+        a_tc = _act_arrays(m.flows[0].net.engine(), B, N, rows)
+        flips = sum(int(((u > 0) != (v > 0)).sum()) for u, v in zip(a_cc, a_tc))
+        if flips:
+            continue
+        ref_loss, ref_g = oracle_loss_and_grads(g, kind, x, g.mask, g.cond, t, n0, n1, sigma)
+        assert abs(float(loss) - float(ref_loss)) <= LOSS_TOL * abs(float(ref_loss)), (float(loss), float(ref_loss))
+        worst = max((rel_l2(got[k], ref_g[k]), k) for k in ref_g if ref_g[k] is not None and float(ref_g[k].norm()) > 0)
+        assert worst[0] < GRAD_TOL, (seed, worst)
+        break
+    else:
+        raise AssertionError("every draw had a kink-ambiguous pre-activation")
 
 
 def test_loss_module_api_and_rng_order():
@@ -261,3 +289,89 @@ def test_training_step_loss_per_jettype_branch():
     logged.clear()
     m.training_step((x, mask, cond.to(DEV)), 0)
     assert set(logged) == {"train/loss"}
+
+
+def _big_batch(kind, seed=77, B=96, N=150):
+    gen = torch.Generator().manual_seed(seed)
+    n_real = torch.randint(1, N + 1, (B,), generator=gen)
+    n_real[3] = N; n_real[5] = 1
+    mask = (torch.arange(N)[None, :] < n_real[:, None]).float().unsqueeze(-1)
+    x = torch.randn(B, N, 3, generator=gen) * 5.0 * mask
+    t = torch.rand(B, generator=gen)
+    n0 = torch.randn(B, N, 3, generator=gen)
+    n1 = torch.randn(B, N, 3, generator=gen) if kind == "CFM" else None
+    return x, mask, t, n0, n1
+
+
+def _act_arrays(eng, B, N, rows):
+    """saved post-activations [stage][row][128] of the last training forward (valid rows only)"""
+    H, L = eng.dims.hid, eng.dims.layers
+    SS = B * N * H
+    a = eng.debug_array("act", (2 + 2 * L) * SS)
+    return [a[s * SS:s * SS + rows * H] for s in range(2 + 2 * L)]
+
+
+@pytest.mark.parametrize("kind", ["FM-OT", "CFM"])
+def test_tensor_core_training_forward_matches_cuda_core_forward(kind):
+    """hid == 128: the training forward runs as tcgen05 GEMM passes over the packed particles (csrc/epic_train_tc.cu, 3-term
+    bf16 split).  Every saved activation agrees with the fused fp32 CUDA-core kernel to 1e-5 (relative L2 per stage) and the
+    loss to 1e-6, on a batch spanning many 128-row tiles with ragged masks (a full jet and a 1-particle jet included)."""
+    from particle_fm_b200.training import fm_loss_autograd
+    g = Golden("c2_jetnet150")
+    x, mask, t, n0, n1 = _big_batch(kind)
+    B, N = x.shape[0], x.shape[1]
+    rows = int(mask.sum())
+    res = {}
+    for mode in ("cuda_cores", "auto"):
+        m = build_module(g.ctor, g.sd, loss_type=kind, device=DEV)
+        eng = m.flows[0].net.engine()
+        eng.set_train_mode(mode)
+        with torch.no_grad():
+            loss = fm_loss_autograd(m.flows[0], kind, x.to(DEV), mask.to(DEV), None, t.to(DEV), n0.to(DEV),
+                                    None if n1 is None else n1.to(DEV), 1e-4)
+        res[mode] = (float(loss), _act_arrays(eng, B, N, rows))
+    (l0, a0), (l1, a1) = res["cuda_cores"], res["auto"]
+    assert abs(l1 - l0) <= 1e-6 * abs(l0), (l0, l1)
+    for s_, (u, v) in enumerate(zip(a0, a1)):
+        assert rel_l2(torch.from_numpy(v), torch.from_numpy(u)) < 1e-5, s_
+
+
+def test_tensor_core_training_backward_matches_cuda_core_backward():
+    """Same saved forward, two backward implementations: the tcgen05 program and the fused fp32 CUDA-core kernel agree to
+    1e-5 on dL/dx and 1e-4 on every weight gradient.  (Sharing the forward removes the one legitimate source of larger
+    differences between two fp32 evaluation orders: a pre-activation within rounding of 0 taking the other branch of
+    leaky_relu'.)"""
+    g = Golden("c2_jetnet150")
+    x, mask, t, n0, _ = _big_batch("FM-OT", seed=78, B=64)
+    B, N = x.shape[0], x.shape[1]
+    m = build_module(g.ctor, g.sd, device=DEV)
+    cnf = m.flows[0]
+    eng = cnf.net.engine()
+    code = cnf.time_code(t.to(DEV))
+    gen = torch.Generator().manual_seed(5)
+    gout = torch.randn(B, N, 3, generator=gen).to(DEV) * mask.to(DEV)
+    out = {}
+    for mode in ("cuda_cores", "auto"):
+        eng.set_train_mode("cuda_cores")
+        _, ticket, saved = eng.forward_train(code, x.to(DEV), mask.to(DEV), None)
+        eng.set_train_mode(mode)
+        gx, flat = eng.backward(ticket, saved, gout, True, True)
+        out[mode] = (gx.cpu(), flat.cpu())
+    eng.set_train_mode("auto")
+    assert rel_l2(out["auto"][0], out["cuda_cores"][0]) < 1e-5
+    off = 0
+    for k, (o, i) in enumerate(eng.linear_shapes()):
+        n = o * i + o
+        a, b = out["auto"][1][off:off + n], out["cuda_cores"][1][off:off + n]
+        if float(b.norm()) > 0:
+            assert rel_l2(a, b) < GRAD_TOL, k
+        off += n
+    # and the other way round: a tensor-core forward differentiated by both backward paths
+    eng.set_train_mode("auto")
+    _, ticket, saved = eng.forward_train(code, x.to(DEV), mask.to(DEV), None)
+    gx_a, flat_a = eng.backward(ticket, saved, gout, True, True)
+    _, ticket, saved = eng.forward_train(code, x.to(DEV), mask.to(DEV), None)
+    eng.set_train_mode("cuda_cores")
+    gx_b, flat_b = eng.backward(ticket, saved, gout, True, True)
+    eng.set_train_mode("auto")
+    assert rel_l2(gx_a, gx_b) < 1e-5 and rel_l2(flat_a, flat_b) < 1e-5
