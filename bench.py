@@ -166,14 +166,20 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024, mode="auto")
     g = torch.Generator().manual_seed(888 + rank)
     x = (5.0 * torch.randn(B, N_PART, FEATS, generator=g) * mask_h).to(dev)
     mask = mask_h.to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-5)
+    fused_opt = mode == "auto"
+    if fused_opt:          # clip 0.5 + AdamW in two launches over flat buffers (particle_fm_b200.optim)
+        from particle_fm_b200.optim import FusedClipAdamW
+        opt = FusedClipAdamW(model.parameters(), lr=1e-3, weight_decay=5e-5, max_grad_norm=0.5)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-5)
     model.flows[0].net.engine().set_train_mode(mode)
 
     def step():
         opt.zero_grad(set_to_none=True)
         loss = model.loss(x, mask=mask, cond=None)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+        if not fused_opt:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
         opt.step()
         return loss
 
@@ -196,7 +202,8 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024, mode="auto")
             "ms_per_step": ms / steps, "loss": "FM-OT", "final_loss": float(loss.detach()),
             "step": ("loss fwd+bwd with the per-particle GEMMs and their transposes on tcgen05 (3-term bf16 split, fp32-accurate), per-jet "
                      "MLPs on CUDA cores" if mode == "auto" else "fused loss fwd+bwd on fp32 CUDA cores") +
-                    "; weight gradients on tcgen05 (3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + clip 0.5 + AdamW",
+                    "; weight gradients on tcgen05 (3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + " +
+                    ("clip 0.5 + AdamW fused over flat buffers (pfm_clip_adamw, 2 launches)" if fused_opt else "torch clip_grad_norm_ 0.5 + torch.optim.AdamW"),
             "kernels": mode,
             "mean_real_particles": float(n_real.float().mean())}
 

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "pfm_tf_loss_fwd_bwd": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p]),
     "pfm_epic_sample_diffusion": (C.c_int, [C.c_void_p] + [_F] * 8 + [C.c_int] * 5 + [C.c_void_p]),
+    "pfm_clip_adamw": (C.c_int, [_F, _F, _F, _F, C.c_longlong] + [C.c_float] * 6 + [C.c_int, _F, C.c_float, _F, C.c_void_p]),
     "pfm_postprocess": (C.c_int, [_F, _F, _F, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
                                   C.c_int, C.c_void_p]),
     "pfm_ot_assign": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, _F, _F, C.c_void_p]),

@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpfm_b200.so")
-SOURCES = ["pfm_api.cu", "epic_simt.cu", "epic_tc.cu", "epic_train.cu", "tf_simt.cu", "tf_tc.cu", "tf_attn_tc.cu", "tf_train.cu", "xty_tc.cu", "extras.cu", "epic_train_tc.cu"]
+SOURCES = ["pfm_api.cu", "epic_simt.cu", "epic_tc.cu", "epic_train.cu", "tf_simt.cu", "tf_tc.cu", "tf_attn_tc.cu", "tf_train.cu", "xty_tc.cu", "extras.cu", "epic_train_tc.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills"]
 

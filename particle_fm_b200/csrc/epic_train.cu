@@ -641,7 +641,17 @@ static int train_backward_simt(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t 
 
 int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   const pfm_epic_cfg& c = h->cfg;
-  int rc = tt_enabled(h) ? tt_train_backward(h, a, st) : train_backward_simt(h, a, st);     // tensor-core path: epic_train_tc.cu
+  int rc;
+  if (tt_enabled(h)) {
+    rc = tt_train_backward(h, a, st);                    // tensor-core path: epic_train_tc.cu
+  } else {
+    if (h->train_tc) {                                   // the forward ran on the tensor-core path: its plan has no CTA groups
+      rc = train_plan_groups(h, a.B, a.lay, st);
+      if (rc != PFM_OK) return rc;
+      h->train_tc = false;
+    }
+    rc = train_backward_simt(h, a, st);
+  }
   if (rc != PFM_OK) return rc;
   if (!a.grad_flat) return PFM_OK;
 

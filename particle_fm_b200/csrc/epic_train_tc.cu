@@ -41,11 +41,12 @@ __device__ __forceinline__ float tt_dlrelu(float post, float s) { return post > 
 struct TtImgSrc { const float* Wt; int ldo; int k0; };   // W[o][k] = Wt[(k0 + k) * ldo + o]
 
 __global__ void tt_pack_kernel(const TtImgSrc* __restrict__ src, uint8_t* __restrict__ img) {
-  const TtImgSrc S = src[blockIdx.x >> 1];
-  const int transposed = blockIdx.x & 1;
-  uint8_t* hi = img + (size_t)blockIdx.x * 2 * TT_IMG;
+  const int im = blockIdx.x >> 3, part = blockIdx.x & 7;    // 8 CTAs per image
+  const TtImgSrc S = src[im >> 1];
+  const int transposed = im & 1;
+  uint8_t* hi = img + (size_t)im * 2 * TT_IMG;
   uint8_t* lo = hi + TT_IMG;
-  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) {
+  for (int i = part * 2048 + threadIdx.x; i < (part + 1) * 2048; i += blockDim.x) {
     const int k = i >> 7, o = i & 127;                   // consecutive threads -> consecutive o: coalesced reads
     const float w = S.Wt[(size_t)(S.k0 + k) * S.ldo + o];
     const __nv_bfloat16 h = __float2bfloat16_rn(w);
@@ -57,21 +58,25 @@ __global__ void tt_pack_kernel(const TtImgSrc* __restrict__ src, uint8_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// rowlin_tc_kernel
+// rowlin_tc_kernel:  Y[rows,128] = epi( X[rows,128] . W^T )
+// A 128-row tile of X is ONE contiguous 64 KB block of global memory: it is fetched by bulk async copies (no registers,
+// a whole tile in flight per SM) into a raw fp32 staging buffer, split into bf16 hi / lo K-major SW128 operands by all
+// threads, multiplied with 24 tcgen05.mma (3-term split) into one of two TMEM accumulators, and the epilogue of tile t
+// runs while the MMAs of tile t+1 execute and the copy of tile t+2 is in flight.
+// Epilogue (in this order): + bias[jet] | + R | + bc[jet] | leaky_relu | * leaky_relu'(sign bits E) ; optionally the sign
+// bits of the result are written (they are all the backward needs of a saved activation: 16 bytes per row instead of 512).
 // ---------------------------------------------------------------------------------------------
 struct RowLinP {
   const float* X;          // [rows][128]
-  const float* bc;         // [B][128] per-jet vector added to X (nullptr: none)
-  const float* S;          // [rows][128] saved post-activation: X' = (X + bc) * leaky_relu'(S) (nullptr: none)
-  float* Xout;             // [rows][128] X' written back (nullptr: none)
   const uint8_t* Wimg;     // hi | lo
   const float* bias;       // per-jet effective bias rows, already offset to the linear's slice (nullptr: none)
   int bias_ld;
-  const float* R;          // [rows][128] residual added before the activation (nullptr: none)
-  int r_is_xout;           // the residual is this launch's own Xout
-  const float* E;          // [rows][128] saved post-activation: Y *= leaky_relu'(E) (nullptr: none)
+  const float* R;          // [rows][128] residual (nullptr: none)
+  const float* bc;         // [B][128] per-jet vector (nullptr: none)
   int act;                 // leaky_relu on the result
+  const uint32_t* E;       // [rows][4] sign bits of a saved post-activation: Y *= leaky_relu'(.) (nullptr: none)
   float* Y;                // [rows][128]
+  uint32_t* sgn_out;       // [rows][4] sign bits of Y (nullptr: none)
   const int* rowjet;       // [rows]
   const int* n_total;
   float slope;
@@ -79,8 +84,10 @@ struct RowLinP {
 
 struct RowLinSmem {
   alignas(1024) uint8_t W[2][TT_IMG];
-  alignas(1024) uint8_t A[2][2][TT_IMG];        // [buffer][hi, lo]
-  uint64_t mbar_w, mbar[2];
+  alignas(1024) uint8_t A[2][TT_IMG];           // hi, lo
+  alignas(1024) float raw[128 * TT_H];          // fp32 tile as it lies in global memory
+  alignas(16) float stage[64 * TT_H];           // epilogue staging of 64 accumulator rows (16-byte chunks XOR-swizzled by row)
+  uint64_t mbar_w, mbar_raw, mbar[2];
   uint32_t tmem;
 };
 
@@ -95,58 +102,108 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
 
   if (warp == 0) tmem_alloc(&s.tmem, 256);
   if (tid == 0) {
-    mbar_init(&s.mbar_w, 1); mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1);
+    mbar_init(&s.mbar_w, 1); mbar_init(&s.mbar_raw, 1); mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1);
     fence_barrier_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  auto load_tile = [&](int t_local) {                      // one thread: the tile's valid rows, two bulk copies
+    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+    const int r0 = tile * 128;
+    const int n = rows - r0 < 128 ? rows - r0 : 128;
+    const uint32_t bytes = (uint32_t)n * TT_H * 4u;
+    const uint32_t half = bytes > 32768u ? 32768u : bytes;
+    mbar_arrive_expect_tx(&s.mbar_raw, bytes);
+    bulk_copy_g2s(s.raw, p.X + (size_t)r0 * TT_H, half, &s.mbar_raw);
+    if (bytes > half) bulk_copy_g2s(reinterpret_cast<uint8_t*>(s.raw) + half, reinterpret_cast<const uint8_t*>(p.X + (size_t)r0 * TT_H) + half,
+                                    bytes - half, &s.mbar_raw);
+  };
   if (tid == 0) {
     mbar_arrive_expect_tx(&s.mbar_w, 2 * TT_IMG);
     bulk_copy_g2s(s.W[0], p.Wimg, TT_IMG, &s.mbar_w);
     bulk_copy_g2s(s.W[1], p.Wimg + TT_IMG, TT_IMG, &s.mbar_w);
+    load_tile(0);
   }
   const uint32_t tm = s.tmem;
   const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
 
-  // unit = half a tile (64 rows): 8 float4 of X (and of S) per thread in flight
-  float4 xv[8], sv[8];
-  auto fetch = [&](int u) {
-    const int tile = (int)blockIdx.x + (u >> 1) * (int)gridDim.x;
-    const int r0 = tile * 128 + (u & 1) * 64;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = tid + 256 * i, r = r0 + (idx >> 5), c = (idx & 31) * 4;
-      if (r < rows) {
-        xv[i] = __ldcg(reinterpret_cast<const float4*>(p.X + (size_t)r * TT_H + c));
-        if (p.S) sv[i] = __ldcg(reinterpret_cast<const float4*>(p.S + (size_t)r * TT_H + c));
-      } else {
-        xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sv[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-      }
-    }
-  };
-  auto store = [&](int u) {
-    const int t_local = u >> 1;
+  // Epilogue of a tile whose MMAs are complete (waited by the caller).  TMEM hands every thread one ROW of the accumulator;
+  // global memory wants consecutive threads on consecutive columns.  The rows go through a shared-memory staging buffer
+  // (64 rows at a time; 16-byte chunk c of row r is stored at chunk c ^ (r & 31): conflict-free both ways), so that every
+  // global load (residual) and store is a fully coalesced 512-byte row segment per warp.
+  auto epilogue = [&](int t_local) {
     const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
-    const int r0 = tile * 128 + (u & 1) * 64;
-    uint8_t* hi = s.A[t_local & 1][0];
-    uint8_t* lo = s.A[t_local & 1][1];
+    const int q = warp & 3, hf = warp >> 2;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if ((q >> 1) == half) {                              // warps owning TMEM lanes [64 half, 64 half + 64)
+        const int rl = (q & 1) * 32 + lane;                // row inside the staging buffer
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = tid + 256 * i, rl = (u & 1) * 64 + (idx >> 5), r = r0 + (idx >> 5), c = (idx & 31) * 4;
-      float4 v = xv[i];
-      if (r < rows) {
-        if (p.bc) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bc + (size_t)p.rowjet[r] * TT_H + c));
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        for (int j = 0; j < 2; ++j) {
+          uint32_t v[32];
+          const int o0 = hf * 64 + j * 32;
+          tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const int chunk = ((o0 >> 2) + i4) ^ (rl & 31);
+            *reinterpret_cast<uint4*>(&s.stage[rl * TT_H + chunk * 4]) = make_uint4(v[i4 * 4 + 0], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+          }
         }
-        if (p.S) {
-          v.x *= tt_dlrelu(sv[i].x, p.slope); v.y *= tt_dlrelu(sv[i].y, p.slope);
-          v.z *= tt_dlrelu(sv[i].z, p.slope); v.w *= tt_dlrelu(sv[i].w, p.slope);
-        }
-        if (p.Xout) __stcg(reinterpret_cast<float4*>(p.Xout + (size_t)r * TT_H + c), v);
       }
+      __syncthreads();
+      // all 256 threads: thread = (row, 16-byte chunk); a warp covers one full row per step
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
+        const int r = tile * 128 + half * 64 + rl;
+        if (r < rows) {
+          const int o = c4 * 4;
+          float4 a = *reinterpret_cast<const float4*>(&s.stage[rl * TT_H + ((c4 ^ (rl & 31)) * 4)]);
+          const int jet = (p.bias || p.bc) ? p.rowjet[r] : 0;
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.R) {
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.R + (size_t)r * TT_H + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.bc) {
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.bc + (size_t)jet * TT_H + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
+          if (p.E) {
+            const uint32_t e = __ldcg(p.E + (size_t)r * 4 + (c4 >> 3)) >> ((c4 & 7) * 4);
+            a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
+          }
+          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+          if (p.sgn_out) {                                 // 8 lanes hold the 32 columns of one sign word
+            uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((c4 & 7) * 4);
+            b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
+            if ((c4 & 7) == 0) p.sgn_out[(size_t)r * 4 + (c4 >> 3)] = b;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    tc_fence_before();
+  };
+
+  mbar_wait(&s.mbar_w, 0);
+  for (int t = 0; t < my_tiles; ++t) {
+    mbar_wait(&s.mbar_raw, (uint32_t)(t & 1));             // the tile's fp32 rows have landed
+    if (t >= 1) {                                          // the operand buffer is free once the previous tile's MMAs are done
+      mbar_wait(&s.mbar[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+      tc_fence_after();
+    }
+    // raw fp32 [128][128] -> bf16 hi / lo, K-major SWIZZLE_128B (thread = 4 consecutive columns of a row)
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int idx = tid + 256 * i, rl = idx >> 5, c = (idx & 31) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(&s.raw[rl * TT_H + c]);
       const uint32_t off = sw128_offset(rl, c, 16384);
       const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z),
                           hw = __float2bfloat16_rn(v.w);
@@ -154,81 +211,33 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
       h2.x = pack_bf16x2(v.x, v.y); h2.y = pack_bf16x2(v.z, v.w);
       l2.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
       l2.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
-      *reinterpret_cast<uint2*>(hi + off) = h2;
-      *reinterpret_cast<uint2*>(lo + off) = l2;
+      *reinterpret_cast<uint2*>(s.A[0] + off) = h2;
+      *reinterpret_cast<uint2*>(s.A[1] + off) = l2;
     }
-  };
-  auto epilogue = [&](int t_local) {
-    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
-    mbar_wait(&s.mbar[t_local & 1], (uint32_t)((t_local >> 1) & 1));
-    tc_fence_after();
-    const int q = warp & 3, hf = warp >> 2;
-    const int r = tile * 128 + q * 32 + lane;
-    const bool ok = r < rows;
-    const int jet = ok ? p.rowjet[r] : 0;
-    const float* res = p.r_is_xout ? p.Xout : p.R;
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        if (t + 1 < my_tiles) load_tile(t + 1);            // the staging buffer is free: the next tile streams in during MMAs + epilogue
+        const uint64_t ah = desc_kmajor(smem_u32(s.A[0])), al = desc_kmajor(smem_u32(s.A[1]));
+        const uint64_t wh = desc_kmajor(smem_u32(s.W[0])), wl = desc_kmajor(smem_u32(s.W[1]));
+        const uint32_t acc = tm + (uint32_t)((t & 1) * 128);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t v[32];
-      const int o0 = hf * 64 + j * 32;
-      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
-      tmem_wait_ld();
-      if (ok) {
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          float4 a = make_float4(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]), __uint_as_float(v[i4 * 4 + 2]),
-                                 __uint_as_float(v[i4 * 4 + 3]));
-          const int o = o0 + i4 * 4;
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (res) {
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(res + (size_t)r * TT_H + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
-          if (p.E) {
-            const float4 e = __ldcg(reinterpret_cast<const float4*>(p.E + (size_t)r * TT_H + o));
-            a.x *= tt_dlrelu(e.x, p.slope); a.y *= tt_dlrelu(e.y, p.slope); a.z *= tt_dlrelu(e.z, p.slope); a.w *= tt_dlrelu(e.w, p.slope);
-          }
-          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t d = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+          mma_ss(acc, ah + d, wh + d, idesc, k ? 1u : 0u);
+          mma_ss(acc, ah + d, wl + d, idesc, 1u);
+          mma_ss(acc, al + d, wh + d, idesc, 1u);
         }
+        mma_commit(&s.mbar[t & 1]);
       }
+      __syncwarp();
     }
-    tc_fence_before();
-  };
-
-  const int n_units = 2 * my_tiles;
-  fetch(0);
-  mbar_wait(&s.mbar_w, 0);                                 // weights have landed (async proxy write: visible to the MMAs)
-  for (int u = 0; u < n_units; ++u) {
-    store(u);
-    if (u + 1 < n_units) fetch(u + 1);
-    if (u & 1) {
-      const int t_local = u >> 1;
-      fence_proxy_async();
-      __syncthreads();
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ah = desc_kmajor(smem_u32(s.A[t_local & 1][0])), al = desc_kmajor(smem_u32(s.A[t_local & 1][1]));
-          const uint64_t wh = desc_kmajor(smem_u32(s.W[0])), wl = desc_kmajor(smem_u32(s.W[1]));
-          const uint32_t acc = tm + (uint32_t)((t_local & 1) * 128);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t d = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
-            mma_ss(acc, ah + d, wh + d, idesc, k ? 1u : 0u);
-            mma_ss(acc, ah + d, wl + d, idesc, 1u);
-            mma_ss(acc, al + d, wh + d, idesc, 1u);
-          }
-          mma_commit(&s.mbar[t_local & 1]);
-        }
-        __syncwarp();
-      }
-      if (t_local >= 1) epilogue(t_local - 1);             // overlaps the MMAs of this tile and the loads of the next
-    }
+    if (t >= 1) epilogue(t - 1);                           // overlaps the MMAs of this tile and the copy of the next
   }
+  mbar_wait(&s.mbar[(my_tiles - 1) & 1], (uint32_t)(((my_tiles - 1) >> 1) & 1));
+  tc_fence_after();
   epilogue(my_tiles - 1);
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 256);
@@ -237,12 +246,36 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
+// rowoff = exclusive prefix sum of n_real, n_total.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) tt_rows_kernel(const int* __restrict__ n_real, int B, int* __restrict__ rowoff,
+                                                       int* __restrict__ n_total) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  int s = 0;
+  for (int i = 0; i < per; ++i) { const int j = tid * per + i; if (j < B) s += n_real[j]; }
+  part[tid] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {                     // Hillis-Steele inclusive scan
+    const int v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int off = part[tid] - s;
+  for (int i = 0; i < per; ++i) {
+    const int j = tid * per + i;
+    if (j < B) { rowoff[j] = off; off += n_real[j]; }
+  }
+  if (tid == 1023) *n_total = part[1023];
+}
+
 // rowjet[rowoff[j] + r] = j
 __global__ void tt_rowjet_kernel(const int* __restrict__ n_real, const int* __restrict__ rowoff, int B, int* __restrict__ rowjet) {
-  const int j = blockIdx.x;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= B) return;
   const int n = n_real[j], r0 = rowoff[j];
-  for (int r = threadIdx.x; r < n; r += blockDim.x) rowjet[r0 + r] = j;
+  for (int r = threadIdx.x & 31; r < n; r += 32) rowjet[r0 + r] = j;
 }
 
 // beff[j][:] = tbias[row(j)][:] + cbias[j][:]      (effective bias of every linear before the global-vector term)
@@ -254,19 +287,34 @@ __global__ void tt_beff_kernel(const float* __restrict__ tbias, int per_jet, con
     beff[(size_t)j * bstride + i] = tb[i] + (cbias ? cbias[(size_t)j * bstride + i] : 0.f);
 }
 
+// sign bits of saved post-activations (only needed when the forward was produced by the CUDA-core kernels)
+__global__ void tt_sign_kernel(const float* __restrict__ act, size_t stage_stride, uint32_t* __restrict__ sgn, size_t sgn_stride,
+                               const int* __restrict__ n_total) {
+  const int rows = *n_total;
+  const int stage = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 4; i += gridDim.x * blockDim.x) {
+    const float* a = act + (size_t)stage * stage_stride + (size_t)(i >> 2) * TT_H + (i & 3) * 32;
+    uint32_t b = 0;
+    for (int k = 0; k < 32; ++k) b |= (a[k] > 0.f ? 1u : 0u) << k;
+    sgn[(size_t)stage * sgn_stride + i] = b;
+  }
+}
+
 struct TtCommon {
   const Lin* lin; int n_lin, L, H, Z, F, Kx, xin_off, N, B, bstride;
   float sum_scale, slope;
   const int* n_real; const uint16_t* ridx; const int* rowoff; const int* n_total; const int* rowjet;
   float* act; float* dact; size_t stage_stride;
+  uint32_t* sgn; size_t sgn_stride;
   float* yact; float* jact; int junit, jstride, LDP, Hp, Zp;
-  float* dpre3; float* dbeff; float* beff; float* bc; float* dGc; float* dhbuf; float* dxs;
+  float* dpre3; float* dbeff; float* beff; float* bc; float* dGc; float* dxs;
   float* loss_acc;
   // loss inputs
   const float* x_in; float* x_out; const float* tjet; const float* noise0; const float* noise1; int loss_kind; float sigma;
 };
 
-// stem: y (flow-matching interpolation or the given input) -> yact;  h1 = lrelu(fc_l1(y)) -> act[0].  One warp per row.
+// stem: y (flow-matching interpolation or the given input) -> yact;  h1 = lrelu(fc_l1(y)) -> act[0] (+ sign bits).
+// One warp per row, lane = 4 consecutive columns.
 __global__ void __launch_bounds__(256) tt_stem_kernel(const TtCommon p) {
   const int lane = threadIdx.x & 31;
   const int rows = *p.n_total;
@@ -292,16 +340,35 @@ __global__ void __launch_bounds__(256) tt_stem_kernel(const TtCommon p) {
     }
     a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope);
     *reinterpret_cast<float4*>(p.act + (size_t)r * TT_H + lane * 4) = a;
+    uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((lane & 7) * 4);
+    b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
+    if ((lane & 7) == 0) p.sgn[(size_t)r * 4 + (lane >> 3)] = b;
   }
 }
 
+// column sums over rows [r0, r0 + n) of a [rows][128] array, rows r0 + part, r0 + part + parts, ...: 8 loads in flight
+__device__ __forceinline__ float tt_colsum_part(const float* __restrict__ a, int r0, int n, int col, int part, int parts) {
+  float s[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] = 0.f;
+  int r = part;
+  for (; r + 7 * parts < n; r += 8 * parts) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] += __ldcg(a + (size_t)(r0 + r + q * parts) * TT_H + col);
+  }
+  for (; r < n; r += parts) s[0] += __ldcg(a + (size_t)(r0 + r) * TT_H + col);
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
 // Forward of one per-jet unit (unit 0 = stem fc_g1 / fc_g2, unit l+1 = EPiC layer l): pooling of the unit's input h,
-// global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).  One CTA (128 threads) per jet.
-__global__ void __launch_bounds__(128) tt_jet_fwd_kernel(const TtCommon p, int unit) {
+// global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).
+// One CTA of 256 threads per jet (latency-bound: two half sums per output, 8 loads in flight per thread).
+__global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int unit) {
   __shared__ float pool[2 * TT_H + 32];
+  __shared__ float half2[TT_H];
   __shared__ float g1s[TT_H];
   __shared__ float gs[32];
-  const int j = blockIdx.x, tid = threadIdx.x;
+  const int j = blockIdx.x, tid = threadIdx.x, col = tid & 127, hp = tid >> 7;
   const int H = p.H, Z = p.Z;
   const int n = p.n_real[j], r0 = p.rowoff[j];
   const int l = unit - 1;
@@ -310,44 +377,54 @@ __global__ void __launch_bounds__(128) tt_jet_fwd_kernel(const TtCommon p, int u
   float* ja = p.jact + (size_t)j * p.jstride + (size_t)unit * p.junit;
   const float* h = p.act + (size_t)(unit == 0 ? 1 : 1 + 2 * l) * p.stage_stride;
   {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int r = 0;
-    for (; r + 4 <= n; r += 4) {
-      s0 += __ldcg(h + (size_t)(r0 + r) * TT_H + tid);     s1 += __ldcg(h + (size_t)(r0 + r + 1) * TT_H + tid);
-      s2 += __ldcg(h + (size_t)(r0 + r + 2) * TT_H + tid); s3 += __ldcg(h + (size_t)(r0 + r + 3) * TT_H + tid);
-    }
-    for (; r < n; ++r) s0 += __ldcg(h + (size_t)(r0 + r) * TT_H + tid);
-    const float sum = (s0 + s1) + (s2 + s3);
-    const float mean = sum / (float)n, ssum = sum * p.sum_scale;
-    if (unit == 0) { pool[tid] = ssum; pool[H + tid] = mean; }       // (sum, mean) in the stem, epic.py:373
-    else { pool[tid] = mean; pool[H + tid] = ssum; }                 // (mean, sum, global) in the layers, :164-171
-    ja[tid] = pool[tid]; ja[H + tid] = pool[H + tid];
-    if (unit > 0 && tid < Z) {
-      const float g = p.jact[(size_t)j * p.jstride + (size_t)(unit - 1) * p.junit + p.LDP + p.Hp + tid];   // previous unit's output
-      pool[2 * H + tid] = g; ja[2 * H + tid] = g;
+    const float part = tt_colsum_part(h, r0, n, col, hp, 2);
+    if (hp) half2[col] = part;
+    __syncthreads();
+    if (!hp) {
+      const float sum = part + half2[col];
+      const float mean = sum / (float)n, ssum = sum * p.sum_scale;
+      if (unit == 0) { pool[col] = ssum; pool[H + col] = mean; }       // (sum, mean) in the stem, epic.py:373
+      else { pool[col] = mean; pool[H + col] = ssum; }                 // (mean, sum, global) in the layers, :164-171
+      ja[col] = pool[col]; ja[H + col] = pool[H + col];
+      if (unit > 0 && col < Z) {
+        const float g = p.jact[(size_t)j * p.jstride + (size_t)(unit - 1) * p.junit + p.LDP + p.Hp + col];   // previous unit's output
+        pool[2 * H + col] = g; ja[2 * H + col] = g;
+      }
     }
   }
   __syncthreads();
-  {
+  {   // fc_g1 / fc_global1: thread (col, hp) sums the k of its half
     const int K = 2 * H + (unit > 0 ? Z : 0);
-    const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + tid;
-    float a0 = p.beff[(size_t)j * p.bstride + Ga.bias_off + tid], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = 0;
-    for (; k + 4 <= K; k += 4) {
-      a0 = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], a0);           a1 = fmaf(__ldg(w + (size_t)(k + 1) * Ga.ldo), pool[k + 1], a1);
-      a2 = fmaf(__ldg(w + (size_t)(k + 2) * Ga.ldo), pool[k + 2], a2); a3 = fmaf(__ldg(w + (size_t)(k + 3) * Ga.ldo), pool[k + 3], a3);
+    const int kh = (K + 1) / 2, k0 = hp * kh, k1 = (k0 + kh < K) ? k0 + kh : K;
+    const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + col;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+      float wv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wv[q] = __ldg(w + (size_t)(k + q) * Ga.ldo);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[q], pool[k + q], acc[q]);
     }
-    for (; k < K; ++k) a0 = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], a0);
-    const float g1 = tt_lrelu((a0 + a1) + (a2 + a3), p.slope);
-    g1s[tid] = g1;
-    ja[p.LDP + tid] = g1;
+    for (; k < k1; ++k) acc[0] = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], acc[0]);
+    const float part = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (hp) half2[col] = part;
+    __syncthreads();
+    if (!hp) {
+      const float g1 = tt_lrelu(part + half2[col] + p.beff[(size_t)j * p.bstride + Ga.bias_off + col], p.slope);
+      g1s[col] = g1;
+      ja[p.LDP + col] = g1;
+    }
   }
   __syncthreads();
-  {   // fc_g2 / fc_global2: warp w handles outputs z = w, w + 4, ...; lanes split K
+  {   // fc_g2 / fc_global2: warp w handles outputs z = w, w + 8, ...; lanes split K
     const int warp = tid >> 5, lane = tid & 31;
-    for (int z = warp; z < Z; z += 4) {
+    for (int z = warp; z < Z; z += 8) {
       float a = 0.f;
-      for (int k = lane; k < H; k += 32) a = fmaf(__ldg(Gb.Wt + (size_t)(Gb.m_off + k) * Gb.ldo + z), g1s[k], a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a = fmaf(__ldg(Gb.Wt + (size_t)(Gb.m_off + lane + 32 * q) * Gb.ldo + z), g1s[lane + 32 * q], a);
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
       if (lane == 0) {
@@ -360,93 +437,106 @@ __global__ void __launch_bounds__(128) tt_jet_fwd_kernel(const TtCommon p, int u
     }
   }
   __syncthreads();
-  if (unit > 0) {   // effective bias of fc_local1: + W_glob . g   (the broadcast global vector, epic.py:189-196)
+  if (unit > 0 && !hp) {   // effective bias of fc_local1: + W_glob . g   (the broadcast global vector, epic.py:189-196)
     const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2];
-    float a = p.beff[(size_t)j * p.bstride + La.bias_off + tid];
-    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(La.Wt + (size_t)(La.g_off + z) * La.ldo + tid), gs[z], a);
-    p.beff[(size_t)j * p.bstride + La.bias_off + tid] = a;
+    float a = p.beff[(size_t)j * p.bstride + La.bias_off + col];
+    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(La.Wt + (size_t)(La.g_off + z) * La.ldo + col), gs[z], a);
+    p.beff[(size_t)j * p.bstride + La.bias_off + col] = a;
   }
 }
 
-// head: v = lrelu(fc_l3(h_L)); flow-matching target, squared error, gradient seed (losses.py:61-62, :75-76).  One warp per row.
-__global__ void __launch_bounds__(256) tt_head_kernel(const TtCommon p) {
-  const int lane = threadIdx.x & 31;
+// head: v = lrelu(fc_l3(h_L)); flow-matching target, squared error, gradient seed (losses.py:61-62, :75-76).
+// One thread per row (its 128 hidden features stream through L1), fc_l3's weights in shared memory.
+__global__ void __launch_bounds__(128) tt_head_kernel(const TtCommon p) {
+  __shared__ float w3[TT_H * 8];
+  __shared__ float red[4];
   const int rows = *p.n_total;
   const Lin L3 = p.lin[p.n_lin - 1];
+  const int F = p.F;
+  for (int i = threadIdx.x; i < TT_H * F; i += blockDim.x) w3[i] = L3.Wt[(size_t)(L3.m_off + i / F) * L3.ldo + (i % F)];
+  __syncthreads();
   const float* hL = p.act + (size_t)(1 + 2 * p.L) * p.stage_stride;
   const float inv_n = 1.f / (float)rows;
   float part = 0.f;
-  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     const int j = p.rowjet[r];
     const int pidx = p.ridx[(size_t)j * p.N + (r - p.rowoff[j])];
-    const float4 hv = __ldcg(reinterpret_cast<const float4*>(hL + (size_t)r * TT_H + lane * 4));
-    for (int f = 0; f < p.F; ++f) {
-      const float* w = L3.Wt + (size_t)(L3.m_off + lane * 4) * L3.ldo + f;
-      float a = hv.x * __ldg(w) + hv.y * __ldg(w + L3.ldo) + hv.z * __ldg(w + 2 * L3.ldo) + hv.w * __ldg(w + 3 * L3.ldo);
+    float v[8];
 #pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
-      if (lane == 0) {
-        const float v = tt_lrelu(a + p.beff[(size_t)j * p.bstride + L3.bias_off + f], p.slope);
-        const size_t gi = ((size_t)j * p.N + pidx) * p.F + f;
-        if (p.loss_kind >= 0) {
-          const float x = p.x_in[gi], z = p.noise0[gi];
-          float u;
-          if (p.loss_kind == PFM_LOSS_FM_OT) u = (1.f - p.sigma) * z - x;
-          else if (p.loss_kind == PFM_LOSS_CFM) u = z - x;
-          else u = z;
-          const float d = v - u;
-          part += d * d;
-          p.dpre3[(size_t)r * p.F + f] = 2.f * d * inv_n * tt_dlrelu(v, p.slope);
-        } else {
-          p.x_out[gi] = v;
-          p.dpre3[(size_t)r * p.F + f] = tt_dlrelu(v, p.slope);      // the backward entry multiplies by the incoming gradient
-        }
+    for (int f = 0; f < 8; ++f) v[f] = 0.f;
+    const float4* hr = reinterpret_cast<const float4*>(hL + (size_t)r * TT_H);
+    for (int c4 = 0; c4 < TT_H / 4; ++c4) {
+      const float4 hv = hr[c4];
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+        if (f < F) v[f] += hv.x * w3[(c4 * 4 + 0) * F + f] + hv.y * w3[(c4 * 4 + 1) * F + f] + hv.z * w3[(c4 * 4 + 2) * F + f] +
+                           hv.w * w3[(c4 * 4 + 3) * F + f];
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      if (f >= F) break;
+      const float o = tt_lrelu(v[f] + p.beff[(size_t)j * p.bstride + L3.bias_off + f], p.slope);
+      const size_t gi = ((size_t)j * p.N + pidx) * F + f;
+      if (p.loss_kind >= 0) {
+        const float x = p.x_in[gi], z = p.noise0[gi];
+        float u;
+        if (p.loss_kind == PFM_LOSS_FM_OT) u = (1.f - p.sigma) * z - x;
+        else if (p.loss_kind == PFM_LOSS_CFM) u = z - x;
+        else u = z;
+        const float d = o - u;
+        part += d * d;
+        p.dpre3[(size_t)r * F + f] = 2.f * d * inv_n * tt_dlrelu(o, p.slope);
+      } else {
+        p.x_out[gi] = o;
+        p.dpre3[(size_t)r * F + f] = tt_dlrelu(o, p.slope);      // the backward entry multiplies by the incoming gradient
       }
     }
   }
-  if (p.loss_kind >= 0 && lane == 0 && part != 0.f) atomicAdd(p.loss_acc, part);
+  if (p.loss_kind >= 0) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sft);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.loss_acc, (red[0] + red[1]) + (red[2] + red[3]));
+  }
 }
 
-// head backward: dh_L[r][c] = sum_f dpre3[r][f] W3[f][c]
+// head backward: dz2 of the last layer (or of fc_l2 when there are no layers) = (dpre3 . W3) * lrelu'(h_L) -> dact[1 + 2L]
+// thread = (row, 4 columns)
 __global__ void __launch_bounds__(256) tt_head_bwd_kernel(const TtCommon p) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float w3[TT_H * 8];
   const int rows = *p.n_total;
   const Lin L3 = p.lin[p.n_lin - 1];
-  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+  const int F = p.F;
+  for (int i = threadIdx.x; i < TT_H * F; i += blockDim.x) w3[i] = L3.Wt[(size_t)(L3.m_off + i / F) * L3.ldo + (i % F)];
+  __syncthreads();
+  float* out = p.dact + (size_t)(1 + 2 * p.L) * p.stage_stride;
+  const uint32_t* sg = p.sgn + (size_t)(1 + 2 * p.L) * p.sgn_stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * 32; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i >> 5), c = (int)(i & 31) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int f = 0; f < p.F; ++f) {
-      const float d = p.dpre3[(size_t)r * p.F + f];
-      const float* w = L3.Wt + (size_t)(L3.m_off + lane * 4) * L3.ldo + f;
-      a.x = fmaf(__ldg(w), d, a.x); a.y = fmaf(__ldg(w + L3.ldo), d, a.y);
-      a.z = fmaf(__ldg(w + 2 * L3.ldo), d, a.z); a.w = fmaf(__ldg(w + 3 * L3.ldo), d, a.w);
+    for (int f = 0; f < F; ++f) {
+      const float d = p.dpre3[(size_t)r * F + f];
+      a.x = fmaf(w3[(c + 0) * F + f], d, a.x); a.y = fmaf(w3[(c + 1) * F + f], d, a.y);
+      a.z = fmaf(w3[(c + 2) * F + f], d, a.z); a.w = fmaf(w3[(c + 3) * F + f], d, a.w);
     }
-    *reinterpret_cast<float4*>(p.dhbuf + (size_t)r * TT_H + lane * 4) = a;
+    const uint32_t e = sg[(size_t)r * 4 + (c >> 5)] >> (c & 31);
+    a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
+    *reinterpret_cast<float4*>(out + (size_t)r * TT_H + c) = a;
   }
 }
 
-// column sums over the rows of jet j of a [rows][128] array (thread = column)
-__device__ __forceinline__ float tt_colsum(const float* __restrict__ a, int r0, int n, int tid) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 4 <= n; r += 4) {
-    s0 += __ldcg(a + (size_t)(r0 + r) * TT_H + tid);     s1 += __ldcg(a + (size_t)(r0 + r + 1) * TT_H + tid);
-    s2 += __ldcg(a + (size_t)(r0 + r + 2) * TT_H + tid); s3 += __ldcg(a + (size_t)(r0 + r + 3) * TT_H + tid);
-  }
-  for (; r < n; ++r) s0 += __ldcg(a + (size_t)(r0 + r) * TT_H + tid);
-  return (s0 + s1) + (s2 + s3);
-}
-
-// Backward of one per-jet unit (mirrors epic_train.cu::global_backward and the code around it).  One CTA per jet.
+// Backward of one per-jet unit (mirrors epic_train.cu::global_backward and the code around it).  One CTA of 256 threads per jet.
 //   unit l+1: db1 / db2 = per-jet sums of the pre-activation gradients of fc_local1 / fc_local2 (-> dbeff),
 //             dG = carry + W_glob^T db1, then the global MLP backward; bc[j] = pooled gradient broadcast (overwritten)
 //   unit 0  : stem global MLP backward from the carry; bc[j] += broadcast (both units pool h0); also the head's bias gradient
-__global__ void __launch_bounds__(128) tt_jet_bwd_kernel(const TtCommon p, int unit, int with_head) {
+__global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int unit, int with_head) {
   __shared__ float db1[TT_H];
   __shared__ float pg1[TT_H];
   __shared__ float pg2[32];
   __shared__ float dG[32];
   __shared__ float din[2 * TT_H + 32];
-  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, col = tid & 127, hp = tid >> 7;
   const int H = p.H, Z = p.Z;
   const int n = p.n_real[j], r0 = p.rowoff[j];
   const int l = unit - 1;
@@ -456,7 +546,7 @@ __global__ void __launch_bounds__(128) tt_jet_bwd_kernel(const TtCommon p, int u
   float* dbe = p.dbeff + (size_t)j * p.bstride;
   if (with_head) {
     const Lin L3 = p.lin[p.n_lin - 1];
-    for (int f = warp; f < p.F; f += 4) {
+    for (int f = warp; f < p.F; f += 8) {
       float a = 0.f;
       for (int r = lane; r < n; r += 32) a += p.dpre3[(size_t)(r0 + r) * p.F + f];
 #pragma unroll
@@ -466,16 +556,16 @@ __global__ void __launch_bounds__(128) tt_jet_bwd_kernel(const TtCommon p, int u
   }
   if (unit > 0) {
     const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2], Lb = p.lin[LIN_LAYER0 + 4 * l + 3];
-    const float s1 = tt_colsum(p.dact + (size_t)(2 + 2 * l) * p.stage_stride, r0, n, tid);
-    const float s2 = tt_colsum(p.dact + (size_t)(3 + 2 * l) * p.stage_stride, r0, n, tid);
-    db1[tid] = s1;
-    dbe[La.bias_off + tid] = s1;
-    dbe[Lb.bias_off + tid] = s2;
+    // threads [0,128): sums of dz1 (stage 2+2l); threads [128,256): sums of dz2 (stage 3+2l)
+    const float sc = tt_colsum_part(p.dact + (size_t)(2 + 2 * l + hp) * p.stage_stride, r0, n, col, 0, 1);
+    if (!hp) { db1[col] = sc; dbe[La.bias_off + col] = sc; }
+    else dbe[Lb.bias_off + col] = sc;
     __syncthreads();
-    for (int z = warp; z < Z; z += 4) {          // gradient w.r.t. the unit's new global vector: carry + W_glob^T . db1
+    for (int z = warp; z < Z; z += 8) {          // gradient w.r.t. the unit's new global vector: carry + W_glob^T . db1
       const float* w = La.Wt + (size_t)(La.g_off + z) * La.ldo;
       float a = 0.f;
-      for (int o = lane; o < H; o += 32) a = fmaf(__ldg(w + o), db1[o], a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a = fmaf(__ldg(w + lane + 32 * q), db1[lane + 32 * q], a);
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
       if (lane == 0) dG[z] = a + p.dGc[(size_t)j * p.Zp + z];
@@ -491,43 +581,48 @@ __global__ void __launch_bounds__(128) tt_jet_bwd_kernel(const TtCommon p, int u
     dbe[Gb.bias_off + tid] = v;
   }
   __syncthreads();
-  {
+  if (!hp) {
     float a = 0.f;
-    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(Gb.Wr + (size_t)z * Gb.ldr + tid), pg2[z], a);
-    const float v = a * tt_dlrelu(ja[p.LDP + tid], p.slope);
-    pg1[tid] = v;
-    dbe[Ga.bias_off + tid] = v;
+    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(Gb.Wr + (size_t)z * Gb.ldr + col), pg2[z], a);
+    const float v = a * tt_dlrelu(ja[p.LDP + col], p.slope);
+    pg1[col] = v;
+    dbe[Ga.bias_off + col] = v;
   }
   __syncthreads();
-  for (int k = tid; k < Ga.m_len; k += 128) {     // din[k] = sum_o W_a[o][m_off + k] pg1[o]
+  for (int k = tid; k < Ga.m_len; k += 256) {     // din[k] = sum_o W_a[o][m_off + k] pg1[o]
     const float* wk = Ga.Wr + k;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int o = 0; o < H; o += 4) {
-      a0 = fmaf(__ldg(wk + (size_t)o * Ga.ldr), pg1[o], a0);           a1 = fmaf(__ldg(wk + (size_t)(o + 1) * Ga.ldr), pg1[o + 1], a1);
-      a2 = fmaf(__ldg(wk + (size_t)(o + 2) * Ga.ldr), pg1[o + 2], a2); a3 = fmaf(__ldg(wk + (size_t)(o + 3) * Ga.ldr), pg1[o + 3], a3);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int o = 0; o < H; o += 8) {
+      float wv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wv[q] = __ldg(wk + (size_t)(o + q) * Ga.ldr);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[q], pg1[o + q], acc[q]);
     }
-    din[k] = (a0 + a1) + (a2 + a3);
+    din[k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
   __syncthreads();
-  {
+  if (!hp) {
     const int o_mean = unit == 0 ? H : 0, o_sum = unit == 0 ? 0 : H;
-    const float v = din[o_mean + tid] / (float)n + p.sum_scale * din[o_sum + tid];
-    float* b = p.bc + (size_t)j * TT_H + tid;
+    const float v = din[o_mean + col] / (float)n + p.sum_scale * din[o_sum + col];
+    float* b = p.bc + (size_t)j * TT_H + col;
     *b = unit == 0 ? *b + v : v;
+    if (unit > 0 && col < Z) p.dGc[(size_t)j * p.Zp + col] = din[2 * H + col] + pg2[col];     // fc_global1's global columns + residual
   }
-  if (unit > 0 && tid < Z) p.dGc[(size_t)j * p.Zp + tid] = din[2 * H + tid] + pg2[tid];     // through fc_global1's global columns + residual
 }
 
 // stem tail: per-jet sums of the fc_l1 / fc_l2 pre-activation gradients, gradient w.r.t. the per-particle input columns
-__global__ void __launch_bounds__(128) tt_stem_bwd_kernel(const TtCommon p) {
-  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__global__ void __launch_bounds__(256) tt_stem_bwd_kernel(const TtCommon p) {
+  const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, col = tid & 127, hp = tid >> 7;
   const int n = p.n_real[j], r0 = p.rowoff[j];
   const Lin L1 = p.lin[LIN_L1], L2 = p.lin[LIN_L2];
   float* dbe = p.dbeff + (size_t)j * p.bstride;
-  dbe[L1.bias_off + tid] = tt_colsum(p.dact, r0, n, tid);
-  dbe[L2.bias_off + tid] = tt_colsum(p.dact + p.stage_stride, r0, n, tid);
+  const float sc = tt_colsum_part(p.dact + (size_t)hp * p.stage_stride, r0, n, col, 0, 1);
+  dbe[(hp ? L2.bias_off : L1.bias_off) + col] = sc;
   if (p.dxs) {
-    for (int r = warp; r < n; r += 4) {
+    for (int r = warp; r < n; r += 8) {
       const float4 d = __ldcg(reinterpret_cast<const float4*>(p.dact + (size_t)(r0 + r) * TT_H + lane * 4));
       for (int c = 0; c < p.Kx; ++c) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(L1.Wt + (size_t)(L1.m_off + p.xin_off + c) * L1.ldo + lane * 4));
@@ -546,11 +641,8 @@ __global__ void __launch_bounds__(128) tt_stem_bwd_kernel(const TtCommon p) {
 bool tt_enabled(const pfm_epic* h) {
   static const int force_simt = getenv("PFM_TRAIN_SIMT") ? atoi(getenv("PFM_TRAIN_SIMT")) : 0;
   const pfm_epic_cfg& c = h->cfg;
-  return !force_simt && h->train_mode != PFM_TRAIN_CUDA_CORES && c.hid == TT_H && c.latent <= 32 && c.feats <= 32;
+  return !force_simt && h->train_mode != PFM_TRAIN_CUDA_CORES && c.hid == TT_H && c.latent <= 32 && c.feats <= 8;
 }
-
-static int tt_gemm_index_fwd(int g) { return 2 * g; }
-static int tt_gemm_index_bwd(int g) { return 2 * g + 1; }
 
 static int tt_pack(pfm_epic* h, cudaStream_t st) {
   const pfm_epic_cfg& c = h->cfg;
@@ -569,8 +661,8 @@ static int tt_pack(pfm_epic* h, cudaStream_t st) {
     PFM_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->tt_store) + bytes, src.data(), aux, cudaMemcpyHostToDevice, st));
     PFM_CUDA_CHECK(cudaStreamSynchronize(st));          // src is a host temporary (pointers into the handle's weight store: once per allocation)
   }
-  tt_pack_kernel<<<n_gemm * 2, 256, 0, st>>>(reinterpret_cast<const TtImgSrc*>(reinterpret_cast<uint8_t*>(h->tt_store) + bytes),
-                                             reinterpret_cast<uint8_t*>(h->tt_store));
+  tt_pack_kernel<<<n_gemm * 2 * 8, 256, 0, st>>>(reinterpret_cast<const TtImgSrc*>(reinterpret_cast<uint8_t*>(h->tt_store) + bytes),
+                                              reinterpret_cast<uint8_t*>(h->tt_store));
   PFM_CUDA_CHECK(cudaGetLastError());
   h->tt_dirty = false;
   h->last_launches++;
@@ -580,7 +672,8 @@ static int tt_pack(pfm_epic* h, cudaStream_t st) {
 static int tt_workspace(pfm_epic* h, int B, int N) {
   const int Zp = (h->cfg.latent + 3) & ~3;
   const size_t rows = (size_t)B * N;
-  const size_t need = (size_t)B * h->bstride + (size_t)B * TT_H + (size_t)B * Zp + rows * TT_H + rows + 64;
+  const size_t stages = 2 + 2 * (size_t)h->cfg.layers;
+  const size_t need = (size_t)B * h->bstride + (size_t)B * TT_H + (size_t)B * Zp + stages * rows * 4 + rows + 64;
   if (h->tt_ws_cap < need) {
     if (h->tt_ws) cudaFree(h->tt_ws);
     h->tt_ws = nullptr; h->tt_ws_cap = 0;
@@ -604,7 +697,7 @@ static void tt_common(pfm_epic* h, int B, int N, int Kx, int xin_off, const Trai
   p->beff = w; w += (size_t)B * h->bstride;
   p->bc = w; w += (size_t)B * TT_H;
   p->dGc = w; w += (size_t)B * Zp;
-  p->dhbuf = w; w += (size_t)B * N * TT_H;
+  p->sgn = reinterpret_cast<uint32_t*>(w); p->sgn_stride = (size_t)B * N * 4; w += (2 + 2 * (size_t)c.layers) * p->sgn_stride;
   p->rowjet = reinterpret_cast<const int*>(w);
 }
 
@@ -616,18 +709,16 @@ __global__ void rowlin_check_kernel(const RowLinP p, const float* __restrict__ W
   const int jet = p.rowjet[r];
   float a = 0.f;
   for (int k = 0; k < 128; ++k) {
-    float x = p.X[(size_t)r * 128 + k];
-    if (p.bc) x += p.bc[(size_t)jet * 128 + k];
-    if (p.S) x *= tt_dlrelu(p.S[(size_t)r * 128 + k], p.slope);
+    const float x = p.X[(size_t)r * 128 + k];
     // forward: W[o][k] = Wt[(k0 + k) * ldo + o];  transposed: contraction over the linear's outputs: W[k][o]
     const float w = transposed ? Wt[(size_t)(k0 + o) * ldo + k] : Wt[(size_t)(k0 + k) * ldo + o];
     a = fmaf(x, w, a);
   }
   if (p.bias) a += p.bias[(size_t)jet * p.bias_ld + o];
-  const float* res = p.r_is_xout ? p.Xout : p.R;
-  if (res) a += res[(size_t)r * 128 + o];
+  if (p.R) a += p.R[(size_t)r * 128 + o];
+  if (p.bc) a += p.bc[(size_t)jet * 128 + o];
   if (p.act) a = tt_lrelu(a, p.slope);
-  if (p.E) a *= tt_dlrelu(p.E[(size_t)r * 128 + o], p.slope);
+  if (p.E) a *= ((p.E[(size_t)r * 4 + (o >> 5)] >> (o & 31)) & 1u) ? 1.f : p.slope;
   const float d = fabsf(a - p.Y[(size_t)r * 128 + o]);
   atomicMax(reinterpret_cast<int*>(maxerr), __float_as_int(d));
   atomicMax(reinterpret_cast<int*>(maxerr + 1), __float_as_int(fabsf(a)));
@@ -640,13 +731,11 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
     PFM_CUDA_CHECK(cudaFuncSetAttribute(rowlin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  q.Wimg = reinterpret_cast<const uint8_t*>(h->tt_store) + (size_t)(transposed ? tt_gemm_index_bwd(gemm) : tt_gemm_index_fwd(gemm)) * 2 * TT_IMG;
+  q.Wimg = reinterpret_cast<const uint8_t*>(h->tt_store) + (size_t)(2 * gemm + (transposed ? 1 : 0)) * 2 * TT_IMG;
   q.rowjet = c.rowjet; q.n_total = c.n_total; q.slope = c.slope;
   rowlin_tc_kernel<<<grid, 256, smem, st>>>(q);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->last_launches++;
-  static const bool sync_each = getenv("PFM_TT_SYNC") != nullptr;
-  if (sync_each) PFM_CUDA_CHECK(cudaStreamSynchronize(st));
   static const bool check = getenv("PFM_TT_CHECK") != nullptr;
   if (check) {
     static float* dm = nullptr;
@@ -663,91 +752,119 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
   return PFM_OK;
 }
 
+// The training plan of this path: rows of the packed particles (prefix sum of the multiplicities) and the row -> jet map.
+// (plan_count_kernel has filled n_real / ridx.)
+int tt_plan(pfm_epic* h, int B, int N, cudaStream_t st) {
+  int rc = tt_workspace(h, B, N);
+  if (rc != PFM_OK) return rc;
+  const pfm_epic_cfg& c = h->cfg;
+  const int Zp = (c.latent + 3) & ~3;
+  int* rowjet = reinterpret_cast<int*>(h->tt_ws + (size_t)B * h->bstride + (size_t)B * TT_H + (size_t)B * Zp +
+                                       (2 + 2 * (size_t)c.layers) * (size_t)B * N * 4);
+  tt_rows_kernel<<<1, 1024, 0, st>>>(h->plan.n_real, B, h->plan.rowoff, h->plan.n_total);
+  tt_rowjet_kernel<<<(B + 7) / 8, 256, 0, st>>>(h->plan.n_real, h->plan.rowoff, B, rowjet);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->last_launches += 2;
+  return PFM_OK;
+}
+
 // forward with saved activations (+ fused flow-matching loss): fills act / yact / jact / dpre3 / loss_acc like
-// epic_simt.cu's TRAIN instantiation
+// epic_simt.cu's TRAIN instantiation (tt_plan has run)
 int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   const pfm_epic_cfg& c = h->cfg;
-  int rc = tt_workspace(h, a.B, a.N);
-  if (rc != PFM_OK) return rc;
+  int rc;
   if (!h->tt_store || h->tt_dirty) { rc = tt_pack(h, st); if (rc != PFM_OK) return rc; }
   TtCommon p;
   tt_common(h, a.B, a.N, a.Kx, a.xin_off, a.lay, &p);
   p.x_in = a.x_in; p.x_out = a.x_out; p.tjet = a.t; p.noise0 = a.noise0; p.noise1 = a.noise1; p.loss_kind = a.loss_kind; p.sigma = a.sigma;
-  const size_t SS = a.lay.stage_stride;
+  const size_t SS = a.lay.stage_stride, GS = p.sgn_stride;
   const int grid_rows = 4 * h->sm_count;
   const int grid_gemm = h->sm_count;
-  tt_rowjet_kernel<<<a.B, 64, 0, st>>>(h->plan.n_real, h->plan.rowoff, a.B, const_cast<int*>(p.rowjet));
+  const int jet_ctas = a.B;
   tt_beff_kernel<<<a.B, 256, 0, st>>>(h->tbias, a.tbias_per_jet, a.has_cbias ? h->cbias : nullptr, h->bstride, p.beff);
   if (a.loss_kind < 0) PFM_CUDA_CHECK(cudaMemsetAsync(a.x_out, 0, sizeof(float) * (size_t)a.B * a.N * c.feats, st));
-  tt_stem_kernel<<<grid_rows, 256, 0, st>>>(p);
-  h->last_launches += 3;
+  tt_stem_kernel<<<(a.B * a.N + 7) / 8 < 16 * grid_rows ? (a.B * a.N + 7) / 8 : 16 * grid_rows, 256, 0, st>>>(p);
+  h->last_launches += 2;
   {   // fc_l2: h0 = lrelu(h1 . W^T + b + h1)     (epic.py:364-367)
     RowLinP q; memset(&q, 0, sizeof(q));
     q.X = h->act; q.R = h->act; q.bias = p.beff + h->lin_host[LIN_L2].bias_off; q.bias_ld = h->bstride; q.act = 1; q.Y = h->act + SS;
+    q.sgn_out = p.sgn + GS;
     if ((rc = tt_rowlin(h, q, 0, 0, p, grid_gemm, st)) != PFM_OK) return rc;
   }
-  tt_jet_fwd_kernel<<<a.B, 128, 0, st>>>(p, 0);
+  tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, 0);
   h->last_launches++;
   for (int l = 0; l < c.layers; ++l) {
-    tt_jet_fwd_kernel<<<a.B, 128, 0, st>>>(p, l + 1);
+    tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, l + 1);
     h->last_launches++;
     RowLinP q; memset(&q, 0, sizeof(q));      // fc_local1: u = lrelu(h . W1^T + beff1[jet])     (epic.py:194-196)
     q.X = h->act + (size_t)(1 + 2 * l) * SS; q.bias = p.beff + h->lin_host[LIN_LAYER0 + 4 * l + 2].bias_off; q.bias_ld = h->bstride;
-    q.act = 1; q.Y = h->act + (size_t)(2 + 2 * l) * SS;
+    q.act = 1; q.Y = h->act + (size_t)(2 + 2 * l) * SS; q.sgn_out = p.sgn + (size_t)(2 + 2 * l) * GS;
     if ((rc = tt_rowlin(h, q, 1 + 2 * l, 0, p, grid_gemm, st)) != PFM_OK) return rc;
     memset(&q, 0, sizeof(q));                 // fc_local2: h' = lrelu(u . W2^T + beff2[jet] + h)  (epic.py:198-200)
     q.X = h->act + (size_t)(2 + 2 * l) * SS; q.R = h->act + (size_t)(1 + 2 * l) * SS;
     q.bias = p.beff + h->lin_host[LIN_LAYER0 + 4 * l + 3].bias_off; q.bias_ld = h->bstride; q.act = 1; q.Y = h->act + (size_t)(3 + 2 * l) * SS;
+    q.sgn_out = p.sgn + (size_t)(3 + 2 * l) * GS;
     if ((rc = tt_rowlin(h, q, 2 + 2 * l, 0, p, grid_gemm, st)) != PFM_OK) return rc;
   }
-  tt_head_kernel<<<grid_rows, 256, 0, st>>>(p);
+  tt_head_kernel<<<grid_rows, 128, 0, st>>>(p);
   h->last_launches++;
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
 
-// backward: fills dact / dbeff (/ dxs) like epic_train.cu::epic_bwd_kernel
+// backward: fills dact / dbeff (/ dxs) like epic_train.cu::epic_bwd_kernel.  Every launch is a plain GEMM pass: the masked
+// gradient entering a layer is produced by the epilogue of the pass before it.
 int tt_train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
   const pfm_epic_cfg& c = h->cfg;
-  // independent of which path produced the saved forward (same arrays): workspace, images and the row -> jet map are
-  // (re)made here, so a forward of the CUDA-core kernels can be differentiated by this path and vice versa
-  int rc = tt_workspace(h, a.B, a.N);
-  if (rc != PFM_OK) return rc;
+  int rc;
+  if (!h->train_tc) {          // the saved forward came from the CUDA-core kernels: this path's row map and sign bits are missing
+    if ((rc = tt_plan(h, a.B, a.N, st)) != PFM_OK) return rc;
+  }
   if (!h->tt_store || h->tt_dirty) { rc = tt_pack(h, st); if (rc != PFM_OK) return rc; }
   TtCommon p;
   tt_common(h, a.B, a.N, a.Kx, a.xin_off, a.lay, &p);
-  tt_rowjet_kernel<<<a.B, 64, 0, st>>>(h->plan.n_real, h->plan.rowoff, a.B, const_cast<int*>(p.rowjet));
-  h->last_launches++;
   p.dxs = a.want_dx ? h->dxs : nullptr;
-  const size_t SS = a.lay.stage_stride;
+  const size_t SS = a.lay.stage_stride, GS = p.sgn_stride;
   const int Zp = a.lay.Zp;
   const int grid_rows = 4 * h->sm_count;
   const int grid_gemm = h->sm_count;
+  const int jet_ctas = a.B;
+  if (!h->train_tc) {
+    tt_sign_kernel<<<dim3(2 * h->sm_count, 2 + 2 * c.layers), 256, 0, st>>>(h->act, SS, p.sgn, GS, p.n_total);
+    h->last_launches++;
+  }
   PFM_CUDA_CHECK(cudaMemsetAsync(p.bc, 0, sizeof(float) * ((size_t)a.B * TT_H + (size_t)a.B * Zp), st));      // bc and dGc are adjacent
-  tt_head_bwd_kernel<<<grid_rows, 256, 0, st>>>(p);
+  tt_head_bwd_kernel<<<grid_rows, 256, 0, st>>>(p);            // dz2 of the last layer -> dact[1 + 2L]
   h->last_launches++;
   for (int l = c.layers - 1; l >= 0; --l) {
     const bool first = l == c.layers - 1;
     RowLinP q; memset(&q, 0, sizeof(q));
-    // dz2 = (dh + bc[jet]) * lrelu'(h_{l+1}) -> dact[3+2l];  du = dz2 . W2;  dz1 = du * lrelu'(u_l) -> dact[2+2l]
-    q.X = p.dhbuf; q.bc = first ? nullptr : p.bc; q.S = h->act + (size_t)(3 + 2 * l) * SS; q.Xout = h->dact + (size_t)(3 + 2 * l) * SS;
-    q.E = h->act + (size_t)(2 + 2 * l) * SS; q.Y = h->dact + (size_t)(2 + 2 * l) * SS;
+    // dz1 = (dz2 . W2) * lrelu'(u_l) -> dact[2+2l]
+    q.X = h->dact + (size_t)(3 + 2 * l) * SS; q.E = p.sgn + (size_t)(2 + 2 * l) * GS; q.Y = h->dact + (size_t)(2 + 2 * l) * SS;
     if ((rc = tt_rowlin(h, q, 2 + 2 * l, 1, p, grid_gemm, st)) != PFM_OK) return rc;
-    // dh = dz2 (residual) + dz1 . W1(main)
+    tt_jet_bwd_kernel<<<jet_ctas, 256, 0, st>>>(p, l + 1, first ? 1 : 0);
+    h->last_launches++;
+    if (l == 0) {
+      tt_jet_bwd_kernel<<<jet_ctas, 256, 0, st>>>(p, 0, 0);
+      h->last_launches++;
+    }
+    // gradient entering the layer below (pre-activation of its fc_local2, or of fc_l2 for l == 0):
+    //   (dz2 [residual] + dz1 . W1(main) + bc[jet] [pooling]) * lrelu'(h_l) -> dact[1+2l]
     memset(&q, 0, sizeof(q));
-    q.X = h->dact + (size_t)(2 + 2 * l) * SS; q.R = h->dact + (size_t)(3 + 2 * l) * SS; q.Y = p.dhbuf;
+    q.X = h->dact + (size_t)(2 + 2 * l) * SS; q.R = h->dact + (size_t)(3 + 2 * l) * SS; q.bc = p.bc; q.E = p.sgn + (size_t)(1 + 2 * l) * GS;
+    q.Y = h->dact + (size_t)(1 + 2 * l) * SS;
     if ((rc = tt_rowlin(h, q, 1 + 2 * l, 1, p, grid_gemm, st)) != PFM_OK) return rc;
-    tt_jet_bwd_kernel<<<a.B, 128, 0, st>>>(p, l + 1, first ? 1 : 0);
+  }
+  if (c.layers == 0) {
+    tt_jet_bwd_kernel<<<jet_ctas, 256, 0, st>>>(p, 0, 1);
     h->last_launches++;
   }
-  tt_jet_bwd_kernel<<<a.B, 128, 0, st>>>(p, 0, c.layers == 0 ? 1 : 0);
-  h->last_launches++;
-  {   // stem: dz_l2 = (dh + bc) * lrelu'(h0) -> dact[1];  dz_l1 = (dz_l2 . W_l2 + dz_l2) * lrelu'(h1) -> dact[0]
+  {   // stem: dz_l1 = (dz_l2 . W_l2 + dz_l2) * lrelu'(h1) -> dact[0]
     RowLinP q; memset(&q, 0, sizeof(q));
-    q.X = p.dhbuf; q.bc = p.bc; q.S = h->act + SS; q.Xout = h->dact + SS; q.r_is_xout = 1; q.E = h->act; q.Y = h->dact;
+    q.X = h->dact + SS; q.R = h->dact + SS; q.E = p.sgn; q.Y = h->dact;
     if ((rc = tt_rowlin(h, q, 0, 1, p, grid_gemm, st)) != PFM_OK) return rc;
   }
-  tt_stem_bwd_kernel<<<a.B, 128, 0, st>>>(p);
+  tt_stem_bwd_kernel<<<a.B, 256, 0, st>>>(p);
   h->last_launches++;
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;

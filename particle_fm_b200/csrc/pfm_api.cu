@@ -411,6 +411,15 @@ static size_t grad_floats(const pfm_epic* h) {
   return n;
 }
 
+// CTA groups of the fused CUDA-core training kernels (needed by their backward when the forward ran on the tensor-core path)
+int train_plan_groups(pfm_epic* h, int B, const TrainLayout& lay, cudaStream_t st) {
+  plan_group_kernel<<<1, 1024, sizeof(int) * B, st>>>(h->plan.n_real, B, lay.R_cap, lay.J_cap, h->plan.groups, h->plan.n_groups,
+                                                     h->plan.counter, h->plan.rowoff, h->plan.n_total);
+  PFM_CUDA_CHECK(cudaGetLastError());
+  h->last_launches++;
+  return PFM_OK;
+}
+
 // forward half shared by pfm_epic_loss_fwd_bwd and pfm_epic_forward_train
 static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, const float* t_code_in, int t_in,
                                 const float* x, float* out, const float* t_jet, const float* noise0, const float* noise1,
@@ -443,9 +452,15 @@ static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, co
   rc = ensure_plan(h, B, N);
   if (rc != PFM_OK) return rc;
   plan_count_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, B, N, h->plan.n_real, h->plan.ridx);
-  plan_group_kernel<<<1, 1024, sizeof(int) * B, st>>>(h->plan.n_real, B, lay->R_cap, lay->J_cap, h->plan.groups, h->plan.n_groups,
-                                                     h->plan.counter, h->plan.rowoff, h->plan.n_total);
-  h->last_launches += 2;
+  h->train_tc = tt_enabled(h);
+  if (h->train_tc) {           // rows only: prefix sum of the multiplicities + row -> jet map (no CTA groups)
+    if ((rc = tt_plan(h, B, N, st)) != PFM_OK) return rc;
+    h->last_launches += 1;
+  } else {
+    plan_group_kernel<<<1, 1024, sizeof(int) * B, st>>>(h->plan.n_real, B, lay->R_cap, lay->J_cap, h->plan.groups, h->plan.n_groups,
+                                                       h->plan.counter, h->plan.rowoff, h->plan.n_total);
+    h->last_launches += 2;
+  }
   PFM_CUDA_CHECK(cudaGetLastError());
   const size_t rows = (size_t)B * N;
   const size_t stages = 2 + 2 * (size_t)c.layers;
@@ -467,7 +482,6 @@ static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, co
   a.x_in = x; a.x_out = out; a.t = t_jet; a.noise0 = noise0; a.noise1 = noise1; a.loss_kind = loss_kind; a.sigma = sigma;
   a.B = B; a.N = N; a.Kx = Kx; a.xin_off = xin_off; a.has_cbias = cond_dim > 0; a.tbias_per_jet = per_jet ? 1 : 0;
   a.lay = *lay;
-  h->train_tc = tt_enabled(h);
   if (h->train_tc) {
     rc = tt_train_forward(h, a, st);
     if (rc != PFM_OK) return rc;

@@ -184,6 +184,8 @@ int xty_launch_one(const float* Y, int ldy, const float* X, int ldx, float* dW, 
 int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* TC, int* RB, int* KC);
 // training with the per-particle GEMMs on tcgen05, fp32-accurate 3-term bf16 split (epic_train_tc.cu); hid == 128
 bool tt_enabled(const pfm_epic* h);
+int tt_plan(pfm_epic* h, int B, int N, cudaStream_t st);
+int train_plan_groups(pfm_epic* h, int B, const TrainLayout& lay, cudaStream_t st);
 int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st);
 int tt_train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st);
 // bf16 tcgen05 path (epic_tc.cu)

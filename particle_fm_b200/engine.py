@@ -126,11 +126,15 @@ class EpicEngine:
         self._keepalive = (ws, bs)      # until the stream has consumed them
         self.weights_key = key
 
-    def set_params(self, linears, key=None):
-        """Raw parameters of the linears (weight_v / weight_g / bias, or weight / bias for a plain linear): the library folds
-        the weight norm and repacks in one launch (pfm_epic_set_params)."""
-        if len(linears) != self.n_lin:
-            raise ValueError(f"expected {self.n_lin} linears, got {len(linears)}")
+    def _raw_ptrs(self, linears):
+        """(key, arrays of device pointers (weight_v | weight, weight_g | NULL, bias), keep-alive tensors) of the linears'
+        raw parameters.  The ctypes arrays are cached: optimizers update parameters in place, so between two training steps
+        the addresses do not change and the 3 x n_lin tensor conversions are skipped (host time is what bounds a step)."""
+        key = tuple((lin.weight_v if lin.weight_norm else lin.weight).data_ptr() for lin in linears) + \
+            tuple(lin.bias.data_ptr() for lin in linears) + tuple(lin.weight_g.data_ptr() if lin.weight_norm else 0 for lin in linears)
+        c = getattr(self, "_ptr_cache", None)
+        if c is not None and c[0] == key:
+            return c
         vs, gs, bs = [], [], []
         for k, ((o, i), lin) in enumerate(zip(self.linear_shapes_cached(), linears)):
             v = _f32c(lin.weight_v if lin.weight_norm else lin.weight, self.device)
@@ -141,9 +145,24 @@ class EpicEngine:
             vs.append(v); gs.append(g); bs.append(b)
         n = self.n_lin
         arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        # cacheable only if the library reads the parameters' own storage (fp32, contiguous, on this device): no copies were made
+        own = all(t is None or t.data_ptr() == src.data_ptr() for ts, srcs in
+                  ((vs, [lin.weight_v if lin.weight_norm else lin.weight for lin in linears]),
+                   (gs, [lin.weight_g if lin.weight_norm else None for lin in linears]),
+                   (bs, [lin.bias for lin in linears])) for t, src in zip(ts, srcs) if t is not None)
+        c = (key, arr(vs), arr(gs), arr(bs), (vs, gs, bs))
+        self._ptr_cache = c if own else None
+        return c
+
+    def set_params(self, linears, key=None):
+        """Raw parameters of the linears (weight_v / weight_g / bias, or weight / bias for a plain linear): the library folds
+        the weight norm and repacks in one launch (pfm_epic_set_params)."""
+        if len(linears) != self.n_lin:
+            raise ValueError(f"expected {self.n_lin} linears, got {len(linears)}")
+        _, av, ag, ab, keep = self._raw_ptrs(linears)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.pfm_epic_set_params(self._h, arr(vs), arr(gs), arr(bs), n, self._stream()), "pfm_epic_set_params")
-        self._keepalive = (vs, gs, bs)
+            _lib.check(self.lib.pfm_epic_set_params(self._h, av, ag, ab, self.n_lin, self._stream()), "pfm_epic_set_params")
+        self._keepalive = keep
         self.weights_key = key
 
     def linear_shapes_cached(self):
@@ -153,26 +172,40 @@ class EpicEngine:
 
     def param_grads(self, flat: Tensor, scale: Optional[Tensor], linears):
         """Flat folded-weight gradient -> gradients of the raw parameters, one launch (pfm_epic_param_grads).
-        Returns [(d weight_v | d weight, d weight_g | None, d bias)] in the order of ``linears``."""
+        Returns [(d weight_v | d weight, d weight_g | None, d bias)] in the order of ``linears``: views of ONE buffer laid out
+        [dv_0 | dg_0 | db_0 | dv_1 | ...] (``self.last_param_grad_buffer``), which a flat optimizer can consume directly."""
         n = self.n_lin
-        vs = [_f32c(lin.weight_v if lin.weight_norm else lin.weight, self.device) for lin in linears]
-        gs = [_f32c(lin.weight_g, self.device) if lin.weight_norm else None for lin in linears]
-        total = sum(v.numel() + (0 if g is None else g.numel()) + v.shape[0] for v, g in zip(vs, gs))
+        _, av, ag, _, keep = self._raw_ptrs(linears)
+        vs, gs, _ = keep
+        lay = getattr(self, "_pg_layout", None)
+        if lay is None or lay[0] != n:
+            total, offs = 0, []
+            for v, g in zip(vs, gs):
+                o_v = total; total += v.numel()
+                o_g = None
+                if g is not None:
+                    o_g = total; total += g.numel()
+                o_b = total; total += v.shape[0]
+                offs.append((o_v, o_g, o_b, tuple(v.shape), None if g is None else tuple(g.shape)))
+            lay = (n, total, offs)
+            self._pg_layout = lay
+        _, total, offs = lay
         buf = torch.empty(total, device=self.device, dtype=torch.float32)     # one allocation, per-parameter views
-        out, off = [], 0
-        for v, g in zip(vs, gs):
-            dv = buf[off:off + v.numel()].view(v.shape); off += v.numel()
-            dg = None
-            if g is not None:
-                dg = buf[off:off + g.numel()].view(g.shape); off += g.numel()
-            db = buf[off:off + v.shape[0]]; off += v.shape[0]
+        out = []
+        for (o_v, o_g, o_b, shv, shg) in offs:
+            dv = buf[o_v:o_v + shv[0] * shv[1]].view(shv)
+            dg = None if o_g is None else buf[o_g:o_g + shg[0] * (shg[1] if len(shg) > 1 else 1)].view(shg)
+            db = buf[o_b:o_b + shv[0]]
             out.append((dv, dg, db))
-        arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        base = buf.data_ptr()
+        adv = (C.c_void_p * n)(*[base + 4 * o[0] for o in offs])
+        adg = (C.c_void_p * n)(*[None if o[1] is None else base + 4 * o[1] for o in offs])
+        adb = (C.c_void_p * n)(*[base + 4 * o[2] for o in offs])
         scale = None if scale is None else _f32c(scale, self.device).reshape(1)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.pfm_epic_param_grads(self._h, _ptr(flat), _ptr(scale), arr(vs), arr(gs), arr([d[0] for d in out]),
-                                                     arr([d[1] for d in out]), arr([d[2] for d in out]), n, self._stream()),
+            _lib.check(self.lib.pfm_epic_param_grads(self._h, _ptr(flat), _ptr(scale), av, ag, adv, adg, adb, n, self._stream()),
                        "pfm_epic_param_grads")
+        self.last_param_grad_buffer = buf
         return out
 
     # -- hot path ------------------------------------------------------------------------------

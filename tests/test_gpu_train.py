@@ -375,3 +375,42 @@ def test_tensor_core_training_backward_matches_cuda_core_backward():
     gx_b, flat_b = eng.backward(ticket, saved, gout, True, True)
     eng.set_train_mode("auto")
     assert rel_l2(gx_a, gx_b) < 1e-5 and rel_l2(flat_a, flat_b) < 1e-5
+
+
+def test_fused_clip_adamw_matches_torch():
+    """particle_fm_b200.optim.FusedClipAdamW (pfm_clip_adamw: global-norm clip + AdamW + EMA over flat buffers, two launches)
+    against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW + the reference's EMA recurrence (callbacks/ema.py:77-81) on
+    the real training step of the default net, three steps."""
+    from particle_fm_b200.optim import FusedClipAdamW
+    g = Golden("c1_jetnet30")
+    x = (g.x * 5.0 * g.mask).to(DEV)
+    mask = g.mask.to(DEV)
+    ma = build_module(g.ctor, g.sd, device=DEV)
+    mb = build_module(g.ctor, g.sd, device=DEV)
+    oa = torch.optim.AdamW(ma.parameters(), lr=1e-3, weight_decay=5e-5)
+    ob = FusedClipAdamW(mb.parameters(), lr=1e-3, weight_decay=5e-5, max_grad_norm=0.5, ema_decay=0.999)
+    ema_ref = [p.detach().clone() for p in ma.parameters()]
+    for it in range(3):
+        # the gradients come from the fused model's real training step and are handed to both optimizers (Adam's update
+        # m/sqrt(v) amplifies rounding noise of near-zero gradients to +-lr, so each needs the SAME gradients)
+        torch.manual_seed(100 + it)
+        ob.zero_grad(set_to_none=True)
+        loss = mb.loss(x, mask=mask, cond=None)
+        loss.backward()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pa.grad = pb.grad.detach().clone()
+        norm = float(torch.nn.utils.clip_grad_norm_(ma.parameters(), 0.5))
+        oa.step()
+        ob.step()
+        for e, p_ in zip(ema_ref, ma.parameters()):
+            diff = e - p_.detach()
+            diff.mul_(1.0 - 0.999)
+            e.sub_(diff)
+        assert abs(float(ob.last_grad_norm) - norm) <= 1e-5 * norm
+        for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7), (it, k, float((pa - pb).abs().max()))
+    for e, eb in zip(ema_ref, ob.ema_parameters()):
+        assert torch.allclose(e, eb, rtol=1e-5, atol=1e-7)
+    # the parameters live in one flat buffer laid out like the library's flat gradient
+    ptrs = sorted(p.data_ptr() for p in mb.parameters())
+    assert ptrs[-1] - ptrs[0] < 4 * sum(p.numel() for p in mb.parameters())

@@ -9,8 +9,10 @@ torch.manual_seed(12345)
 from particle_fm_b200.models.flow_matching_module import SetFlowMatchingLitModule
 model = SetFlowMatchingLitModule(optimizer=None, **bench.YAML_NET).to(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-for mode in ("auto", "cuda_cores", "auto"):
-    r = bench.train_bench(model, dev, 1, 0, steps=10, warmup=3, B=B, mode=mode)
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["auto", "cuda_cores", "auto"]
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+for mode in modes:
+    r = bench.train_bench(model, dev, 1, 0, steps=steps, warmup=3 if steps > 2 else 2, B=B, mode=mode)
     print(mode, json.dumps({k: r[k] for k in ("value", "ms_per_step", "final_loss")}))
 eng = model.flows[0].net.engine()
 print("launches of the last step's library calls:", eng.last_launches())
