@@ -80,6 +80,7 @@ struct RowLinP {
   const int* rowjet;       // [rows]
   const int* n_total;
   float slope;
+  long long* prof;         // debug (PFM_TT_PROF): per-phase cycle counters of CTA 0
 };
 
 struct RowLinSmem {
@@ -91,7 +92,9 @@ struct RowLinSmem {
   uint32_t tmem;
 };
 
-__global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
+static constexpr int RL_THREADS = 256;
+
+__global__ void __launch_bounds__(RL_THREADS, 1) rowlin_tc_kernel(const RowLinP p) {
   extern __shared__ uint8_t smem_raw[];
   RowLinSmem& s = *reinterpret_cast<RowLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,10 +135,31 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
   // global memory wants consecutive threads on consecutive columns.  The rows go through a shared-memory staging buffer
   // (64 rows at a time; 16-byte chunk c of row r is stored at chunk c ^ (r & 31): conflict-free both ways), so that every
   // global load (residual) and store is a fully coalesced 512-byte row segment per warp.
+  // global operands of a tile's epilogue (residual, row -> jet, sign words): issued one pipeline stage early, so that their
+  // HBM latency hides behind the operand conversion of the next tile instead of stalling the 8 warps of the CTA
+  float4 rr[2][8];
+  int jets[2][8];
+  uint32_t eb[2][8];
+  auto epi_loads = [&](int t_local) {
+    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
+        const int r = tile * 128 + half * 64 + rl;
+        jets[half][i] = 0; eb[half][i] = 0xffffffffu;
+        if (r < rows) {
+          if (p.R) rr[half][i] = __ldcg(reinterpret_cast<const float4*>(p.R + (size_t)r * TT_H + c4 * 4));
+          if (p.bias || p.bc) jets[half][i] = p.rowjet[r];
+          if (p.E) eb[half][i] = __ldcg(p.E + (size_t)r * 4 + (c4 >> 3));
+        }
+      }
+  };
   auto epilogue = [&](int t_local) {
     const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
     const int q = warp & 3, hf = warp >> 2;
-#pragma unroll 1
+#pragma unroll
     for (int half = 0; half < 2; ++half) {
       if ((q >> 1) == half) {                              // warps owning TMEM lanes [64 half, 64 half + 64)
         const int rl = (q & 1) * 32 + lane;                // row inside the staging buffer
@@ -153,37 +177,36 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
         }
       }
       __syncthreads();
-      // all 256 threads: thread = (row, 16-byte chunk); a warp covers one full row per step
-#pragma unroll 2
-      for (int i = 0; i < 8; ++i) {
-        const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
-        const int r = tile * 128 + half * 64 + rl;
-        if (r < rows) {
-          const int o = c4 * 4;
-          float4 a = *reinterpret_cast<const float4*>(&s.stage[rl * TT_H + ((c4 ^ (rl & 31)) * 4)]);
-          const int jet = (p.bias || p.bc) ? p.rowjet[r] : 0;
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (p.R) {
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.R + (size_t)r * TT_H + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (p.bc) {
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.bc + (size_t)jet * TT_H + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
-          if (p.E) {
-            const uint32_t e = __ldcg(p.E + (size_t)r * 4 + (c4 >> 3)) >> ((c4 & 7) * 4);
-            a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
-          }
-          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
-          if (p.sgn_out) {                                 // 8 lanes hold the 32 columns of one sign word
-            uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((c4 & 7) * 4);
-            b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
-            if ((c4 & 7) == 0) p.sgn_out[(size_t)r * 4 + (c4 >> 3)] = b;
+      // all 256 threads: thread = (row, 16-byte chunk); a warp covers one full row per step.  All global loads of the 8 steps
+      // are issued before the first use (the residual comes from HBM: one exposed latency per half tile, not eight)
+      {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
+          const int r = tile * 128 + half * 64 + rl;
+          if (r < rows) {
+            const int o = c4 * 4;
+            float4 a = *reinterpret_cast<const float4*>(&s.stage[rl * TT_H + ((c4 ^ (rl & 31)) * 4)]);
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jets[half][i] * p.bias_ld + o));
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (p.R) { a.x += rr[half][i].x; a.y += rr[half][i].y; a.z += rr[half][i].z; a.w += rr[half][i].w; }
+            if (p.bc) {
+              const float4 b = __ldcg(reinterpret_cast<const float4*>(p.bc + (size_t)jets[half][i] * TT_H + o));
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
+            if (p.E) {
+              const uint32_t e = eb[half][i] >> ((c4 & 7) * 4);
+              a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
+            }
+            __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+            if (p.sgn_out) {                               // 8 lanes hold the 32 columns of one sign word
+              uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((c4 & 7) * 4);
+              b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
+              if ((c4 & 7) == 0) p.sgn_out[(size_t)r * 4 + (c4 >> 3)] = b;
+            }
           }
         }
       }
@@ -192,13 +215,22 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
     tc_fence_before();
   };
 
+  long long pt = 0, pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool prof = p.prof && blockIdx.x == 0 && tid == 0;
+#define TT_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
+  if (prof) pt = clock64();
   mbar_wait(&s.mbar_w, 0);
+  TT_PROF(0);
   for (int t = 0; t < my_tiles; ++t) {
+    if (t >= 1) epi_loads(t - 1);
+    TT_PROF(1);
     mbar_wait(&s.mbar_raw, (uint32_t)(t & 1));             // the tile's fp32 rows have landed
+    TT_PROF(2);
     if (t >= 1) {                                          // the operand buffer is free once the previous tile's MMAs are done
       mbar_wait(&s.mbar[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
       tc_fence_after();
     }
+    TT_PROF(3);
     // raw fp32 [128][128] -> bf16 hi / lo, K-major SWIZZLE_128B (thread = 4 consecutive columns of a row)
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
@@ -215,7 +247,9 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
       *reinterpret_cast<uint2*>(s.A[1] + off) = l2;
     }
     fence_proxy_async();
+    TT_PROF(4);
     __syncthreads();
+    TT_PROF(5);
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -234,11 +268,16 @@ __global__ void __launch_bounds__(256, 1) rowlin_tc_kernel(const RowLinP p) {
       }
       __syncwarp();
     }
+    TT_PROF(6);
     if (t >= 1) epilogue(t - 1);                           // overlaps the MMAs of this tile and the copy of the next
+    TT_PROF(7);
   }
+  epi_loads(my_tiles - 1);
   mbar_wait(&s.mbar[(my_tiles - 1) & 1], (uint32_t)(((my_tiles - 1) >> 1) & 1));
   tc_fence_after();
   epilogue(my_tiles - 1);
+  TT_PROF(7);
+  if (prof) for (int k = 0; k < 8; ++k) p.prof[k] = pc[k];
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 256);
 }
@@ -733,9 +772,22 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
   }
   q.Wimg = reinterpret_cast<const uint8_t*>(h->tt_store) + (size_t)(2 * gemm + (transposed ? 1 : 0)) * 2 * TT_IMG;
   q.rowjet = c.rowjet; q.n_total = c.n_total; q.slope = c.slope;
-  rowlin_tc_kernel<<<grid, 256, smem, st>>>(q);
+  static const bool do_prof = getenv("PFM_TT_PROF") != nullptr;
+  static long long* dprof = nullptr;
+  if (do_prof) {
+    if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, 64));
+    q.prof = dprof;
+  }
+  rowlin_tc_kernel<<<grid, RL_THREADS, smem, st>>>(q);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->last_launches++;
+  if (do_prof) {
+    long long hp[8];
+    PFM_CUDA_CHECK(cudaMemcpyAsync(hp, dprof, 64, cudaMemcpyDeviceToHost, st));
+    PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[pfm tt prof] gemm %2d %s  w %lld | epi_loads %lld  wait_raw %lld  wait_mma %lld  convert %lld  sync %lld  issue %lld  epilogue %lld\n",
+            gemm, transposed ? "bwd" : "fwd", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+  }
   static const bool check = getenv("PFM_TT_CHECK") != nullptr;
   if (check) {
     static float* dm = nullptr;
