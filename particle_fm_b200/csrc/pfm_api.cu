@@ -808,11 +808,7 @@ int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* 
   wn_fold_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_ptrs, n);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
-  h->tc_dirty = true; h->tt_dirty = true;
-  if (h->precision == PFM_PREC_BF16) {
-    rc = tc_pack_weights(h, st);
-    if (rc != PFM_OK) return rc;
-  }
+  h->tc_dirty = true; h->tt_dirty = true;      // the bf16 / hi-lo images are repacked lazily by the next call that needs them
   return PFM_OK;
 }
 

@@ -191,11 +191,23 @@ class EpicEngine:
             self._pg_layout = lay
         _, total, offs = lay
         buf = torch.empty(total, device=self.device, dtype=torch.float32)     # one allocation, per-parameter views
-        out = []
+        sizes = getattr(self, "_pg_sizes", None)
+        if sizes is None:
+            sizes = []
+            for (o_v, o_g, o_b, shv, shg) in offs:
+                sizes.append(shv[0] * shv[1])
+                if o_g is not None:
+                    sizes.append(shg[0] * (shg[1] if len(shg) > 1 else 1))
+                sizes.append(shv[0])
+            self._pg_sizes = sizes
+        parts = buf.split_with_sizes(sizes)           # one call for all views (host time bounds a training step)
+        out, k = [], 0
         for (o_v, o_g, o_b, shv, shg) in offs:
-            dv = buf[o_v:o_v + shv[0] * shv[1]].view(shv)
-            dg = None if o_g is None else buf[o_g:o_g + shg[0] * (shg[1] if len(shg) > 1 else 1)].view(shg)
-            db = buf[o_b:o_b + shv[0]]
+            dv = parts[k].view(shv); k += 1
+            dg = None
+            if o_g is not None:
+                dg = parts[k].view(shg); k += 1
+            db = parts[k]; k += 1
             out.append((dv, dg, db))
         base = buf.data_ptr()
         adv = (C.c_void_p * n)(*[base + 4 * o[0] for o in offs])
