@@ -167,14 +167,20 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024, mode="auto")
     x = (5.0 * torch.randn(B, N_PART, FEATS, generator=g) * mask_h).to(dev)
     mask = mask_h.to(dev)
     fused_opt = mode == "auto"
+    graphed = fused_opt and os.environ.get("PFM_BENCH_NO_GRAPH") is None
+    model.flows[0].net.engine().set_train_mode(mode)
     if fused_opt:          # clip 0.5 + AdamW in two launches over flat buffers (particle_fm_b200.optim)
         from particle_fm_b200.optim import FusedClipAdamW
-        opt = FusedClipAdamW(model.parameters(), lr=1e-3, weight_decay=5e-5, max_grad_norm=0.5)
+        opt = FusedClipAdamW(model.parameters(), lr=1e-3, weight_decay=5e-5, max_grad_norm=0.5, device_step_count=graphed)
     else:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=5e-5)
-    model.flows[0].net.engine().set_train_mode(mode)
+    if graphed:            # the whole step replayed from a CUDA graph (launch.GraphedTrainStep); t is drawn on the CPU per step
+        from particle_fm_b200.launch import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, x, mask)
 
     def step():
+        if graphed:
+            return gstep(x, mask)
         opt.zero_grad(set_to_none=True)
         loss = model.loss(x, mask=mask, cond=None)
         loss.backward()
@@ -203,8 +209,9 @@ def train_bench(model, dev, world, rank, steps=8, warmup=3, B=1024, mode="auto")
             "step": ("loss fwd+bwd with the per-particle GEMMs and their transposes on tcgen05 (3-term bf16 split, fp32-accurate), per-jet "
                      "MLPs on CUDA cores" if mode == "auto" else "fused loss fwd+bwd on fp32 CUDA cores") +
                     "; weight gradients on tcgen05 (3-term bf16 split) + in-library weight-norm fold/chain rule + flat-grad all-reduce + " +
-                    ("clip 0.5 + AdamW fused over flat buffers (pfm_clip_adamw, 2 launches)" if fused_opt else "torch clip_grad_norm_ 0.5 + torch.optim.AdamW"),
-            "kernels": mode,
+                    ("clip 0.5 + AdamW fused over flat buffers (pfm_clip_adamw, 2 launches)" if fused_opt else "torch clip_grad_norm_ 0.5 + torch.optim.AdamW") +
+                    ("; the whole step replayed from a CUDA graph (per-jet times drawn on the CPU generator each step)" if graphed else ""),
+            "kernels": mode, "cuda_graph": bool(graphed),
             "mean_real_particles": float(n_real.float().mean())}
 
 

@@ -249,9 +249,11 @@ int pfm_tf_loss_fwd_bwd(pfm_tf* h, const float* x1, const float* t, const float*
  * Fused optimizer step over FLAT fp32 buffers of n elements (all device memory): global-norm gradient clipping
  * (torch.nn.utils.clip_grad_norm_, Lightning gradient_clip_val), AdamW (torch.optim.AdamW, configs/model/flow_matching.yaml:3-7)
  * and, if ema != NULL, the EMA callback's update ema -= (ema - w) * (1 - ema_decay) (callbacks/ema.py:73-81), in two launches.
- *   step       1-based step count (bias corrections 1 - beta^step)
+ *   step       1-based step count (bias corrections 1 - beta^step); step <= 0: the count is kept ON THE DEVICE in
+ *              workspace[2] (as an int, start it at 0) and incremented by the call -- for replay from a CUDA graph
  *   max_norm   <= 0: no clipping
- *   workspace  2 device floats: [0] scratch (sum of squares), [1] receives the total gradient norm before clipping */
+ *   workspace  3 device words: [0] scratch (sum of squares), [1] receives the total gradient norm before clipping,
+ *              [2] the device-side step count */
 int pfm_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float max_norm, int step, float* ema, float ema_decay,
                    float* workspace, void* stream);

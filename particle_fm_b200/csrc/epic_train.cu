@@ -726,8 +726,8 @@ int train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st) {
     PFM_CUDA_CHECK(cudaMalloc(&h->jobs_dev, bytes));
     h->jobs_cap = bytes;
   }
-  // pageable source: the runtime stages the table before cudaMemcpyAsync returns, no stream synchronisation needed
-  PFM_CUDA_CHECK(cudaMemcpyAsync(h->jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice, st));
+  rc = upload_table(h, 2, h->jobs_dev, jobs.data(), bytes, st);      // pinned staging, skipped when unchanged (CUDA-graph safe)
+  if (rc != PFM_OK) return rc;
   const size_t maxrows = maxrows_part > maxrows_jet ? maxrows_part : maxrows_jet;
   while ((int)h->grad_ev.size() < n_chunks) {
     cudaEvent_t e;

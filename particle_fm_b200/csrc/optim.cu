@@ -26,11 +26,15 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
-struct AdamP { float lr, b1, b2, eps, wd, max_norm, bc1, bc2_sqrt, ema_keep; };
+struct AdamP { float lr, b1, b2, eps, wd, max_norm, ema_keep; };
 
 __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, float* __restrict__ ema, long long n,
-                                                         const float* __restrict__ sumsq, float* __restrict__ norm_out, AdamP a) {
+                                                         const float* __restrict__ sumsq, float* __restrict__ norm_out,
+                                                         const int* __restrict__ step_dev, int step_host, AdamP a) {
+  // the step count lives on the device when the caller replays this launch from a CUDA graph (bumped by step_bump_kernel)
+  const float stepf = (float)(step_dev ? *step_dev : step_host);
+  const float bc1 = 1.f - powf(a.b1, stepf), bc2_sqrt = sqrtf(1.f - powf(a.b2, stepf));
   float coef = 1.f;
   if (a.max_norm > 0.f) {
     const float total = sqrtf(*sumsq);
@@ -43,12 +47,14 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
     const float mi = a.b1 * m[i] + (1.f - a.b1) * gi;
     const float vi = a.b2 * v[i] + (1.f - a.b2) * gi * gi;
     m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
-    w -= (a.lr / a.bc1) * (mi / denom);
+    const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+    w -= (a.lr / bc1) * (mi / denom);
     p[i] = w;
     if (ema) { const float e = ema[i]; ema[i] = e - (e - w) * a.ema_keep; }     // ema.py:77-81
   }
 }
+
+__global__ void step_bump_kernel(int* step) { *step += 1; }
 
 }  // namespace pfm
 
@@ -57,7 +63,7 @@ using namespace pfm;
 extern "C" int pfm_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, float max_norm, int step, float* ema,
                               float ema_decay, float* workspace, void* stream) {
-  if (!params || !grads || !exp_avg || !exp_avg_sq || !workspace || n <= 0 || step < 1) { set_error("pfm_clip_adamw: bad argument"); return PFM_ERR_INVALID; }
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !workspace || n <= 0) { set_error("pfm_clip_adamw: bad argument"); return PFM_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 1184) blocks = 1184;                         // 8 CTAs per SM on 148 SMs, grid-stride beyond
@@ -67,10 +73,13 @@ extern "C" int pfm_clip_adamw(float* params, const float* grads, float* exp_avg,
   }
   AdamP a;
   a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
-  a.bc1 = 1.f - powf(beta1, (float)step);
-  a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   a.ema_keep = 1.f - ema_decay;
-  clip_adamw_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, ema, n, workspace, workspace + 1, a);
+  int* step_dev = nullptr;
+  if (step < 1) {               // step <= 0: the count is kept in workspace[2] (an int) and incremented here -- graph-replay safe
+    step_dev = reinterpret_cast<int*>(workspace + 2);
+    step_bump_kernel<<<1, 1, 0, st>>>(step_dev);
+  }
+  clip_adamw_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, ema, n, workspace, workspace + 1, step_dev, step, a);
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }

@@ -411,6 +411,36 @@ static size_t grad_floats(const pfm_epic* h) {
   return n;
 }
 
+static constexpr size_t kPinSlot = 64 * 1024;       // bytes per staging slot
+
+int upload_table(pfm_epic* h, int slot, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes + sizeof(void*) > kPinSlot) {               // too large for the staging slot: plain (pageable) copy
+    PFM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return PFM_OK;
+  }
+  if (!h->pin_stage) {
+    PFM_CUDA_CHECK(cudaHostAlloc(&h->pin_stage, 3 * kPinSlot, cudaHostAllocDefault));
+    h->pin_cap = 3 * kPinSlot;
+  }
+  uint8_t* stage = reinterpret_cast<uint8_t*>(h->pin_stage) + (size_t)slot * kPinSlot;
+  void** tag = reinterpret_cast<void**>(stage + kPinSlot - sizeof(void*));
+  if (h->pin_used[slot] == bytes && *tag == dst && memcmp(stage, src, bytes) == 0) return PFM_OK;    // device copy is current
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  // the slot may still be the source of the previous copy: wait for that copy only (an event, not the stream)
+  if (h->pin_ev_set[slot] && cs == cudaStreamCaptureStatusNone) PFM_CUDA_CHECK(cudaEventSynchronize(h->pin_ev[slot]));
+  memcpy(stage, src, bytes);
+  *tag = dst;
+  h->pin_used[slot] = bytes;
+  PFM_CUDA_CHECK(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, st));
+  if (cs == cudaStreamCaptureStatusNone) {
+    if (!h->pin_ev[slot]) PFM_CUDA_CHECK(cudaEventCreateWithFlags(&h->pin_ev[slot], cudaEventDisableTiming));
+    PFM_CUDA_CHECK(cudaEventRecord(h->pin_ev[slot], st));
+    h->pin_ev_set[slot] = true;
+  }
+  return PFM_OK;
+}
+
 // CTA groups of the fused CUDA-core training kernels (needed by their backward when the forward ran on the tensor-core path)
 int train_plan_groups(pfm_epic* h, int B, const TrainLayout& lay, cudaStream_t st) {
   plan_group_kernel<<<1, 1024, sizeof(int) * B, st>>>(h->plan.n_real, B, lay.R_cap, lay.J_cap, h->plan.groups, h->plan.n_groups,
@@ -578,6 +608,8 @@ int pfm_epic_create(const pfm_epic_cfg* cfg, int device, pfm_epic** out) {
   h->last_launches = 0; h->last_groups_host = 0;
   h->timing = false; h->ev_used = 0;
   h->step_kind = 0; h->step_coef = nullptr; h->step_noise = nullptr;
+  h->pin_stage = nullptr; h->pin_cap = 0; h->pin_used[0] = h->pin_used[1] = h->pin_used[2] = 0;
+  for (int i = 0; i < 3; ++i) { h->pin_ev[i] = nullptr; h->pin_ev_set[i] = false; }
   h->tt_store = nullptr; h->tt_bytes = 0; h->tt_dirty = true; h->tt_ws = nullptr; h->tt_ws_cap = 0; h->train_tc = false; h->train_mode = PFM_TRAIN_AUTO;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -637,6 +669,8 @@ void pfm_epic_destroy(pfm_epic* h) {
   if (h->tc_store) cudaFree(h->tc_store);
   if (h->tt_store) cudaFree(h->tt_store);
   if (h->tt_ws) cudaFree(h->tt_ws);
+  if (h->pin_stage) cudaFreeHost(h->pin_stage);
+  for (int i = 0; i < 3; ++i) if (h->pin_ev[i]) cudaEventDestroy(h->pin_ev[i]);
   if (h->wr_store) cudaFree(h->wr_store);
   if (h->act) cudaFree(h->act);
   if (h->dact) cudaFree(h->dact);
@@ -804,7 +838,8 @@ int pfm_epic_set_params(pfm_epic* h, const float* const* v, const float* const* 
     tab[i] = v[i]; tab[n + i] = g[i]; tab[2 * n + i] = b[i];
   }
   // pageable source: staged by the runtime before the call returns
-  PFM_CUDA_CHECK(cudaMemcpyAsync(h->wn_ptrs, tab.data(), sizeof(float*) * tab.size(), cudaMemcpyHostToDevice, st));
+  rc = upload_table(h, 0, h->wn_ptrs, tab.data(), sizeof(float*) * tab.size(), st);
+  if (rc != PFM_OK) return rc;
   wn_fold_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_ptrs, n);
   PFM_CUDA_CHECK(cudaGetLastError());
   h->weights_set = true;
@@ -825,7 +860,8 @@ int pfm_epic_param_grads(pfm_epic* h, const float* grad_flat, const float* scale
     if (!v[i] || !dv[i] || !db[i] || (g[i] && !dg[i])) { set_error("null pointer for linear %d", i); return PFM_ERR_INVALID; }
     tab[i] = v[i]; tab[n + i] = g[i]; tab[2 * n + i] = dv[i]; tab[3 * n + i] = dg[i]; tab[4 * n + i] = db[i];
   }
-  PFM_CUDA_CHECK(cudaMemcpyAsync(h->wn_ptrs + 3 * (size_t)n, tab.data(), sizeof(float*) * tab.size(), cudaMemcpyHostToDevice, st));
+  rc = upload_table(h, 1, h->wn_ptrs + 3 * (size_t)n, tab.data(), sizeof(float*) * tab.size(), st);
+  if (rc != PFM_OK) return rc;
   wn_bwd_kernel<<<h->wn_total_rows, 128, 0, st>>>(h->lin_dev, h->wn_rows, h->wn_goff, grad_flat, scale, h->wn_ptrs + 3 * (size_t)n, n);
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;

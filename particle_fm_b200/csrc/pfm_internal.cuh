@@ -100,6 +100,10 @@ struct pfm_epic {
   int train_mode;                   // pfm_train_mode requested by the host
   // diffusion step program of the next sampling call (pfm_epic_sample_diffusion; 0 = plain flow-matching ODE)
   int step_kind; const float* step_coef; const float* step_noise;
+  // pinned host staging of the small tables uploaded per call (pointer tables of the weight-norm kernels, weight-gradient job
+  // table): async copies from PINNED memory are legal inside CUDA-graph capture, pageable ones are not; an unchanged table is
+  // not uploaded again
+  void* pin_stage; size_t pin_cap; size_t pin_used[3]; cudaEvent_t pin_ev[3]; bool pin_ev_set[3];
   bool timing;
   std::vector<cudaEvent_t> ev_pool;   // start/stop pairs of the main kernel, one pair per chunk of a call
   int ev_used;
@@ -186,6 +190,9 @@ int simt_caps_for_train(const pfm_epic* h, int N, int* R_cap, int* J_cap, int* T
 bool tt_enabled(const pfm_epic* h);
 int tt_plan(pfm_epic* h, int B, int N, cudaStream_t st);
 int train_plan_groups(pfm_epic* h, int B, const TrainLayout& lay, cudaStream_t st);
+// upload `bytes` of a small host table to `dst` through slot `slot` (0..2) of the handle's pinned staging buffer; skipped when the
+// slot already holds the same bytes for the same destination
+int upload_table(pfm_epic* h, int slot, void* dst, const void* src, size_t bytes, cudaStream_t st);
 int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st);
 int tt_train_backward(pfm_epic* h, const TrainBwdArgs& a, cudaStream_t st);
 // bf16 tcgen05 path (epic_tc.cu)

@@ -38,6 +38,19 @@ class EpicDims:
         return self.t_dim > 0 and (self.t_local_cat or self.t_global_cat)
 
 
+# Parameter updates that bypass torch's version counters (raw-pointer kernels such as the fused optimizer step) announce
+# themselves here; the modules' "did the weights change" key includes this counter.
+_GENERATION = [0]
+
+
+def bump_weights_generation():
+    _GENERATION[0] += 1
+
+
+def weights_generation() -> int:
+    return _GENERATION[0]
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 

@@ -4,4 +4,4 @@ generate.py  jets sharded over the ranks, no data-path collective, one final gat
 train.py     data-parallel training: all-reduce of the flat folded-weight gradient    (training)
 """
 from .generate import block_noise, generate_data_sharded, integrate_and_gather, shard_bounds  # noqa: F401
-from .train import attach_flat_grad_allreduce, detach_flat_grad_allreduce  # noqa: F401
+from .train import GraphedTrainStep, attach_flat_grad_allreduce, detach_flat_grad_allreduce  # noqa: F401

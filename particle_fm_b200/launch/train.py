@@ -55,3 +55,62 @@ def detach_flat_grad_allreduce(model):
     for f in model.flows:
         f.net.flat_grad_hook = None
     return model
+
+
+class GraphedTrainStep:
+    """One training step of the fused flow-matching loss replayed from a CUDA graph.
+
+    A step is ~70 kernel launches plus the autograd / optimizer glue; at small per-GPU batches (strong scaling) the host,
+    not the GPU, bounds it.  The whole step -- noise draws on the device, loss forward + backward in libpfm_b200,
+    weight-norm chain rule, fused clip + AdamW (``particle_fm_b200.optim.FusedClipAdamW(device_step_count=True)``) -- is
+    captured once and replayed; per step the host only draws the per-jet times on the CPU generator (the reference's RNG
+    placement, losses.py:46) and copies them plus the batch into static buffers.
+
+        step = GraphedTrainStep(model, optimizer, x_example, mask_example)
+        loss = step(x, mask)            # same shapes as the examples
+
+    Library calls are capture-safe after the warm-up steps done here (no allocation, pinned staging for the small tables).
+    Data-parallel training: the flat-gradient all-reduce hook is captured with the step when attached before construction."""
+
+    def __init__(self, model, optimizer, x: torch.Tensor, mask: torch.Tensor, cond: torch.Tensor = None, warmup: int = 3):
+        if not x.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU fallback)")
+        if getattr(optimizer, "device_step_count", True) is False:
+            raise ValueError("FusedClipAdamW must be built with device_step_count=True to be replayed from a graph")
+        self.model, self.opt = model, optimizer
+        self.x, self.mask = x.clone(), mask.clone()
+        self.cond = None if cond is None else cond.clone()
+        self.t = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+        self._t_pin = torch.empty(x.shape[0], pin_memory=True)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):                     # warm-up on a side stream, as torch.cuda.graphs prescribes
+            for _ in range(warmup):
+                self._draw_t()
+                self._body()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        self._draw_t()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _draw_t(self):
+        torch.rand(self._t_pin.shape, out=self._t_pin)    # CPU default generator, like torch.rand_like(torch.ones(B))
+        self.t.copy_(self._t_pin, non_blocking=True)
+
+    def _body(self):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.model.loss(self.x, mask=self.mask, cond=self.cond, t=self.t)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, mask: torch.Tensor, cond: torch.Tensor = None) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        if cond is not None:
+            self.cond.copy_(cond, non_blocking=True)
+        self._draw_t()
+        self.graph.replay()
+        return self.loss

@@ -373,7 +373,8 @@ class _DroidNet(nn.Module):
                     num_tokens=getattr(core, "num_tokens", 4))
 
     def _weights_key(self):
-        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+        from ...engine import weights_generation
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + (weights_generation(),)
 
     def invalidate_weights(self):
         """See EPiC_encoder.invalidate_weights: in-place ``.data`` updates are invisible to the change detector."""

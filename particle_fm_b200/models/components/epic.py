@@ -144,7 +144,8 @@ class EPiC_encoder(nn.Module):
         return out
 
     def _weights_key(self):
-        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+        from ...engine import weights_generation
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + (weights_generation(),)
 
     def invalidate_weights(self):
         """Force the next engine() call to re-fold and repack the parameters.  The change detector below keys on

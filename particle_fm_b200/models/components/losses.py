@@ -41,7 +41,9 @@ class _FusedFMLoss(nn.Module):
         n1 = torch.randn_like(x) if self.kind == "CFM" else None
         return t, n0, n1
 
-    def forward(self, x: Tensor, mask: Optional[Tensor] = None, cond: Optional[Tensor] = None) -> Tensor:
+    def forward(self, x: Tensor, mask: Optional[Tensor] = None, cond: Optional[Tensor] = None, t: Optional[Tensor] = None) -> Tensor:
+        """``t`` (optional, (B,) on x's device) replaces the per-jet time draw: the CPU-generator draw cannot be replayed from a
+        CUDA graph, so a graphed step (launch.train.GraphedTrainStep) draws it outside and hands it in; the noise draws stay here."""
         if len(self.flows) != 1:
             raise NotImplementedError("n_transforms != 1 is not supported by the CUDA path (1 in every config)")
         if x.dim() != 3:
@@ -51,7 +53,11 @@ class _FusedFMLoss(nn.Module):
                 raise TypeError("ConditionalFlowMatchingLoss needs a mask (the reference fails on mask=None too, "
                                 "losses.py:119,130)")
             mask = torch.ones_like(x[..., 0]).unsqueeze(-1)
-        t, n0, n1 = self.draw(x)
+        if t is None:
+            t, n0, n1 = self.draw(x)
+        else:
+            n0 = torch.randn_like(x)
+            n1 = torch.randn_like(x) if self.kind == "CFM" else None
         from .droid_transformer import _DroidNet, droid_loss_autograd
         if isinstance(self.flows[0].net, _DroidNet):
             return droid_loss_autograd(self.flows[0], self.kind, x, mask, cond, t, n0, n1, float(self.sigma))

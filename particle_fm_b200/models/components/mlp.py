@@ -49,7 +49,8 @@ class _CondMLPBase(nn.Module):
         return widths, concat, act
 
     def _weights_key(self):
-        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+        from ...engine import weights_generation
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + (weights_generation(),)
 
     def engine(self, device=None, force_sync: bool = False) -> MlpFlowEngine:
         p0 = next(self.parameters())

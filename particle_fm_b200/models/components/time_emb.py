@@ -13,6 +13,9 @@ import torch
 Tensor = torch.Tensor
 
 
+_EXP_FREQS = {}
+
+
 def cosine_encoding(x: Tensor, outp_dim: int = 32, min_value: float = 0.0, max_value: float = 1.0,
                     frequency_scaling: str = "exponential") -> Tensor:
     if x.shape[-1] != 1 or x.dim() == 1:
@@ -21,7 +24,11 @@ def cosine_encoding(x: Tensor, outp_dim: int = 32, min_value: float = 0.0, max_v
         # exp() is evaluated on the HOST and the 32-entry table moved: CPU and CUDA expf differ in the last
         # bit for some k, and one ulp of e^31 turns the high channels into a different hash of t.  The host
         # table is what the CPU reference (and the oracle) use; see DESIGN.md "time code".
-        freqs = torch.arange(outp_dim).exp().to(x.device)
+        key = (outp_dim, x.device)
+        freqs = _EXP_FREQS.get(key)
+        if freqs is None:              # cached per device: no host -> device copy per call (illegal inside CUDA-graph capture)
+            freqs = torch.arange(outp_dim).exp().to(x.device)
+            _EXP_FREQS[key] = freqs
     elif frequency_scaling == "linear":
         freqs = torch.arange(1, outp_dim + 1, device=x.device)
     else:

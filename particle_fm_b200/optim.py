@@ -21,13 +21,15 @@ from . import _lib
 
 class FusedClipAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None, ema_decay: Optional[float] = None):
+                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None, ema_decay: Optional[float] = None,
+                 device_step_count: bool = False):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise NotImplementedError("FusedClipAdamW takes one parameter group")
         self.max_grad_norm = max_grad_norm
         self.ema_decay = ema_decay
+        self.device_step_count = device_step_count     # keep the step count on the device (replay of step() from a CUDA graph)
         self._flat = None          # (params, offsets, flat_p, m, v, ema, ws, ptr_key)
         self._step = 0
         self.last_grad_norm = None
@@ -59,7 +61,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 p.data = flat[o:o + p.numel()].view(p.shape)
         m, v = torch.zeros_like(flat), torch.zeros_like(flat)
         ema = flat.clone() if self.ema_decay is not None else None
-        ws = torch.zeros(2, device=dev, dtype=torch.float32)
+        ws = torch.zeros(4, device=dev, dtype=torch.float32)    # [sumsq, grad norm, device-side step count (int), pad]
         key = tuple(p.data_ptr() for p in ps)
         self._flat = (ps, offs, flat, m, v, ema, ws, key)
 
@@ -115,9 +117,12 @@ class FusedClipAdamW(torch.optim.Optimizer):
             st = C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
             _lib.check(lib.pfm_clip_adamw(C.c_void_p(flat.data_ptr()), C.c_void_p(gflat.data_ptr()), C.c_void_p(m.data_ptr()),
                                           C.c_void_p(v.data_ptr()), total, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                          float(group["weight_decay"]), float(self.max_grad_norm or 0.0), self._step,
+                                          float(group["weight_decay"]), float(self.max_grad_norm or 0.0),
+                                          0 if self.device_step_count else self._step,
                                           None if ema is None else C.c_void_p(ema.data_ptr()), float(self.ema_decay or 0.0),
                                           C.c_void_p(ws.data_ptr()), st), "pfm_clip_adamw")
         gflat.record_stream(torch.cuda.current_stream(flat.device))
+        from .engine import bump_weights_generation
+        bump_weights_generation()          # the kernel wrote the parameters behind torch's version counters: packed copies are stale
         self.last_grad_norm = ws[1]
         return loss
