@@ -455,12 +455,12 @@ def test_graphed_training_step_learns_and_matches_eager_shapes():
     opt = FusedClipAdamW(m.parameters(), lr=2e-3, weight_decay=0.0, max_grad_norm=0.5, device_step_count=True)
     step = GraphedTrainStep(m, opt, x, mask)
     p0 = [p.detach().clone() for p in m.parameters()]
-    losses = [float(step(x, mask)) for _ in range(60)]
-    first, last = sum(losses[:10]) / 10, sum(losses[-10:]) / 10
-    assert last < 0.93 * first, (first, last)
+    losses = [float(step(x, mask)) for _ in range(300)]       # fresh noise every replay: compare 30-step averages
+    first, last = sum(losses[:30]) / 30, sum(losses[-30:]) / 30
+    assert last < 0.85 * first, (first, last)
     assert any(not torch.equal(a, b.detach()) for a, b in zip(p0, m.parameters()))
     # the graph and the eager path leave the same kind of state behind: an eager evaluation still works and sees the new weights
     torch.manual_seed(1)
     with torch.no_grad():
         l_eager = float(m.loss(x, mask=mask, cond=None))
-    assert abs(l_eager - last) < 0.25 * last
+    assert abs(l_eager - last) < 0.35 * last, (l_eager, last)
