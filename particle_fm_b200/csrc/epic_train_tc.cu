@@ -156,7 +156,49 @@ __global__ void __launch_bounds__(RL_THREADS, 1) rowlin_tc_kernel(const RowLinP 
         }
       }
   };
+  // Launches without a residual / broadcast operand have nothing to load per element: their epilogue goes straight from TMEM
+  // to global memory (thread = row, 16-byte stores; measured faster than the staged path when there is no operand to coalesce)
+  const bool direct = !p.R && !p.bc;
+  auto epilogue_direct = [&](int t_local) {
+    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = tile * 128 + q * 32 + lane;
+    const bool ok = r < rows;
+    const int jet = (ok && p.bias) ? p.rowjet[r] : 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t v[32];
+      const int o0 = hf * 64 + j * 32;
+      uint32_t ebits = 0xffffffffu;
+      if (ok && p.E) ebits = __ldcg(p.E + (size_t)r * 4 + (hf * 2 + j));
+      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
+      tmem_wait_ld();
+      if (ok) {
+        uint32_t sbits = 0;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 a = make_float4(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]), __uint_as_float(v[i4 * 4 + 2]),
+                                 __uint_as_float(v[i4 * 4 + 3]));
+          const int o = o0 + i4 * 4;
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
+          if (p.E) {
+            const uint32_t e = ebits >> (i4 * 4);
+            a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
+          }
+          sbits |= ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << (i4 * 4);
+          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+        }
+        if (p.sgn_out) p.sgn_out[(size_t)r * 4 + (hf * 2 + j)] = sbits;
+      }
+    }
+    tc_fence_before();
+  };
   auto epilogue = [&](int t_local) {
+    if (direct) { epilogue_direct(t_local); return; }
     const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
     const int q = warp & 3, hf = warp >> 2;
 #pragma unroll
@@ -222,7 +264,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) rowlin_tc_kernel(const RowLinP 
   mbar_wait(&s.mbar_w, 0);
   TT_PROF(0);
   for (int t = 0; t < my_tiles; ++t) {
-    if (t >= 1) epi_loads(t - 1);
+    if (t >= 1 && !direct) epi_loads(t - 1);
     TT_PROF(1);
     mbar_wait(&s.mbar_raw, (uint32_t)(t & 1));             // the tile's fp32 rows have landed
     TT_PROF(2);
@@ -272,7 +314,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) rowlin_tc_kernel(const RowLinP 
     if (t >= 1) epilogue(t - 1);                           // overlaps the MMAs of this tile and the copy of the next
     TT_PROF(7);
   }
-  epi_loads(my_tiles - 1);
+  if (!direct) epi_loads(my_tiles - 1);
   mbar_wait(&s.mbar[(my_tiles - 1) & 1], (uint32_t)(((my_tiles - 1) >> 1) & 1));
   tc_fence_after();
   epilogue(my_tiles - 1);
