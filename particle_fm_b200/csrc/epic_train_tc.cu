@@ -482,6 +482,13 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.f;
     int k = k0;
+    for (; k + 16 <= k1; k += 16) {                       // 16 independent weight loads in flight (the chain is latency-bound)
+      float wv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) wv[q] = __ldg(w + (size_t)(k + q) * Ga.ldo);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q & 7] = fmaf(wv[q], pool[k + q], acc[q & 7]);
+    }
     for (; k + 8 <= k1; k += 8) {
       float wv[8];
 #pragma unroll
@@ -521,7 +528,11 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
   if (unit > 0 && !hp) {   // effective bias of fc_local1: + W_glob . g   (the broadcast global vector, epic.py:189-196)
     const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2];
     float a = p.beff[(size_t)j * p.bstride + La.bias_off + col];
-    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(La.Wt + (size_t)(La.g_off + z) * La.ldo + col), gs[z], a);
+    float wz[32];
+#pragma unroll
+    for (int z = 0; z < 32; ++z) wz[z] = z < Z ? __ldg(La.Wt + (size_t)(La.g_off + z) * La.ldo + col) : 0.f;
+#pragma unroll
+    for (int z = 0; z < 32; ++z) a = fmaf(wz[z], z < Z ? gs[z] : 0.f, a);
     p.beff[(size_t)j * p.bstride + La.bias_off + col] = a;
   }
 }
@@ -664,7 +675,11 @@ __global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int u
   __syncthreads();
   if (!hp) {
     float a = 0.f;
-    for (int z = 0; z < Z; ++z) a = fmaf(__ldg(Gb.Wr + (size_t)z * Gb.ldr + col), pg2[z], a);
+    float wz[32];
+#pragma unroll
+    for (int z = 0; z < 32; ++z) wz[z] = z < Z ? __ldg(Gb.Wr + (size_t)z * Gb.ldr + col) : 0.f;
+#pragma unroll
+    for (int z = 0; z < 32; ++z) a = fmaf(wz[z], z < Z ? pg2[z] : 0.f, a);
     const float v = a * tt_dlrelu(ja[p.LDP + col], p.slope);
     pg1[col] = v;
     dbe[Ga.bias_off + col] = v;
@@ -675,12 +690,12 @@ __global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int u
     float acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    for (int o = 0; o < H; o += 8) {
-      float wv[8];
+    for (int o = 0; o < H; o += 16) {
+      float wv[16];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) wv[q] = __ldg(wk + (size_t)(o + q) * Ga.ldr);
+      for (int q = 0; q < 16; ++q) wv[q] = __ldg(wk + (size_t)(o + q) * Ga.ldr);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[q], pg1[o + q], acc[q]);
+      for (int q = 0; q < 16; ++q) acc[q & 7] = fmaf(wv[q], pg1[o + q], acc[q & 7]);
     }
     din[k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
