@@ -483,16 +483,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
         PROF_T(0);
         mbar_wait(&s.spk_full, c_spk++ & 1);
         PROF_T(1);
-        float b3[FP];                              // head bias and step size: loaded now, used at the end of the evaluation
-#pragma unroll
-        for (int f = 0; f < FP; ++f) {
-          b3[f] = 0.f;
-          if (f < F) {
-            b3[f] = p.tbias[(size_t)((!SIMPLE && p.tbias_per_jet) ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
-            if (!SIMPLE && p.cbias) b3[f] += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
-          }
-        }
-        const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
         for (int i = et; i < nj * TCH; i += 256) {
           const int j = i >> 7, o = i & 127;
           s.bl1[j][o] = unit_bias(LIN_L1, 0, s.jid[j], o);
@@ -799,9 +789,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) epic_tc_kernel(const TcParams p
           }
         }
         // ---------------- head bias + activation, integrator step (thread-local) ----------------
+        // (head bias and step size are loaded HERE, from L2, not at the start of the evaluation: five registers that were
+        // live across the whole layer loop were what spilled)
+        const float dt_ev = p.solver >= 0 ? p.dt[p.solver == PFM_SOLVER_MIDPOINT ? (ev >> 1) : ev] : 0.f;
 #pragma unroll
         for (int f = 0; f < FP; ++f)
-          if (f < F) vout[f] = valid ? lrelu_tc(vout[f] + b3[f], p.slope) : 0.f;
+          if (f < F) {
+            float b3 = p.tbias[(size_t)((!SIMPLE && p.tbias_per_jet) ? jg : ev) * p.bstride + s.boff[p.n_lin - 1] + f];
+            if (!SIMPLE && p.cbias) b3 += p.cbias[(size_t)jg * p.bstride + s.boff[p.n_lin - 1] + f];
+            vout[f] = valid ? lrelu_tc(vout[f] + b3, p.slope) : 0.f;
+          }
         if (p.solver >= 0) {
           const bool mid = p.solver == PFM_SOLVER_MIDPOINT;
           const float dt = dt_ev;
