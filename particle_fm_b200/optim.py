@@ -52,6 +52,24 @@ class FusedClipAdamW(torch.optim.Optimizer):
             return None
         return offs, base_store, total
 
+    def _layout_fast(self, ps):
+        """Steady state: the gradients sit at the offsets adopted at the first step (one data_ptr() per parameter
+        instead of the full dtype / contiguity / storage scan)."""
+        f = self._flat
+        if f is None or len(f[0]) != len(ps):
+            return None
+        offs, total = f[1], f[2].numel()
+        g0 = ps[0].grad
+        store = g0.untyped_storage()
+        base = store.data_ptr()
+        if g0.dtype != torch.float32 or store.nbytes() < 4 * total:
+            return None
+        for p, o in zip(ps, offs):
+            g = p.grad
+            if g.data_ptr() != base + 4 * o or g.numel() != p.numel() or not g.is_contiguous():
+                return None
+        return offs, base, total
+
     def _flatten(self, ps, offs, total):
         dev = ps[0].device
         flat = torch.empty(total, device=dev, dtype=torch.float32)
@@ -84,7 +102,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
             return loss
         if ps[0].device.type != "cuda":
             raise _lib.PfmError("FusedClipAdamW runs on CUDA devices only (no CPU fallback)")
-        lay = self._layout_from_grads(ps)
+        lay = self._layout_fast(ps) or self._layout_from_grads(ps)
         if lay is None:              # gradients not produced as views of one buffer: gather them (one multi-tensor copy)
             total = sum(p.numel() for p in ps)
             offs, o = [], 0
