@@ -877,6 +877,14 @@ int tt_plan(pfm_epic* h, int B, int N, cudaStream_t st) {
   return PFM_OK;
 }
 
+// output of the plain forward before the head scatters the real particles into it: 0 at padding, NaN for a jet without
+// particles (its mean pooling is 0/0 in the reference, epic.py:161-163, and NaN * mask stays NaN)
+__global__ void tt_out_init_kernel(float* __restrict__ out, const int* __restrict__ n_real, int NF) {
+  const float v = n_real[blockIdx.x] == 0 ? __int_as_float(0x7fc00000) : 0.f;
+  float* o = out + (size_t)blockIdx.x * NF;
+  for (int i = threadIdx.x; i < NF; i += blockDim.x) o[i] = v;
+}
+
 // forward with saved activations (+ fused flow-matching loss): fills act / yact / jact / dpre3 / loss_acc like
 // epic_simt.cu's TRAIN instantiation (tt_plan has run)
 int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
@@ -891,7 +899,7 @@ int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   const int grid_gemm = h->sm_count;
   const int jet_ctas = a.B;
   tt_beff_kernel<<<a.B, 256, 0, st>>>(h->tbias, a.tbias_per_jet, a.has_cbias ? h->cbias : nullptr, h->bstride, p.beff);
-  if (a.loss_kind < 0) PFM_CUDA_CHECK(cudaMemsetAsync(a.x_out, 0, sizeof(float) * (size_t)a.B * a.N * c.feats, st));
+  if (a.loss_kind < 0) tt_out_init_kernel<<<a.B, 128, 0, st>>>(a.x_out, h->plan.n_real, a.N * c.feats);
   tt_stem_kernel<<<(a.B * a.N + 7) / 8 < 16 * grid_rows ? (a.B * a.N + 7) / 8 : 16 * grid_rows, 256, 0, st>>>(p);
   h->last_launches += 2;
   {   // fc_l2: h0 = lrelu(h1 . W^T + b + h1)     (epic.py:364-367)

@@ -373,8 +373,18 @@ static int run_chunked(pfm_epic* h, const float* t_code, int t_rows, bool per_je
 // ---------------------------------------------------------------------------------------------
 // training: forward with saved activations (+ fused flow-matching loss), backward, weight gradients
 // ---------------------------------------------------------------------------------------------
-__global__ void loss_finalize_kernel(const float* __restrict__ acc, const int* __restrict__ n_total, float* __restrict__ loss) {
-  *loss = *acc / (float)(*n_total);          // sum((v-u)^2) / sum(mask)   (losses.py:76,130,341)
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, const int* __restrict__ n_total,
+                                     const int* __restrict__ n_real, int B, float* __restrict__ loss) {
+  // A jet without particles makes the reference's loss NaN (its pooled mean is 0/0 and NaN * mask stays NaN in the sum):
+  // the packed kernels never visit such a jet, so the NaN is put back here.
+  __shared__ int empty;
+  if (threadIdx.x == 0) empty = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < B; j += blockDim.x)
+    if (n_real[j] == 0) empty = 1;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    *loss = empty ? __int_as_float(0x7fc00000) : *acc / (float)(*n_total);      // sum((v-u)^2) / sum(mask)   (losses.py:76,130,341)
 }
 
 // dpre3[row][f] (holds leaky_relu'(pre3)) *= grad_out[jet][particle][f]; one warp per jet
@@ -1007,7 +1017,7 @@ int pfm_epic_loss_fwd_bwd(pfm_epic* h, const float* x1, const float* t, const fl
   int rc = train_forward_common(h, t_code, B, t_code_in, t_in, x1, nullptr, t, noise0, noise1, loss_kind, sigma, mask, cond, B, N,
                                 c.feats, t_in, &lay, st);
   if (rc != PFM_OK) return rc;
-  loss_finalize_kernel<<<1, 1, 0, st>>>(h->loss_acc, h->plan.n_total, loss_out);
+  loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_acc, h->plan.n_total, h->plan.n_real, B, loss_out);
   h->last_launches++;
   if (!grad_flat) return PFM_OK;
   PFM_CUDA_CHECK(cudaMemsetAsync(grad_flat, 0, sizeof(float) * grad_floats(h), st));
