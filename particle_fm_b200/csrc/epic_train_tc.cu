@@ -30,6 +30,15 @@ static constexpr int TT_H = 128;
 static constexpr uint32_t TT_IMG = 32768;          // one bf16 128 x 128 K-major SW128 image
 
 __device__ __forceinline__ float tt_lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+// Accumulator column of output feature n.  tcgen05.ld.16x256b gives thread T of a warp the columns 8j + 2(T%4) + {0,1}
+// (j = 0..3) of a 32-column group; the weight images are packed with their N rows permuted inside every group so that
+// those eight registers are the features 4(T%4) + {0..3} and 16 + 4(T%4) + {0..3}: two float4 per thread, and a quad of
+// threads covers 64 contiguous bytes of a global row per instruction (full 32-byte sectors, half the requests of a
+// float2 layout).
+__host__ __device__ __forceinline__ int tt_ncol(int n) {
+  const int f = n & 31;
+  return (n & ~31) | (8 * (2 * (f >> 4) + ((f >> 1) & 1)) + 2 * ((f >> 2) & 3) + (f & 1));
+}
 __device__ __forceinline__ float tt_dlrelu(float post, float s) { return post > 0.f ? 1.f : s; }
 
 // ---------------------------------------------------------------------------------------------
@@ -51,7 +60,8 @@ __global__ void tt_pack_kernel(const TtImgSrc* __restrict__ src, uint8_t* __rest
     const float w = S.Wt[(size_t)(S.k0 + k) * S.ldo + o];
     const __nv_bfloat16 h = __float2bfloat16_rn(w);
     const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-    const uint32_t off = transposed ? sw128_offset(k, o, 16384) : sw128_offset(o, k, 16384);
+    // the GEMM's N index (o forward, k transposed) is stored at accumulator column tt_ncol(.): see rowlin2_tc_kernel's epilogue
+    const uint32_t off = transposed ? sw128_offset(tt_ncol(k), o, 16384) : sw128_offset(tt_ncol(o), k, 16384);
     *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
   }
@@ -83,243 +93,255 @@ struct RowLinP {
   long long* prof;         // debug (PFM_TT_PROF): per-phase cycle counters of CTA 0
 };
 
-struct RowLinSmem {
+// ---------------------------------------------------------------------------------------------
+// rowlin2_tc_kernel: the same pass as rowlin_tc_kernel, warp-specialised so that its three streams overlap instead of taking
+// turns on the same 8 warps (the v1 kernel spends 17.8 k cycles per 128-row tile of a residual pass where its HBM share
+// allows 8.4 k):
+//   warps 0-3  (128 threads) "converters": fp32 half tiles (64 rows, 32 KB) arrive in a 3-slot ring by cp.async.bulk and are
+//              split into the bf16 hi / lo SWIZZLE_128B operand; thread 32 refills the slot it just drained, an elected lane
+//              of warp 0 issues the 24 MMAs of the tile into one of two TMEM accumulators;
+//   warps 4-11 (256 threads) epilogue: tcgen05.ld.16x256b hands a QUAD of lanes 8 consecutive fp32 columns of a row (layout
+//              checked by tools/tmem_ld_probe.cu), so residual loads and result stores are full 32-byte sectors straight
+//              from / to global memory -- no shared-memory staging, no CTA-wide barriers; the operands of chunk c + 2
+//              (residual, sign words, row -> jet) are in flight while chunk c is processed.
+// Hand-offs: raw_full[3] (bulk-copy bytes), mma_done[2] (tcgen05.commit; read by the epilogue AND by the converters, whose
+// operand buffer is single), acc_free[2] (8 epilogue warps).
+// ---------------------------------------------------------------------------------------------
+struct RowLin2Smem {
   alignas(1024) uint8_t W[2][TT_IMG];
   alignas(1024) uint8_t A[2][TT_IMG];           // hi, lo
-  alignas(1024) float raw[128 * TT_H];          // fp32 tile as it lies in global memory
-  alignas(16) float stage[64 * TT_H];           // epilogue staging of 64 accumulator rows (16-byte chunks XOR-swizzled by row)
-  uint64_t mbar_w, mbar_raw, mbar[2];
+  alignas(1024) float raw[3][64 * TT_H];        // ring of fp32 half tiles as they lie in global memory
+  uint64_t mbar_w, raw_full[3], mma_done[2], acc_free[2];
   uint32_t tmem;
 };
 
-static constexpr int RL_THREADS = 256;
+static constexpr int RL2_CONV_WARPS = 8;                    // converter warps (the 8 epilogue warps follow them)
+static constexpr int RL2_CONV = 32 * RL2_CONV_WARPS;
+static constexpr int RL2_THREADS = RL2_CONV + 256;
+static constexpr int RL2_AHEAD = 1;                         // epilogue operands are fetched this many chunks ahead (1 or 2)
 
-__global__ void __launch_bounds__(RL_THREADS, 1) rowlin_tc_kernel(const RowLinP p) {
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+
+// operands of one epilogue chunk (16 rows x 32 features of a warp: this thread's rows A = qr, B = qr + 8; features
+// 4 (T%4) + {0..3} and 16 + 4 (T%4) + {0..3} of the group)
+struct Rl2Pre { float4 r[4]; uint32_t e[2]; int jet[2]; };
+
+// which operands a pass has: compile-time, so that each of the five passes of a training step runs straight-line epilogue code
+enum : int { RL2_BIAS = 1, RL2_RES = 2, RL2_BC = 4, RL2_ACT = 8, RL2_E = 16, RL2_SGN = 32 };
+
+template <int FL>
+__global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLinP p) {
+  constexpr bool HAS_BIAS = (FL & RL2_BIAS) != 0, HAS_RES = (FL & RL2_RES) != 0, HAS_BC = (FL & RL2_BC) != 0, HAS_ACT = (FL & RL2_ACT) != 0,
+                 HAS_E = (FL & RL2_E) != 0, HAS_SGN = (FL & RL2_SGN) != 0, HAS_PJ = HAS_BIAS || HAS_BC;
+  static_assert(!(HAS_BIAS && HAS_BC), "a pass has one per-jet vector");
   extern __shared__ uint8_t smem_raw[];
-  RowLinSmem& s = *reinterpret_cast<RowLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  RowLin2Smem& s = *reinterpret_cast<RowLin2Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = *p.n_total;
   const int n_tiles = (rows + 127) >> 7;
   if ((int)blockIdx.x >= n_tiles) return;                 // uniform, before any barrier / allocation
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_half = 2 * my_tiles;
 
   if (warp == 0) tmem_alloc(&s.tmem, 256);
   if (tid == 0) {
-    mbar_init(&s.mbar_w, 1); mbar_init(&s.mbar_raw, 1); mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1);
+    mbar_init(&s.mbar_w, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&s.raw_full[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.mma_done[i], 1); mbar_init(&s.acc_free[i], 8); }
     fence_barrier_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  auto load_tile = [&](int t_local) {                      // one thread: the tile's valid rows, two bulk copies
-    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
-    const int r0 = tile * 128;
-    const int n = rows - r0 < 128 ? rows - r0 : 128;
-    const uint32_t bytes = (uint32_t)n * TT_H * 4u;
-    const uint32_t half = bytes > 32768u ? 32768u : bytes;
-    mbar_arrive_expect_tx(&s.mbar_raw, bytes);
-    bulk_copy_g2s(s.raw, p.X + (size_t)r0 * TT_H, half, &s.mbar_raw);
-    if (bytes > half) bulk_copy_g2s(reinterpret_cast<uint8_t*>(s.raw) + half, reinterpret_cast<const uint8_t*>(p.X + (size_t)r0 * TT_H) + half,
-                                    bytes - half, &s.mbar_raw);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&s.mbar_w, 2 * TT_IMG);
-    bulk_copy_g2s(s.W[0], p.Wimg, TT_IMG, &s.mbar_w);
-    bulk_copy_g2s(s.W[1], p.Wimg + TT_IMG, TT_IMG, &s.mbar_w);
-    load_tile(0);
-  }
   const uint32_t tm = s.tmem;
-  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
 
-  // Epilogue of a tile whose MMAs are complete (waited by the caller).  TMEM hands every thread one ROW of the accumulator;
-  // global memory wants consecutive threads on consecutive columns.  The rows go through a shared-memory staging buffer
-  // (64 rows at a time; 16-byte chunk c of row r is stored at chunk c ^ (r & 31): conflict-free both ways), so that every
-  // global load (residual) and store is a fully coalesced 512-byte row segment per warp.
-  // global operands of a tile's epilogue (residual, row -> jet, sign words): issued one pipeline stage early, so that their
-  // HBM latency hides behind the operand conversion of the next tile instead of stalling the 8 warps of the CTA
-  float4 rr[2][8];
-  int jets[2][8];
-  uint32_t eb[2][8];
-  auto epi_loads = [&](int t_local) {
-    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+  if (warp < RL2_CONV_WARPS) {
+    // ------------------------------------------------------------------ converters / MMA issue / loads
+    auto load_half = [&](int hc) {                         // one thread: the valid rows of half tile hc, one bulk copy
+      const int tile = (int)blockIdx.x + (hc >> 1) * (int)gridDim.x;
+      const int r0 = tile * 128 + (hc & 1) * 64;
+      int n = rows - r0;
+      n = n < 0 ? 0 : (n > 64 ? 64 : n);
+      const uint32_t bytes = (uint32_t)n * TT_H * 4u;
+      uint64_t* bar = &s.raw_full[hc % 3];
+      mbar_arrive_expect_tx(bar, bytes);
+      if (bytes) bulk_copy_g2s(s.raw[hc % 3], p.X + (size_t)r0 * TT_H, bytes, bar);
+    };
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&s.mbar_w, 2 * TT_IMG);
+      bulk_copy_g2s(s.W[0], p.Wimg, TT_IMG, &s.mbar_w);
+      bulk_copy_g2s(s.W[1], p.Wimg + TT_IMG, TT_IMG, &s.mbar_w);
+    }
+    if (tid == 32) for (int hc = 0; hc < 3 && hc < n_half; ++hc) load_half(hc);
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    long long pt = 0, pc[5] = {0, 0, 0, 0, 0};
+    const bool prof = p.prof && blockIdx.x == 0 && tid == 0;
+#define RL2_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
+    if (prof) pt = clock64();
+    for (int t = 0; t < my_tiles; ++t) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int hc = 2 * t + half;
+        mbar_wait(&s.raw_full[hc % 3], (uint32_t)((hc / 3) & 1));
+        RL2_PROF(0);
+        if (half == 0 && t >= 1) mbar_wait(&s.mma_done[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));    // operand buffer free
+        RL2_PROF(1);
+        const float* src = s.raw[hc % 3];
+        // raw fp32 [64][128] -> bf16 hi / lo, K-major SWIZZLE_128B (thread = 4 consecutive columns of a row)
+#pragma unroll 8
+        for (int i = 0; i < 2048 / RL2_CONV; ++i) {
+          const int idx = tid + RL2_CONV * i, rl = idx >> 5, c = (idx & 31) * 4;
+          const float4 v = *reinterpret_cast<const float4*>(&src[rl * TT_H + c]);
+          const uint32_t off = sw128_offset(half * 64 + rl, c, 16384);
+          const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z),
+                              hw = __float2bfloat16_rn(v.w);
+          uint2 h2, l2;
+          h2.x = pack_bf16x2(v.x, v.y); h2.y = pack_bf16x2(v.z, v.w);
+          l2.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
+          l2.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
+          *reinterpret_cast<uint2*>(s.A[0] + off) = h2;
+          *reinterpret_cast<uint2*>(s.A[1] + off) = l2;
+        }
+        fence_proxy_async();
+        RL2_PROF(2);
+        named_bar_sync(1, RL2_CONV);
+        if (tid == 32 && hc + 3 < n_half) load_half(hc + 3);     // the slot is drained: refill it
+        RL2_PROF(3);
+      }
+      if (warp == 0) {
+        if (t >= 2) mbar_wait(&s.acc_free[t & 1], (uint32_t)(((t >> 1) - 1) & 1));      // the epilogue of tile t - 2 has read it
+        tc_fence_after();
+        if (elect_one()) {
+          if (t == 0) mbar_wait(&s.mbar_w, 0);
+          const uint64_t ah = desc_kmajor(smem_u32(s.A[0])), al = desc_kmajor(smem_u32(s.A[1]));
+          const uint64_t wh = desc_kmajor(smem_u32(s.W[0])), wl = desc_kmajor(smem_u32(s.W[1]));
+          const uint32_t acc = tm + (uint32_t)((t & 1) * 128);
 #pragma unroll
-    for (int half = 0; half < 2; ++half)
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t d = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+            mma_ss(acc, ah + d, wh + d, idesc, k ? 1u : 0u);
+            mma_ss(acc, ah + d, wl + d, idesc, 1u);
+            mma_ss(acc, al + d, wh + d, idesc, 1u);
+          }
+          mma_commit(&s.mma_done[t & 1]);
+        }
+        __syncwarp();
+      }
+      RL2_PROF(4);
+    }
+    if (prof) for (int k = 0; k < 5; ++k) p.prof[k] = pc[k];
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3, hf = (warp - RL2_CONV_WARPS) >> 2;     // TMEM lane quadrant (= warp % 4), column half
+    const int qr = lane >> 2, qf = (lane & 3) * 4;          // row inside the 8-row block, first feature inside the group
+    const float* pj = HAS_BIAS ? p.bias : p.bc;            // the per-jet vector of this pass (never both)
+    const int pj_ld = HAS_BIAS ? p.bias_ld : TT_H;
+    Rl2Pre pre[2 * RL2_AHEAD];
+    // chunk c of tile t: lane half lh = c >> 1 (16 rows), feature group g = 2 hf + (c & 1) (32 features)
+    auto prefetch = [&](int t_local, int c, Rl2Pre& o) {
+      const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+      const int g = hf * 2 + (c & 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
-        const int r = tile * 128 + half * 64 + rl;
-        jets[half][i] = 0; eb[half][i] = 0xffffffffu;
-        if (r < rows) {
-          if (p.R) rr[half][i] = __ldcg(reinterpret_cast<const float4*>(p.R + (size_t)r * TT_H + c4 * 4));
-          if (p.bias || p.bc) jets[half][i] = p.rowjet[r];
-          if (p.E) eb[half][i] = __ldcg(p.E + (size_t)r * 4 + (c4 >> 3));
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int r = tile * 128 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
+        const bool ok = t_local < my_tiles && r < rows;
+        o.jet[h2] = 0; o.e[h2] = 0xffffffffu;
+        if (ok) {
+          if (HAS_PJ) o.jet[h2] = __ldg(p.rowjet + r);
+          if (HAS_E) o.e[h2] = __ldcg(p.E + (size_t)r * 4 + g);
+          if (HAS_RES) {
+            const float4* src = reinterpret_cast<const float4*>(p.R + (size_t)r * TT_H + g * 32 + qf);
+            o.r[2 * h2] = __ldcg(src);
+            o.r[2 * h2 + 1] = __ldcg(src + 4);
+          }
         }
       }
-  };
-  // Launches without a residual / broadcast operand have nothing to load per element: their epilogue goes straight from TMEM
-  // to global memory (thread = row, 16-byte stores; measured faster than the staged path when there is no operand to coalesce)
-  const bool direct = !p.R && !p.bc;
-  auto epilogue_direct = [&](int t_local) {
-    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
-    const int q = warp & 3, hf = warp >> 2;
-    const int r = tile * 128 + q * 32 + lane;
-    const bool ok = r < rows;
-    const int jet = (ok && p.bias) ? p.rowjet[r] : 0;
+    };
+    auto process = [&](int t_local, int c, const Rl2Pre& o) {
+      const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+      const int g = hf * 2 + (c & 1);
+      uint32_t v[16];
+      tmem_ld_16x256b_x4(tm + ((uint32_t)(q * 32 + (c >> 1) * 16) << 16) + (uint32_t)((t_local & 1) * 128 + g * 32), v);
+      float4 b[4];
+      if (HAS_PJ) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t v[32];
-      const int o0 = hf * 64 + j * 32;
-      uint32_t ebits = 0xffffffffu;
-      if (ok && p.E) ebits = __ldcg(p.E + (size_t)r * 4 + (hf * 2 + j));
-      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const float4* src = reinterpret_cast<const float4*>(pj + (size_t)o.jet[h2] * pj_ld + g * 32 + qf);
+          b[2 * h2] = __ldg(src);
+          b[2 * h2 + 1] = __ldg(src + 4);
+        }
+      }
       tmem_wait_ld();
-      if (ok) {
-        uint32_t sbits = 0;
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          float4 a = make_float4(__uint_as_float(v[i4 * 4 + 0]), __uint_as_float(v[i4 * 4 + 1]), __uint_as_float(v[i4 * 4 + 2]),
-                                 __uint_as_float(v[i4 * 4 + 3]));
-          const int o = o0 + i4 * 4;
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jet * p.bias_ld + o));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
-          if (p.E) {
-            const uint32_t e = ebits >> (i4 * 4);
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int r = tile * 128 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
+        const bool ok = r < rows;
+        uint32_t sb = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                      // features g*32 + 16 k + qf + {0..3}: registers 8k + 2 h2 + {0, 1, 4, 5}
+          float4 a = make_float4(__uint_as_float(v[8 * k + 2 * h2]), __uint_as_float(v[8 * k + 2 * h2 + 1]),
+                                 __uint_as_float(v[8 * k + 2 * h2 + 4]), __uint_as_float(v[8 * k + 2 * h2 + 5]));
+          const int bit = 16 * k + qf;
+          if (HAS_BIAS) { const float4 w = b[2 * h2 + k]; a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w; }
+          if (HAS_RES) { const float4 w = o.r[2 * h2 + k]; a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w; }
+          if (HAS_BC) { const float4 w = b[2 * h2 + k]; a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w; }
+          if (HAS_ACT) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
+          if (HAS_E) {
+            const uint32_t e = o.e[h2] >> bit;
             a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
           }
-          sbits |= ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << (i4 * 4);
-          __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
+          if (ok) __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + g * 32 + bit), a);
+          if (HAS_SGN) sb |= ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << bit;
         }
-        if (p.sgn_out) p.sgn_out[(size_t)r * 4 + (hf * 2 + j)] = sbits;
-      }
-    }
-    tc_fence_before();
-  };
-  auto epilogue = [&](int t_local) {
-    if (direct) { epilogue_direct(t_local); return; }
-    const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
-    const int q = warp & 3, hf = warp >> 2;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if ((q >> 1) == half) {                              // warps owning TMEM lanes [64 half, 64 half + 64)
-        const int rl = (q & 1) * 32 + lane;                // row inside the staging buffer
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t v[32];
-          const int o0 = hf * 64 + j * 32;
-          tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + (uint32_t)((t_local & 1) * 128 + o0), v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const int chunk = ((o0 >> 2) + i4) ^ (rl & 31);
-            *reinterpret_cast<uint4*>(&s.stage[rl * TT_H + chunk * 4]) = make_uint4(v[i4 * 4 + 0], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
-          }
+        if (HAS_SGN) {                                     // the quad holds the 32 features of one sign word
+          sb |= __shfl_xor_sync(0xffffffffu, sb, 1);
+          sb |= __shfl_xor_sync(0xffffffffu, sb, 2);
+          if (ok && (lane & 3) == 0) p.sgn_out[(size_t)r * 4 + g] = sb;
         }
       }
-      __syncthreads();
-      // all 256 threads: thread = (row, 16-byte chunk); a warp covers one full row per step.  All global loads of the 8 steps
-      // are issued before the first use (the residual comes from HBM: one exposed latency per half tile, not eight)
-      {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + 256 * i, rl = idx >> 5, c4 = idx & 31;
-          const int r = tile * 128 + half * 64 + rl;
-          if (r < rows) {
-            const int o = c4 * 4;
-            float4 a = *reinterpret_cast<const float4*>(&s.stage[rl * TT_H + ((c4 ^ (rl & 31)) * 4)]);
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)jets[half][i] * p.bias_ld + o));
-              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            if (p.R) { a.x += rr[half][i].x; a.y += rr[half][i].y; a.z += rr[half][i].z; a.w += rr[half][i].w; }
-            if (p.bc) {
-              const float4 b = __ldcg(reinterpret_cast<const float4*>(p.bc + (size_t)jets[half][i] * TT_H + o));
-              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            if (p.act) { a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope); }
-            if (p.E) {
-              const uint32_t e = eb[half][i] >> ((c4 & 7) * 4);
-              a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
-            }
-            __stcg(reinterpret_cast<float4*>(p.Y + (size_t)r * TT_H + o), a);
-            if (p.sgn_out) {                               // 8 lanes hold the 32 columns of one sign word
-              uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((c4 & 7) * 4);
-              b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
-              if ((c4 & 7) == 0) p.sgn_out[(size_t)r * 4 + (c4 >> 3)] = b;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    tc_fence_before();
-  };
-
-  long long pt = 0, pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool prof = p.prof && blockIdx.x == 0 && tid == 0;
-#define TT_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
-  if (prof) pt = clock64();
-  mbar_wait(&s.mbar_w, 0);
-  TT_PROF(0);
-  for (int t = 0; t < my_tiles; ++t) {
-    if (t >= 1 && !direct) epi_loads(t - 1);
-    TT_PROF(1);
-    mbar_wait(&s.mbar_raw, (uint32_t)(t & 1));             // the tile's fp32 rows have landed
-    TT_PROF(2);
-    if (t >= 1) {                                          // the operand buffer is free once the previous tile's MMAs are done
-      mbar_wait(&s.mbar[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+    };
+    long long pt = 0, pc[2] = {0, 0};
+    const bool prof = p.prof && blockIdx.x == 0 && tid == RL2_CONV;
+    if (prof) pt = clock64();
+    prefetch(0, 0, pre[0]);
+    if (RL2_AHEAD == 2) prefetch(0, 1, pre[1]);
+    for (int t = 0; t < my_tiles; ++t) {
+      mbar_wait(&s.mma_done[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-    }
-    TT_PROF(3);
-    // raw fp32 [128][128] -> bf16 hi / lo, K-major SWIZZLE_128B (thread = 4 consecutive columns of a row)
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int idx = tid + 256 * i, rl = idx >> 5, c = (idx & 31) * 4;
-      const float4 v = *reinterpret_cast<const float4*>(&s.raw[rl * TT_H + c]);
-      const uint32_t off = sw128_offset(rl, c, 16384);
-      const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z),
-                          hw = __float2bfloat16_rn(v.w);
-      uint2 h2, l2;
-      h2.x = pack_bf16x2(v.x, v.y); h2.y = pack_bf16x2(v.z, v.w);
-      l2.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
-      l2.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
-      *reinterpret_cast<uint2*>(s.A[0] + off) = h2;
-      *reinterpret_cast<uint2*>(s.A[1] + off) = l2;
-    }
-    fence_proxy_async();
-    TT_PROF(4);
-    __syncthreads();
-    TT_PROF(5);
-    if (warp == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-        if (t + 1 < my_tiles) load_tile(t + 1);            // the staging buffer is free: the next tile streams in during MMAs + epilogue
-        const uint64_t ah = desc_kmajor(smem_u32(s.A[0])), al = desc_kmajor(smem_u32(s.A[1]));
-        const uint64_t wh = desc_kmajor(smem_u32(s.W[0])), wl = desc_kmajor(smem_u32(s.W[1]));
-        const uint32_t acc = tm + (uint32_t)((t & 1) * 128);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t d = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
-          mma_ss(acc, ah + d, wh + d, idesc, k ? 1u : 0u);
-          mma_ss(acc, ah + d, wl + d, idesc, 1u);
-          mma_ss(acc, al + d, wh + d, idesc, 1u);
-        }
-        mma_commit(&s.mbar[t & 1]);
+      RL2_PROF(0);
+      if (RL2_AHEAD == 2) {
+        prefetch(t, 2, pre[2]);
+        process(t, 0, pre[0]);
+        prefetch(t, 3, pre[3]);
+        process(t, 1, pre[1]);
+        prefetch(t + 1, 0, pre[0]);
+        process(t, 2, pre[2]);
+        prefetch(t + 1, 1, pre[1]);
+        process(t, 3, pre[3]);
+      } else {
+        prefetch(t, 1, pre[1]);
+        process(t, 0, pre[0]);
+        prefetch(t, 2, pre[0]);
+        process(t, 1, pre[1]);
+        prefetch(t, 3, pre[1]);
+        process(t, 2, pre[0]);
+        prefetch(t + 1, 0, pre[0]);
+        process(t, 3, pre[1]);
       }
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_free[t & 1]);
+      RL2_PROF(1);
     }
-    TT_PROF(6);
-    if (t >= 1) epilogue(t - 1);                           // overlaps the MMAs of this tile and the copy of the next
-    TT_PROF(7);
+    if (prof) { p.prof[5] = pc[0]; p.prof[6] = pc[1]; }
   }
-  if (!direct) epi_loads(my_tiles - 1);
-  mbar_wait(&s.mbar[(my_tiles - 1) & 1], (uint32_t)(((my_tiles - 1) >> 1) & 1));
-  tc_fence_after();
-  epilogue(my_tiles - 1);
-  TT_PROF(7);
-  if (prof) for (int k = 0; k < 8; ++k) p.prof[k] = pc[k];
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 256);
 }
@@ -821,29 +843,44 @@ __global__ void rowlin_check_kernel(const RowLinP p, const float* __restrict__ W
 }
 
 static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const TtCommon& c, int grid, cudaStream_t st) {
-  static bool attr = false;
-  const int smem = (int)sizeof(RowLinSmem) + 1024;
-  if (!attr) {
-    PFM_CUDA_CHECK(cudaFuncSetAttribute(rowlin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   q.Wimg = reinterpret_cast<const uint8_t*>(h->tt_store) + (size_t)(2 * gemm + (transposed ? 1 : 0)) * 2 * TT_IMG;
   q.rowjet = c.rowjet; q.n_total = c.n_total; q.slope = c.slope;
   static const bool do_prof = getenv("PFM_TT_PROF") != nullptr;
+
   static long long* dprof = nullptr;
   if (do_prof) {
     if (!dprof) PFM_CUDA_CHECK(cudaMalloc(&dprof, 64));
     q.prof = dprof;
   }
-  rowlin_tc_kernel<<<grid, RL_THREADS, smem, st>>>(q);
+  {
+    const int fl = (q.bias ? RL2_BIAS : 0) | (q.R ? RL2_RES : 0) | (q.bc ? RL2_BC : 0) | (q.act ? RL2_ACT : 0) | (q.E ? RL2_E : 0) |
+                   (q.sgn_out ? RL2_SGN : 0);
+    const int smem2 = (int)sizeof(RowLin2Smem) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {                                            // every instantiation the switch below can launch
+      void (*ks[5])(const RowLinP) = {rowlin2_tc_kernel<(RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN)>, rowlin2_tc_kernel<(RL2_BIAS | RL2_ACT | RL2_SGN)>,
+                                      rowlin2_tc_kernel<RL2_E>, rowlin2_tc_kernel<(RL2_RES | RL2_BC | RL2_E)>, rowlin2_tc_kernel<(RL2_RES | RL2_E)>};
+      for (auto k : ks) PFM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    auto launch = [&](void (*kernel)(const RowLinP)) { kernel<<<grid, RL2_THREADS, smem2, st>>>(q); };
+    switch (fl) {
+      case RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN: launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN)>); break;   // fc_l2, fc_local2
+      case RL2_BIAS | RL2_ACT | RL2_SGN:           launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_ACT | RL2_SGN)>); break;             // fc_local1
+      case RL2_E:                                  launch(rowlin2_tc_kernel<RL2_E>); break;                                      // dz2 . W2
+      case RL2_RES | RL2_BC | RL2_E:               launch(rowlin2_tc_kernel<(RL2_RES | RL2_BC | RL2_E)>); break;                 // dz1 . W1 + residual + pooling
+      case RL2_RES | RL2_E:                        launch(rowlin2_tc_kernel<(RL2_RES | RL2_E)>); break;                          // stem
+      default: set_error("rowlin pass with operand set %d is not instantiated", fl); return PFM_ERR_UNSUPPORTED;
+    }
+  }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->last_launches++;
   if (do_prof) {
     long long hp[8];
     PFM_CUDA_CHECK(cudaMemcpyAsync(hp, dprof, 64, cudaMemcpyDeviceToHost, st));
     PFM_CUDA_CHECK(cudaStreamSynchronize(st));
-    fprintf(stderr, "[pfm tt prof] gemm %2d %s  w %lld | epi_loads %lld  wait_raw %lld  wait_mma %lld  convert %lld  sync %lld  issue %lld  epilogue %lld\n",
-            gemm, transposed ? "bwd" : "fwd", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+    fprintf(stderr, "[pfm tt prof] gemm %2d %s  converters: wait_raw %lld  wait_mma %lld  convert %lld  barrier+load %lld  issue %lld | epilogue: wait_mma %lld  process %lld\n",
+            gemm, transposed ? "bwd" : "fwd", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
   }
   static const bool check = getenv("PFM_TT_CHECK") != nullptr;
   if (check) {
