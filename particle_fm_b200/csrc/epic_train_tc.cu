@@ -449,28 +449,59 @@ __global__ void __launch_bounds__(256) tt_stem_kernel(const TtCommon p) {
   }
 }
 
-// column sums over rows [r0, r0 + n) of a [rows][128] array, rows r0 + part, r0 + part + parts, ...: 8 loads in flight
-__device__ __forceinline__ float tt_colsum_part(const float* __restrict__ a, int r0, int n, int col, int part, int parts) {
-  float s[8];
+// Column sums over rows [r0, r0 + n) of a [rows][128] array by a group of 32 * G threads (t = 0 .. 32 G - 1): thread t sums
+// the four columns 4 (t % 32) .. + 3 of rows t / 32, t / 32 + G, ... with 8 independent 16-byte loads in flight, the G partial
+// rows are combined through `red` ([G][128] floats of shared memory).  The caller synchronises the CTA afterwards and reads
+// the sums with tt_colsum_get.  (A jet has <= 150 rows: with G = 4 / 8 a thread issues all its loads in 1-3 batches, where one
+// thread per column needed up to 10 dependent batches of HBM latency.)
+template <int G>
+__device__ __forceinline__ void tt_colsum_put(const float* __restrict__ a, int r0, int n, int t, float* __restrict__ red) {
+  const int c4 = t & 31, rg = t >> 5;
+  float4 s[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) s[q] = 0.f;
-  int r = part;
-  for (; r + 7 * parts < n; r += 8 * parts) {
+  for (int q = 0; q < 8; ++q) s[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* base = reinterpret_cast<const float4*>(a + (size_t)r0 * TT_H) + c4;
+  int r = rg;
+  for (; r + 7 * G < n; r += 8 * G) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s[q] += __ldcg(a + (size_t)(r0 + r + q * parts) * TT_H + col);
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldcg(base + (size_t)(r + q * G) * (TT_H / 4));
+      s[q].x += v.x; s[q].y += v.y; s[q].z += v.z; s[q].w += v.w;
+    }
   }
-  for (; r < n; r += parts) s[0] += __ldcg(a + (size_t)(r0 + r) * TT_H + col);
-  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {                            // tail: still independent loads
+    if (r + q * G < n) {
+      const float4 v = __ldcg(base + (size_t)(r + q * G) * (TT_H / 4));
+      s[q].x += v.x; s[q].y += v.y; s[q].z += v.z; s[q].w += v.w;
+    }
+  }
+  float4 o;
+  o.x = ((s[0].x + s[1].x) + (s[2].x + s[3].x)) + ((s[4].x + s[5].x) + (s[6].x + s[7].x));
+  o.y = ((s[0].y + s[1].y) + (s[2].y + s[3].y)) + ((s[4].y + s[5].y) + (s[6].y + s[7].y));
+  o.z = ((s[0].z + s[1].z) + (s[2].z + s[3].z)) + ((s[4].z + s[5].z) + (s[6].z + s[7].z));
+  o.w = ((s[0].w + s[1].w) + (s[2].w + s[3].w)) + ((s[4].w + s[5].w) + (s[6].w + s[7].w));
+  *reinterpret_cast<float4*>(red + rg * TT_H + c4 * 4) = o;
+}
+template <int G>
+__device__ __forceinline__ float tt_colsum_get(const float* __restrict__ red, int col) {
+  float s = red[col];
+#pragma unroll
+  for (int g = 1; g < G; ++g) s += red[g * TT_H + col];
+  return s;
 }
 
 // Forward of one per-jet unit (unit 0 = stem fc_g1 / fc_g2, unit l+1 = EPiC layer l): pooling of the unit's input h,
 // global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).
-// One CTA of 256 threads per jet (latency-bound: two half sums per output, 8 loads in flight per thread).
-__global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int unit) {
+// One CTA of 256 threads per jet (latency-bound: every phase keeps 8-16 independent loads in flight per thread).
+__global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int unit, long long* prof) {
+  long long pt = prof ? clock64() : 0, pc[6] = {0, 0, 0, 0, 0, 0};
+#define JF_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
   __shared__ float pool[2 * TT_H + 32];
   __shared__ float half2[TT_H];
   __shared__ float g1s[TT_H];
   __shared__ float gs[32];
+  __shared__ __align__(16) float red[8 * TT_H];
   const int j = blockIdx.x, tid = threadIdx.x, col = tid & 127, hp = tid >> 7;
   const int H = p.H, Z = p.Z;
   const int n = p.n_real[j], r0 = p.rowoff[j];
@@ -480,11 +511,12 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
   float* ja = p.jact + (size_t)j * p.jstride + (size_t)unit * p.junit;
   const float* h = p.act + (size_t)(unit == 0 ? 1 : 1 + 2 * l) * p.stage_stride;
   {
-    const float part = tt_colsum_part(h, r0, n, col, hp, 2);
-    if (hp) half2[col] = part;
+    JF_PROF(0);
+    tt_colsum_put<8>(h, r0, n, tid, red);
     __syncthreads();
+    JF_PROF(1);
     if (!hp) {
-      const float sum = part + half2[col];
+      const float sum = tt_colsum_get<8>(red, col);
       const float mean = sum / (float)n, ssum = sum * p.sum_scale;
       if (unit == 0) { pool[col] = ssum; pool[H + col] = mean; }       // (sum, mean) in the stem, epic.py:373
       else { pool[col] = mean; pool[H + col] = ssum; }                 // (mean, sum, global) in the layers, :164-171
@@ -496,6 +528,7 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
     }
   }
   __syncthreads();
+  JF_PROF(2);
   {   // fc_g1 / fc_global1: thread (col, hp) sums the k of its half
     const int K = 2 * H + (unit > 0 ? Z : 0);
     const int kh = (K + 1) / 2, k0 = hp * kh, k1 = (k0 + kh < K) ? k0 + kh : K;
@@ -529,6 +562,7 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
     }
   }
   __syncthreads();
+  JF_PROF(3);
   {   // fc_g2 / fc_global2: warp w handles outputs z = w, w + 8, ...; lanes split K
     const int warp = tid >> 5, lane = tid & 31;
     for (int z = warp; z < Z; z += 8) {
@@ -547,6 +581,7 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
     }
   }
   __syncthreads();
+  JF_PROF(4);
   if (unit > 0 && !hp) {   // effective bias of fc_local1: + W_glob . g   (the broadcast global vector, epic.py:189-196)
     const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2];
     float a = p.beff[(size_t)j * p.bstride + La.bias_off + col];
@@ -557,6 +592,8 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
     for (int z = 0; z < 32; ++z) a = fmaf(wz[z], z < Z ? gs[z] : 0.f, a);
     p.beff[(size_t)j * p.bstride + La.bias_off + col] = a;
   }
+  JF_PROF(5);
+  if (prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) for (int q = 0; q < 6; ++q) prof[(blockIdx.x ? 8 : 0) + q] = pc[q];
 }
 
 // head: v = lrelu(fc_l3(h_L)); flow-matching target, squared error, gradient seed (losses.py:61-62, :75-76).
@@ -650,6 +687,7 @@ __global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int u
   __shared__ float pg2[32];
   __shared__ float dG[32];
   __shared__ float din[2 * TT_H + 32];
+  __shared__ __align__(16) float red[2 * 4 * TT_H];
   const int j = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, col = tid & 127, hp = tid >> 7;
   const int H = p.H, Z = p.Z;
   const int n = p.n_real[j], r0 = p.rowoff[j];
@@ -671,7 +709,9 @@ __global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int u
   if (unit > 0) {
     const Lin La = p.lin[LIN_LAYER0 + 4 * l + 2], Lb = p.lin[LIN_LAYER0 + 4 * l + 3];
     // threads [0,128): sums of dz1 (stage 2+2l); threads [128,256): sums of dz2 (stage 3+2l)
-    const float sc = tt_colsum_part(p.dact + (size_t)(2 + 2 * l + hp) * p.stage_stride, r0, n, col, 0, 1);
+    tt_colsum_put<4>(p.dact + (size_t)(2 + 2 * l + hp) * p.stage_stride, r0, n, tid & 127, red + hp * 4 * TT_H);
+    __syncthreads();
+    const float sc = tt_colsum_get<4>(red + hp * 4 * TT_H, col);
     if (!hp) { db1[col] = sc; dbe[La.bias_off + col] = sc; }
     else dbe[Lb.bias_off + col] = sc;
     __syncthreads();
@@ -737,7 +777,10 @@ __global__ void __launch_bounds__(256) tt_stem_bwd_kernel(const TtCommon p) {
   const int n = p.n_real[j], r0 = p.rowoff[j];
   const Lin L1 = p.lin[LIN_L1], L2 = p.lin[LIN_L2];
   float* dbe = p.dbeff + (size_t)j * p.bstride;
-  const float sc = tt_colsum_part(p.dact + (size_t)hp * p.stage_stride, r0, n, col, 0, 1);
+  __shared__ __align__(16) float red[2 * 4 * TT_H];
+  tt_colsum_put<4>(p.dact + (size_t)hp * p.stage_stride, r0, n, tid & 127, red + hp * 4 * TT_H);
+  __syncthreads();
+  const float sc = tt_colsum_get<4>(red + hp * 4 * TT_H, col);
   dbe[(hp ? L2.bias_off : L1.bias_off) + col] = sc;
   if (p.dxs) {
     for (int r = warp; r < n; r += 8) {
@@ -945,10 +988,20 @@ int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
     q.sgn_out = p.sgn + GS;
     if ((rc = tt_rowlin(h, q, 0, 0, p, grid_gemm, st)) != PFM_OK) return rc;
   }
-  tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, 0);
+  static const bool jprof = getenv("PFM_TT_PROF") != nullptr;
+  static long long* djp = nullptr;
+  if (jprof && !djp) PFM_CUDA_CHECK(cudaMalloc(&djp, 128));
+  tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, 0, nullptr);
   h->last_launches++;
   for (int l = 0; l < c.layers; ++l) {
-    tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, l + 1);
+    tt_jet_fwd_kernel<<<jet_ctas, 256, 0, st>>>(p, l + 1, jprof ? djp : nullptr);
+    if (jprof) {
+      long long hp[16];
+      PFM_CUDA_CHECK(cudaMemcpyAsync(hp, djp, 128, cudaMemcpyDeviceToHost, st));
+      PFM_CUDA_CHECK(cudaStreamSynchronize(st));
+      fprintf(stderr, "[pfm tt prof] jet fwd unit %d  first CTA: head %lld colsum %lld pool %lld g1 %lld g2 %lld bias %lld | last CTA: %lld %lld %lld %lld %lld %lld\n", l + 1,
+              hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[8], hp[9], hp[10], hp[11], hp[12], hp[13]);
+    }
     h->last_launches++;
     RowLinP q; memset(&q, 0, sizeof(q));      // fc_local1: u = lrelu(h . W1^T + beff1[jet])     (epic.py:194-196)
     q.X = h->act + (size_t)(1 + 2 * l) * SS; q.bias = p.beff + h->lin_host[LIN_LAYER0 + 4 * l + 2].bias_off; q.bias_ld = h->bstride;
