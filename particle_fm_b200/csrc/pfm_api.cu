@@ -57,6 +57,59 @@ __global__ void tbias_kernel(const Lin* __restrict__ lin, const float* __restric
   }
 }
 
+// The same table for many rows (training: one row per jet): a CTA handles TB_ROWS rows of one linear, so a thread loads the
+// time columns of its output's weights once per TB_ROWS rows (32 independent loads, one latency) and reads the codes from
+// shared memory.  Per (row, output) the accumulation order is tbias_kernel's (bias, then k ascending): identical bits.
+static constexpr int TB_ROWS = 8;
+static constexpr int TB_KMAX = 64;         // time-code width handled here (2 * frequencies = 32 in the shipped configs)
+
+__global__ void __launch_bounds__(128) tbias_rows_kernel(const Lin* __restrict__ lin, const float* __restrict__ code, int t_dim,
+                                                         const float* __restrict__ code_in, int t_in, float* __restrict__ tbias,
+                                                         int bstride, int rows) {
+  __shared__ __align__(16) float sc[TB_ROWS][TB_KMAX];
+  const Lin L = lin[blockIdx.y];
+  const int row0 = blockIdx.x * TB_ROWS;
+  const int nr = rows - row0 < TB_ROWS ? rows - row0 : TB_ROWS;
+  const int T = L.t_len;                                   // <= TB_KMAX (checked by the caller)
+  for (int i = threadIdx.x; i < TB_ROWS * TB_KMAX; i += blockDim.x) {
+    const int r = i / TB_KMAX, k = i % TB_KMAX;
+    sc[r][k] = (r < nr && k < T) ? code[(size_t)(row0 + r) * t_dim + k] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
+    float acc[TB_ROWS];
+    const float b = L.b[o];
+#pragma unroll
+    for (int r = 0; r < TB_ROWS; ++r) acc[r] = b;
+    for (int k0 = 0; k0 < T; k0 += 32) {
+      float w[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) w[k] = k0 + k < T ? __ldg(L.Wt + (size_t)(L.t_off + k0 + k) * L.ldo + o) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        if (k0 + k < T) {
+#pragma unroll
+          for (int r = 0; r < TB_ROWS; ++r) {
+            const float4 c = *reinterpret_cast<const float4*>(&sc[r][k0 + k]);
+            acc[r] = fmaf(w[k], c.x, acc[r]);
+            if (k0 + k + 1 < T) acc[r] = fmaf(w[k + 1], c.y, acc[r]);
+            if (k0 + k + 2 < T) acc[r] = fmaf(w[k + 2], c.z, acc[r]);
+            if (k0 + k + 3 < T) acc[r] = fmaf(w[k + 3], c.w, acc[r]);
+          }
+        }
+      }
+    }
+    for (int r = 0; r < nr; ++r) {
+      float a = acc[r];
+      if (blockIdx.y == 0 && t_in > 0) {   // add_time_to_input: first t_in columns of fc_l1's main block
+        const float* c = code_in + (size_t)(row0 + r) * t_in;
+        for (int k = 0; k < t_in; ++k) a = fmaf(L.Wt[(size_t)(L.m_off + k) * L.ldo + o], c[k], a);
+      }
+      tbias[(size_t)(row0 + r) * bstride + L.bias_off + o] = a;
+    }
+  }
+}
+
 __global__ void cbias_kernel(const Lin* __restrict__ lin, const float* __restrict__ cond, int cond_dim,
                              float* __restrict__ cbias, int bstride) {
   const Lin L = lin[blockIdx.y];
@@ -481,7 +534,11 @@ static int train_forward_common(pfm_epic* h, const float* t_code, int t_rows, co
   const int trows = per_jet ? B : 1;
   rc = ensure_floats(&h->tbias, &h->tbias_cap, (size_t)trows * h->bstride);
   if (rc != PFM_OK) return rc;
-  tbias_kernel<<<dim3(trows, h->n_lin), 128, 0, st>>>(h->lin_dev, t_code, c.t_dim, t_code_in, t_in, h->tbias, h->bstride);
+  if (trows >= 2 * TB_ROWS && c.t_dim <= TB_KMAX)
+    tbias_rows_kernel<<<dim3((trows + TB_ROWS - 1) / TB_ROWS, h->n_lin), 128, 0, st>>>(h->lin_dev, t_code, c.t_dim, t_code_in, t_in, h->tbias,
+                                                                                       h->bstride, trows);
+  else
+    tbias_kernel<<<dim3(trows, h->n_lin), 128, 0, st>>>(h->lin_dev, t_code, c.t_dim, t_code_in, t_in, h->tbias, h->bstride);
   h->last_launches++;
   if (cond_dim > 0) {
     rc = ensure_floats(&h->cbias, &h->cbias_cap, (size_t)B * h->bstride);
