@@ -10,6 +10,7 @@
 // One CTA = one 128 x 128 tile of dW over a chunk of rows (two CTAs per SM); double-buffered 32-row stages, the MMAs of stage s overlap the
 // global loads + conversion of stage s+1.  Bound: HBM/L2 (each operand element is read once per 128-wide tile).
 #include <cstdlib>
+#include <type_traits>
 
 #include "pfm_internal.cuh"
 #include "tc_ptx.cuh"
@@ -92,18 +93,29 @@ __global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict
   const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
   const int n_st = (r_end - r_begin + XS_ROWS - 1) / XS_ROWS;
   constexpr int NLD = XS_ROWS * 32 / 256;          // 16-byte loads per thread and operand
-  float4 xv[NLD], yv[NLD];
-  auto fetch = [&](int st) {                       // 2 NLD independent 16-byte loads in flight per thread
+  // register prefetch two stages deep (a CTA's stage time is load latency + conversion: with one stage in flight it was
+  // ~2.2 k cycles per 32 rows): stage st + 2 is requested as soon as stage st has been converted
+  // FAST: both operands are full, 16-byte aligned 128-column tiles (the particle-row jobs, i.e. all the traffic): plain
+  // vector loads with one row predicate instead of xty_load4's per-column guards
+  auto run = [&](auto fast_tag) {
+  constexpr bool FAST = decltype(fast_tag)::value;
+  float4 xa[NLD], ya[NLD], xb[NLD], yb[NLD];
+  auto fetch = [&](int st, float4 (&xv)[NLD], float4 (&yv)[NLD]) {       // 2 NLD independent 16-byte loads per thread
     const int r0 = r_begin + st * XS_ROWS;
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       const int idx = tid + 256 * i, r = idx >> 5, c = (idx & 31) * 4;
-      xv[i] = xty_load4(Xb, J.ldx, r0 + r, r_end, c, wx < 128 ? wx : 128, vx);
-      yv[i] = xty_load4(Yb, J.ldy, r0 + r, r_end, c, wy < 128 ? wy : 128, vy);
+      if (FAST) {
+        const bool ok = r0 + r < r_end;
+        xv[i] = ok ? __ldg(reinterpret_cast<const float4*>(Xb + (size_t)(r0 + r) * J.ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        yv[i] = ok ? __ldg(reinterpret_cast<const float4*>(Yb + (size_t)(r0 + r) * J.ldy + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        xv[i] = xty_load4(Xb, J.ldx, r0 + r, r_end, c, wx < 128 ? wx : 128, vx);
+        yv[i] = xty_load4(Yb, J.ldy, r0 + r, r_end, c, wy < 128 ? wy : 128, vy);
+      }
     }
   };
-  fetch(0);
-  for (int st = 0; st < n_st; ++st) {
+  auto stage = [&](int st, float4 (&xv)[NLD], float4 (&yv)[NLD]) {
     const int b = st & 1;
     if (st >= 2) mbar_wait(&s.mbar[b], (uint32_t)(((st >> 1) - 1) & 1));     // the MMAs that read this buffer are done
 #pragma unroll
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict
       xty_store4(s.buf[b][0], s.buf[b][1], r, c, xv[i]);
       xty_store4(s.buf[b][2], s.buf[b][3], r, c, yv[i]);
     }
-    if (st + 1 < n_st) fetch(st + 1);              // the next stage's loads fly during the barrier and the MMAs
+    if (st + 2 < n_st) fetch(st + 2, xv, yv);      // flies during the barrier, the MMAs and the whole next stage
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
@@ -131,7 +143,16 @@ __global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict
       }
       __syncwarp();
     }
+  };
+  fetch(0, xa, ya);
+  if (n_st > 1) fetch(1, xb, yb);
+  for (int st = 0; st < n_st; st += 2) {
+    stage(st, xa, ya);
+    if (st + 1 < n_st) stage(st + 1, xb, yb);
   }
+  };
+  if (wx >= 128 && wy >= 128 && vx && vy) run(std::true_type{});
+  else run(std::false_type{});
   {
     const int last = n_st - 1;
     mbar_wait(&s.mbar[last & 1], (uint32_t)((last >> 1) & 1));
