@@ -199,12 +199,8 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
           const int idx = tid + RL2_CONV * i, rl = idx >> 5, c = (idx & 31) * 4;
           const float4 v = *reinterpret_cast<const float4*>(&src[rl * TT_H + c]);
           const uint32_t off = sw128_offset(half * 64 + rl, c, 16384);
-          const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z),
-                              hw = __float2bfloat16_rn(v.w);
           uint2 h2, l2;
-          h2.x = pack_bf16x2(v.x, v.y); h2.y = pack_bf16x2(v.z, v.w);
-          l2.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
-          l2.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
+          split_bf16x4(v, h2, l2);
           *reinterpret_cast<uint2*>(s.A[0] + off) = h2;
           *reinterpret_cast<uint2*>(s.A[1] + off) = l2;
         }

@@ -246,6 +246,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), for four values: the hi pairs are packed first and unpacked with two
+// integer ops each (a bf16 is the upper half of the fp32 it rounds to), which saves the four scalar conversions
+__device__ __forceinline__ void split_bf16x4(const float4 v, uint2& hi, uint2& lo) {
+  hi.x = pack_bf16x2(v.x, v.y);
+  hi.y = pack_bf16x2(v.z, v.w);
+  lo.x = pack_bf16x2(v.x - __uint_as_float(hi.x << 16), v.y - __uint_as_float(hi.x & 0xffff0000u));
+  lo.y = pack_bf16x2(v.z - __uint_as_float(hi.y << 16), v.w - __uint_as_float(hi.y & 0xffff0000u));
+}
+
 // Byte offset of element (row, col) inside a K-major SWIZZLE_128B tile whose rows are `row` (M or N index)
 // and whose 64-element column blocks are `blk_bytes` apart:  [col/64][row/8][row%8][(col%64/8) ^ (row%8)][col%8]
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, uint32_t blk_bytes) {

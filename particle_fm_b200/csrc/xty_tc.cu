@@ -46,11 +46,8 @@ __device__ __forceinline__ float4 xty_load4(const float* __restrict__ base, int 
 }
 __device__ __forceinline__ void xty_store4(uint8_t* hi, uint8_t* lo, int r, int c, float4 v) {
   const uint32_t off = sw128_offset(r, c, XS_ROWS * 128);
-  const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y), hz = __float2bfloat16_rn(v.z), hw = __float2bfloat16_rn(v.w);
   uint2 h, l;
-  h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
-  l.x = pack_bf16x2(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
-  l.y = pack_bf16x2(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
+  split_bf16x4(v, h, l);
   *reinterpret_cast<uint2*>(hi + off) = h;
   *reinterpret_cast<uint2*>(lo + off) = l;
 }
