@@ -143,12 +143,9 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
   extern __shared__ uint8_t smem_raw[];
   RowLin2Smem& s = *reinterpret_cast<RowLin2Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rows = *p.n_total;
-  const int n_tiles = (rows + 127) >> 7;
-  if ((int)blockIdx.x >= n_tiles) return;                 // uniform, before any barrier / allocation
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_half = 2 * my_tiles;
 
+  // Launched with programmatic stream serialization: everything up to griddepcontrol.wait (TMEM allocation, barrier
+  // initialisation -- nothing that reads global memory) overlaps the tail of the kernel before this one in the stream.
   if (warp == 0) tmem_alloc(&s.tmem, 256);
   if (tid == 0) {
     mbar_init(&s.mbar_w, 1);
@@ -160,6 +157,16 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = s.tmem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int rows = *p.n_total;
+  const int n_tiles = (rows + 127) >> 7;
+  if ((int)blockIdx.x >= n_tiles) {                       // uniform: nothing to do for this CTA
+    if (warp == 0) tmem_dealloc(tm, 256);
+    return;
+  }
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_half = 2 * my_tiles;
 
   if (warp < RL2_CONV_WARPS) {
     // ------------------------------------------------------------------ converters / MMA issue / loads
@@ -902,7 +909,17 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
       for (auto k : ks) PFM_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       attr2 = true;
     }
-    auto launch = [&](void (*kernel)(const RowLinP)) { kernel<<<grid, RL2_THREADS, smem2, st>>>(q); };
+    cudaError_t lerr = cudaSuccess;
+    auto launch = [&](void (*kernel)(const RowLinP)) {       // may start while the previous kernel of the stream drains (see the kernel)
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RL2_THREADS); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      lerr = cudaLaunchKernelEx(&cfg, kernel, q);
+    };
     switch (fl) {
       case RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN: launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN)>); break;   // fc_l2, fc_local2
       case RL2_BIAS | RL2_ACT | RL2_SGN:           launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_ACT | RL2_SGN)>); break;             // fc_local1
@@ -911,6 +928,7 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
       case RL2_RES | RL2_E:                        launch(rowlin2_tc_kernel<(RL2_RES | RL2_E)>); break;                          // stem
       default: set_error("rowlin pass with operand set %d is not instantiated", fl); return PFM_ERR_UNSUPPORTED;
     }
+    PFM_CUDA_CHECK(lerr);
   }
   PFM_CUDA_CHECK(cudaGetLastError());
   h->last_launches++;
