@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = s.tmem;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
   const int rows = *p.n_total;
   const int n_tiles = (rows + 127) >> 7;
   if ((int)blockIdx.x >= n_tiles) {                       // uniform: nothing to do for this CTA
@@ -910,16 +910,7 @@ static int tt_rowlin(pfm_epic* h, RowLinP& q, int gemm, int transposed, const Tt
       attr2 = true;
     }
     cudaError_t lerr = cudaSuccess;
-    auto launch = [&](void (*kernel)(const RowLinP)) {       // may start while the previous kernel of the stream drains (see the kernel)
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RL2_THREADS); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      lerr = cudaLaunchKernelEx(&cfg, kernel, q);
-    };
+    auto launch = [&](void (*kernel)(const RowLinP)) { lerr = launch_pdl(kernel, dim3((unsigned)grid), dim3(RL2_THREADS), (size_t)smem2, st, q); };
     switch (fl) {
       case RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN: launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_RES | RL2_ACT | RL2_SGN)>); break;   // fc_l2, fc_local2
       case RL2_BIAS | RL2_ACT | RL2_SGN:           launch(rowlin2_tc_kernel<(RL2_BIAS | RL2_ACT | RL2_SGN)>); break;             // fc_local1
