@@ -2,13 +2,12 @@
 //
 // In training every activation has to reach HBM anyway (the backward needs it), so unlike the sampler the network is NOT
 // kept resident in one CTA: it runs as a short program of kernels over the PACKED real particles of the whole batch,
-//   rowlin_tc_kernel   Y[rows,128] = epi( pro(X)[rows,128] . W^T )            every 128 x 128 per-particle linear and its
+//   rowlin2_tc_kernel  Y[rows,128] = epi( X[rows,128] . W^T )                 every 128 x 128 per-particle linear and its
 //                      transpose (dX = dY . W), tcgen05.mma with fp32 accumulation in TMEM.  fp32 accuracy is kept with the
 //                      3-term split x = hi + lo (two bf16): X W^T ~ Xh Wh^T + Xh Wl^T + Xl Wh^T (the dropped Xl Wl^T term is
 //                      2^-16 relative), so loss and gradients stay inside the fp32 gates (1e-5 / 1e-4) of the CUDA-core path.
-//                      Prologue (fused into the operand load): + per-jet broadcast vector, * leaky_relu'(saved activation),
-//                      write-back of the masked gradient.  Epilogue: + per-jet effective bias, + residual, leaky_relu,
-//                      * leaky_relu'(saved activation).
+//                      Epilogue: + per-jet effective bias | + residual | + per-jet broadcast vector, leaky_relu,
+//                      * leaky_relu'(saved sign bits), sign bits of the result.
 //   per-jet kernels    pooling + global MLP + effective biases (forward) and their backward, one CTA per jet, CUDA cores
 //                      (1% of the FLOPs), plus the K = 3 stem / N = 3 head.
 // Bound: HBM.  One 128-row tile moves 64 KB in and 64 KB out per operand array against 24 MMAs (1.5 k cycles).
@@ -68,11 +67,9 @@ __global__ void tt_pack_kernel(const TtImgSrc* __restrict__ src, uint8_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// rowlin_tc_kernel:  Y[rows,128] = epi( X[rows,128] . W^T )
-// A 128-row tile of X is ONE contiguous 64 KB block of global memory: it is fetched by bulk async copies (no registers,
-// a whole tile in flight per SM) into a raw fp32 staging buffer, split into bf16 hi / lo K-major SW128 operands by all
-// threads, multiplied with 24 tcgen05.mma (3-term split) into one of two TMEM accumulators, and the epilogue of tile t
-// runs while the MMAs of tile t+1 execute and the copy of tile t+2 is in flight.
+// One GEMM pass:  Y[rows,128] = epi( X[rows,128] . W^T )   (rowlin2_tc_kernel below)
+// A 128-row tile of X is one contiguous 64 KB block of global memory, fetched by bulk async copies (no registers), split into
+// bf16 hi / lo K-major SW128 operands and multiplied with 24 tcgen05.mma (3-term split) into one of two TMEM accumulators.
 // Epilogue (in this order): + bias[jet] | + R | + bc[jet] | leaky_relu | * leaky_relu'(sign bits E) ; optionally the sign
 // bits of the result are written (they are all the backward needs of a saved activation: 16 bytes per row instead of 512).
 // ---------------------------------------------------------------------------------------------
@@ -94,16 +91,18 @@ struct RowLinP {
 };
 
 // ---------------------------------------------------------------------------------------------
-// rowlin2_tc_kernel: the same pass as rowlin_tc_kernel, warp-specialised so that its three streams overlap instead of taking
-// turns on the same 8 warps (the v1 kernel spends 17.8 k cycles per 128-row tile of a residual pass where its HBM share
-// allows 8.4 k):
-//   warps 0-3  (128 threads) "converters": fp32 half tiles (64 rows, 32 KB) arrive in a 3-slot ring by cp.async.bulk and are
+// rowlin2_tc_kernel: warp-specialised so that its three streams (operand conversion, MMA, epilogue) overlap instead of taking
+// turns on the same warps (the first version of this pass did, and spent 17.8 k cycles per 128-row tile of a residual pass
+// where its HBM share allows 8.4 k):
+//   warps 0-7  (256 threads) "converters": fp32 half tiles (64 rows, 32 KB) arrive in a 3-slot ring by cp.async.bulk and are
 //              split into the bf16 hi / lo SWIZZLE_128B operand; thread 32 refills the slot it just drained, an elected lane
 //              of warp 0 issues the 24 MMAs of the tile into one of two TMEM accumulators;
-//   warps 4-11 (256 threads) epilogue: tcgen05.ld.16x256b hands a QUAD of lanes 8 consecutive fp32 columns of a row (layout
-//              checked by tools/tmem_ld_probe.cu), so residual loads and result stores are full 32-byte sectors straight
-//              from / to global memory -- no shared-memory staging, no CTA-wide barriers; the operands of chunk c + 2
-//              (residual, sign words, row -> jet) are in flight while chunk c is processed.
+//   warps 8-15 (256 threads) epilogue: tcgen05.ld.16x256b hands a QUAD of lanes 8 columns of a row (layout checked by
+//              tools/tmem_ld_probe.cu); the weight images are packed with permuted N rows (tt_ncol) so that those are
+//              two groups of 4 consecutive features per lane: residual loads and result stores are float4 accesses, 64
+//              contiguous bytes per quad, straight from / to global memory -- no shared-memory staging, no CTA-wide
+//              barriers; the operands of the next chunk (residual, sign words, row -> jet) are in flight while a chunk
+//              is processed.
 // Hand-offs: raw_full[3] (bulk-copy bytes), mma_done[2] (tcgen05.commit; read by the epilogue AND by the converters, whose
 // operand buffer is single), acc_free[2] (8 epilogue warps).
 // ---------------------------------------------------------------------------------------------
