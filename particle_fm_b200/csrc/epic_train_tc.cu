@@ -496,7 +496,7 @@ __device__ __forceinline__ float tt_colsum_get(const float* __restrict__ red, in
 // Forward of one per-jet unit (unit 0 = stem fc_g1 / fc_g2, unit l+1 = EPiC layer l): pooling of the unit's input h,
 // global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).
 // One CTA of 256 threads per jet (latency-bound: every phase keeps 8-16 independent loads in flight per thread).
-__global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int unit, long long* prof) {
+__global__ void __launch_bounds__(256, 4) tt_jet_fwd_kernel(const TtCommon p, int unit, long long* prof) {
   long long pt = prof ? clock64() : 0, pc[6] = {0, 0, 0, 0, 0, 0};
 #define JF_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
   __shared__ float pool[2 * TT_H + 32];
@@ -531,34 +531,37 @@ __global__ void __launch_bounds__(256) tt_jet_fwd_kernel(const TtCommon p, int u
   }
   __syncthreads();
   JF_PROF(2);
-  {   // fc_g1 / fc_global1: thread (col, hp) sums the k of its half
+  {   // fc_g1 / fc_global1.  The phase is bound by the number of memory instructions (five co-resident CTAs issue them through
+      // one LSU), so a thread takes 4 output columns with one 16-byte weight load per k and the 8 warps split K; the partial
+      // sums meet in shared memory.
     const int K = 2 * H + (unit > 0 ? Z : 0);
-    const int kh = (K + 1) / 2, k0 = hp * kh, k1 = (k0 + kh < K) ? k0 + kh : K;
-    const float* w = Ga.Wt + (size_t)Ga.m_off * Ga.ldo + col;
-    float acc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    const int c4 = tid & 31, kg = tid >> 5;
+    const int kc = (K + 7) >> 3, k0 = kg * kc, k1 = (k0 + kc < K) ? k0 + kc : K;
+    const float4* w = reinterpret_cast<const float4*>(Ga.Wt + (size_t)Ga.m_off * Ga.ldo) + c4;
+    const int ld4 = Ga.ldo >> 2;
+    float4 acc[2];
+    acc[0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[1] = acc[0];
     int k = k0;
-    for (; k + 16 <= k1; k += 16) {                       // 16 independent weight loads in flight (the chain is latency-bound)
-      float wv[16];
+    for (; k + 4 <= k1; k += 4) {
+      float4 wv[4];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) wv[q] = __ldg(w + (size_t)(k + q) * Ga.ldo);
+      for (int q = 0; q < 4; ++q) wv[q] = __ldg(w + (size_t)(k + q) * ld4);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q & 7] = fmaf(wv[q], pool[k + q], acc[q & 7]);
+      for (int q = 0; q < 4; ++q) {
+        const float x = pool[k + q];
+        acc[q & 1].x = fmaf(wv[q].x, x, acc[q & 1].x); acc[q & 1].y = fmaf(wv[q].y, x, acc[q & 1].y);
+        acc[q & 1].z = fmaf(wv[q].z, x, acc[q & 1].z); acc[q & 1].w = fmaf(wv[q].w, x, acc[q & 1].w);
+      }
     }
-    for (; k + 8 <= k1; k += 8) {
-      float wv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) wv[q] = __ldg(w + (size_t)(k + q) * Ga.ldo);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[q], pool[k + q], acc[q]);
+    for (; k < k1; ++k) {
+      const float4 wv = __ldg(w + (size_t)k * ld4);
+      const float x = pool[k];
+      acc[0].x = fmaf(wv.x, x, acc[0].x); acc[0].y = fmaf(wv.y, x, acc[0].y); acc[0].z = fmaf(wv.z, x, acc[0].z); acc[0].w = fmaf(wv.w, x, acc[0].w);
     }
-    for (; k < k1; ++k) acc[0] = fmaf(__ldg(w + (size_t)k * Ga.ldo), pool[k], acc[0]);
-    const float part = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    if (hp) half2[col] = part;
+    *reinterpret_cast<float4*>(red + kg * TT_H + c4 * 4) = make_float4(acc[0].x + acc[1].x, acc[0].y + acc[1].y, acc[0].z + acc[1].z, acc[0].w + acc[1].w);
     __syncthreads();
     if (!hp) {
-      const float g1 = tt_lrelu(part + half2[col] + p.beff[(size_t)j * p.bstride + Ga.bias_off + col], p.slope);
+      const float g1 = tt_lrelu(tt_colsum_get<8>(red, col) + p.beff[(size_t)j * p.bstride + Ga.bias_off + col], p.slope);
       g1s[col] = g1;
       ja[p.LDP + col] = g1;
     }
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(256) tt_head_bwd_kernel(const TtCommon p) {
 //   unit l+1: db1 / db2 = per-jet sums of the pre-activation gradients of fc_local1 / fc_local2 (-> dbeff),
 //             dG = carry + W_glob^T db1, then the global MLP backward; bc[j] = pooled gradient broadcast (overwritten)
 //   unit 0  : stem global MLP backward from the carry; bc[j] += broadcast (both units pool h0); also the head's bias gradient
-__global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int unit, int with_head) {
+__global__ void __launch_bounds__(256, 4) tt_jet_bwd_kernel(const TtCommon p, int unit, int with_head) {
   __shared__ float db1[TT_H];
   __shared__ float pg1[TT_H];
   __shared__ float pg2[32];
@@ -749,19 +752,37 @@ __global__ void __launch_bounds__(256) tt_jet_bwd_kernel(const TtCommon p, int u
     dbe[Ga.bias_off + col] = v;
   }
   __syncthreads();
-  for (int k = tid; k < Ga.m_len; k += 256) {     // din[k] = sum_o W_a[o][m_off + k] pg1[o]
-    const float* wk = Ga.Wr + k;
-    float acc[8];
+  {   // din[k] = sum_o W_a[o][m_off + k] pg1[o]: thread = 4 consecutive k (one 16-byte load per weight row) x one third of the
+      // 128 output rows; the three partial rows meet in shared memory (memory-instruction bound like fc_global1's forward)
+    const int n4 = (Ga.m_len + 3) >> 2;                    // <= 72 (m_len <= 2 H + 32: tt_enabled caps the latent width at 32)
+    const int og = tid / 72, k4 = tid - og * 72;
+    if (og < 3 && k4 < n4) {
+      const int o0 = og * 43, o1 = (o0 + 43 < H) ? o0 + 43 : H;
+      const float4* wk = reinterpret_cast<const float4*>(Ga.Wr) + k4;
+      const int ld4 = Ga.ldr >> 2;
+      float4 acc[2];
+      acc[0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[1] = acc[0];
+      int o = o0;
+      for (; o + 4 <= o1; o += 4) {
+        float4 wv[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    for (int o = 0; o < H; o += 16) {
-      float wv[16];
+        for (int q = 0; q < 4; ++q) wv[q] = __ldg(wk + (size_t)(o + q) * ld4);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) wv[q] = __ldg(wk + (size_t)(o + q) * Ga.ldr);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q & 7] = fmaf(wv[q], pg1[o + q], acc[q & 7]);
+        for (int q = 0; q < 4; ++q) {
+          const float x = pg1[o + q];
+          acc[q & 1].x = fmaf(wv[q].x, x, acc[q & 1].x); acc[q & 1].y = fmaf(wv[q].y, x, acc[q & 1].y);
+          acc[q & 1].z = fmaf(wv[q].z, x, acc[q & 1].z); acc[q & 1].w = fmaf(wv[q].w, x, acc[q & 1].w);
+        }
+      }
+      for (; o < o1; ++o) {
+        const float4 wv = __ldg(wk + (size_t)o * ld4);
+        const float x = pg1[o];
+        acc[0].x = fmaf(wv.x, x, acc[0].x); acc[0].y = fmaf(wv.y, x, acc[0].y); acc[0].z = fmaf(wv.z, x, acc[0].z); acc[0].w = fmaf(wv.w, x, acc[0].w);
+      }
+      *reinterpret_cast<float4*>(red + og * 288 + k4 * 4) = make_float4(acc[0].x + acc[1].x, acc[0].y + acc[1].y, acc[0].z + acc[1].z, acc[0].w + acc[1].w);
     }
-    din[k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    __syncthreads();
+    for (int k = tid; k < Ga.m_len; k += 256) din[k] = (red[k] + red[288 + k]) + red[576 + k];
   }
   __syncthreads();
   if (!hp) {
