@@ -53,7 +53,7 @@ __device__ __forceinline__ void xty_store4(uint8_t* hi, uint8_t* lo, int r, int 
 }
 
 __global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict__ jobs, int n_jobs, const int* __restrict__ n_total,
-                                                        const XtyJob single, int use_single) {
+                                                        const XtyJob single, int use_single, int min_chunk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   XtyTcSmem& s = *reinterpret_cast<XtyTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256, 2) xty_tc_kernel(const XtyJob* __restrict
   const int rows = J.rows >= 0 ? J.rows : *n_total;
   int chunk = (rows + (int)gridDim.x - 1) / (int)gridDim.x;
   chunk = (chunk + XS_ROWS - 1) / XS_ROWS * XS_ROWS;
+  if (chunk < min_chunk) chunk = min_chunk;      // per-jet jobs (rows = jets): a few CTAs of 8 stages, not one CTA (+ a 128 x 128 atomic epilogue) per stage
   const int r_begin = blockIdx.x * chunk;
   if (r_begin >= rows) return;                     // uniform for the block, before any barrier / allocation
   const int r_end = min(rows, r_begin + chunk);
@@ -195,6 +196,11 @@ static int xty_tc_grid_x(int max_rows, int tiles, int sm_count) {
   return gx < 1 ? 1 : gx;
 }
 
+static int xty_min_chunk() {
+  static const int v = getenv("PFM_XTY_MINCHUNK") ? atoi(getenv("PFM_XTY_MINCHUNK")) : 8 * XS_ROWS;
+  return v;
+}
+
 static int xty_tc_prepare() {
   static bool done = false;
   if (!done) {
@@ -211,7 +217,7 @@ int xty_tc_launch(const XtyJob* jobs_dev, int n_jobs, int tiles, const int* n_to
   XtyJob dummy;
   memset(&dummy, 0, sizeof(dummy));
   dim3 grid((unsigned)xty_tc_grid_x(max_rows, tiles, sm_count), (unsigned)tiles);
-  xty_tc_kernel<<<grid, 256, sizeof(XtyTcSmem) + 1024, st>>>(jobs_dev, n_jobs, n_total, dummy, 0);
+  xty_tc_kernel<<<grid, 256, sizeof(XtyTcSmem) + 1024, st>>>(jobs_dev, n_jobs, n_total, dummy, 0, xty_min_chunk());
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
@@ -226,7 +232,7 @@ int xty_tc_launch_one(const float* Y, int ldy, const float* X, int ldx, float* d
   J.tiles_o = (out + 127) / 128; J.tiles_k = (K + 127) / 128;
   const int tiles = J.tiles_o * J.tiles_k;
   dim3 grid((unsigned)xty_tc_grid_x(rows, tiles, sm_count), (unsigned)tiles);
-  xty_tc_kernel<<<grid, 256, sizeof(XtyTcSmem) + 1024, st>>>(nullptr, 0, nullptr, J, 1);
+  xty_tc_kernel<<<grid, 256, sizeof(XtyTcSmem) + 1024, st>>>(nullptr, 0, nullptr, J, 1, xty_min_chunk());
   PFM_CUDA_CHECK(cudaGetLastError());
   return PFM_OK;
 }
