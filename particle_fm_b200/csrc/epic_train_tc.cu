@@ -159,20 +159,33 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
   pdl_trigger();
   pdl_wait();
   const int rows = *p.n_total;
+  // Tiles of 128 rows, round-robin over the CTAs.  The tiles of the last, incomplete round (R < grid of them: with 660
+  // tiles on 148 SMs every pass would end with 68 CTAs working and 80 idle) are handed out as 64-row half tiles when that
+  // gives every CTA at most one: a half tile still takes a full M = 128 MMA, but a tile's time is conversion, epilogue and
+  // HBM traffic, which halve.
   const int n_tiles = (rows + 127) >> 7;
-  if ((int)blockIdx.x >= n_tiles) {                       // uniform: nothing to do for this CTA
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int full_rounds = n_tiles / G, R = n_tiles - full_rounds * G;
+  const bool split = R > 0 && 2 * R <= G;
+  const int my_tiles = full_rounds + (split ? (cta < 2 * R ? 1 : 0) : (cta < R ? 1 : 0));
+  if (my_tiles == 0) {                                    // uniform: nothing to do for this CTA
     if (warp == 0) tmem_dealloc(tm, 256);
     return;
   }
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_half = 2 * my_tiles;
+  auto tile_rows = [&](int t_local, int& row0, int& rend) {          // rows [row0, rend) of this CTA's t_local-th tile
+    if (split && t_local >= full_rounds) { row0 = full_rounds * G * 128 + cta * 64; rend = row0 + 64; }
+    else { row0 = (cta + t_local * G) * 128; rend = row0 + 128; }
+    if (rend > rows) rend = rows;
+  };
 
   if (warp < RL2_CONV_WARPS) {
     // ------------------------------------------------------------------ converters / MMA issue / loads
     auto load_half = [&](int hc) {                         // one thread: the valid rows of half tile hc, one bulk copy
-      const int tile = (int)blockIdx.x + (hc >> 1) * (int)gridDim.x;
-      const int r0 = tile * 128 + (hc & 1) * 64;
-      int n = rows - r0;
+      int row0, rend;
+      tile_rows(hc >> 1, row0, rend);
+      const int r0 = row0 + (hc & 1) * 64;
+      int n = rend - r0;
       n = n < 0 ? 0 : (n > 64 ? 64 : n);
       const uint32_t bytes = (uint32_t)n * TT_H * 4u;
       uint64_t* bar = &s.raw_full[hc % 3];
@@ -247,12 +260,13 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
     Rl2Pre pre[2 * RL2_AHEAD];
     // chunk c of tile t: lane half lh = c >> 1 (16 rows), feature group g = 2 hf + (c & 1) (32 features)
     auto prefetch = [&](int t_local, int c, Rl2Pre& o) {
-      const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+      int row0, rend;
+      tile_rows(t_local, row0, rend);
       const int g = hf * 2 + (c & 1);
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const int r = tile * 128 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
-        const bool ok = t_local < my_tiles && r < rows;
+        const int r = row0 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
+        const bool ok = t_local < my_tiles && r < rend;
         o.jet[h2] = 0; o.e[h2] = 0xffffffffu;
         if (ok) {
           if (HAS_PJ) o.jet[h2] = __ldg(p.rowjet + r);
@@ -266,7 +280,8 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
       }
     };
     auto process = [&](int t_local, int c, const Rl2Pre& o) {
-      const int tile = (int)blockIdx.x + t_local * (int)gridDim.x;
+      int row0, rend;
+      tile_rows(t_local, row0, rend);
       const int g = hf * 2 + (c & 1);
       uint32_t v[16];
       tmem_ld_16x256b_x4(tm + ((uint32_t)(q * 32 + (c >> 1) * 16) << 16) + (uint32_t)((t_local & 1) * 128 + g * 32), v);
@@ -282,8 +297,8 @@ __global__ void __launch_bounds__(RL2_THREADS, 1) rowlin2_tc_kernel(const RowLin
       tmem_wait_ld();
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const int r = tile * 128 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
-        const bool ok = r < rows;
+        const int r = row0 + q * 32 + (c >> 1) * 16 + qr + 8 * h2;
+        const bool ok = r < rend;
         uint32_t sb = 0;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {                      // features g*32 + 16 k + qf + {0..3}: registers 8k + 2 h2 + {0, 1, 4, 5}
