@@ -16,6 +16,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from ..training import direct_param_grads
+
 
 def attach_flat_grad_allreduce(model, group=None):
     """Average the flat gradient over `group` inside the fused training step of every flow of `model`.
@@ -100,9 +102,14 @@ class GraphedTrainStep:
         self.t.copy_(self._t_pin, non_blocking=True)
 
     def _body(self):
+        from ..models.components.droid_transformer import _DroidNet
         self.opt.zero_grad(set_to_none=True)
-        loss = self.model.loss(self.x, mask=self.mask, cond=self.cond, t=self.t)
-        loss.backward()
+        if any(isinstance(f.net, _DroidNet) for f in self.model.flows):
+            loss = self.model.loss(self.x, mask=self.mask, cond=self.cond, t=self.t)
+            loss.backward()                               # droid nets: through autograd (see training.direct_param_grads for the pitfall)
+        else:
+            with direct_param_grads():                    # the library writes p.grad itself: nothing of autograd inside the capture
+                loss = self.model.loss(self.x, mask=self.mask, cond=self.cond, t=self.t)
         self.opt.step()
         return loss.detach()
 

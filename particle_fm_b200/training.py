@@ -63,6 +63,27 @@ class _FMLossParamFn(torch.autograd.Function):
         return tuple(grads)
 
 
+_DIRECT_GRADS = False
+
+
+class direct_param_grads:
+    """Context: the fused EPiC losses write ``p.grad`` of the raw parameters themselves (loss forward + backward + weight-norm
+    chain rule in the library) and return a detached loss -- no autograd graph, no ``backward()``.  Used by
+    launch.GraphedTrainStep: ``backward()`` runs every parameter's AccumulateGrad node on the stream that node was created on,
+    and a node kept alive by an earlier eager backward on the default stream (a retained ``loss`` is enough) would pull the
+    legacy stream into a CUDA-graph capture (cudaErrorStreamCaptureImplicit)."""
+
+    def __enter__(self):
+        global _DIRECT_GRADS
+        self._old, _DIRECT_GRADS = _DIRECT_GRADS, True
+        return self
+
+    def __exit__(self, *exc):
+        global _DIRECT_GRADS
+        _DIRECT_GRADS = self._old
+        return False
+
+
 def fm_loss_autograd(cnf, kind: str, x: Tensor, mask: Tensor, cond: Optional[Tensor], t: Tensor, n0: Tensor,
                      n1: Optional[Tensor], sigma: float) -> Tensor:
     """Scalar loss with an autograd graph to ``cnf.net``'s parameters (x: (B,N,F), t: (B,) per jet)."""
@@ -74,6 +95,21 @@ def fm_loss_autograd(cnf, kind: str, x: Tensor, mask: Tensor, cond: Optional[Ten
     takes = net.t_local_cat or net.t_global_cat
     with torch.no_grad():
         code = cnf.time_code(t.to(x.device)) if (takes or cnf.add_time_to_input) else None     # [B, 2*frequencies]
+    if _DIRECT_GRADS:
+        with torch.no_grad():
+            loss, flat = eng.loss_fwd_bwd(kind, x, mask, cond, t, code if takes else None, code if cnf.add_time_to_input else None,
+                                          n0, n1, sigma, want_grad=True)
+            hook = getattr(net, "flat_grad_hook", None)
+            if hook is not None:
+                flat = hook(flat, eng)
+            lins = net.linears()
+            for lin, (dv, dg, db) in zip(lins, eng.param_grads(flat, None, lins)):
+                pairs = ((lin.weight_v, dv), (lin.weight_g, dg.view(lin.weight_g.shape)), (lin.bias, db)) if lin.weight_norm \
+                    else ((lin.weight, dv), (lin.bias, db))
+                for prm, grad in pairs:
+                    if prm.requires_grad:
+                        prm.grad = grad if prm.grad is None else prm.grad + grad
+        return loss.reshape(())
     return _FMLossParamFn.apply(net, eng, kind, sigma, x, mask, cond, t, code if takes else None,
                                 code if cnf.add_time_to_input else None, n0, n1, *_raw_params(net))
 

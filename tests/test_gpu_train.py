@@ -549,3 +549,22 @@ def test_graphed_training_step_learns_and_matches_eager_shapes():
     with torch.no_grad():
         l_eager = float(m.loss(x, mask=mask, cond=None))
     assert abs(l_eager - last) < 0.35 * last, (l_eager, last)
+
+
+def test_graphed_training_step_after_an_eager_backward_on_the_default_stream():
+    """An eager backward on the default stream whose ``loss`` is still alive keeps the parameters' AccumulateGrad nodes bound to
+    the legacy stream; the captured step must not run them (the library writes p.grad itself, training.direct_param_grads)."""
+    from particle_fm_b200.launch import GraphedTrainStep
+    from particle_fm_b200.optim import FusedClipAdamW
+    g, x, mask = _fixed_batch()
+    m = build_module(g.ctor, g.sd, device=DEV)
+    kept = m.loss(x[:7], mask=mask[:7], cond=None)
+    kept.backward()                                        # grad accumulators created on the default stream, graph kept alive
+    opt = FusedClipAdamW(m.parameters(), lr=2e-3, weight_decay=0.0, max_grad_norm=0.5, device_step_count=True)
+    step = GraphedTrainStep(m, opt, x, mask)
+    first = float(step(x, mask))
+    for _ in range(60):
+        last = float(step(x, mask))
+    assert first == first and last == last and float(kept) == float(kept)
+    assert last < first
+
