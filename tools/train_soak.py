@@ -27,6 +27,14 @@ for it in range(n_eager):
     loss.backward()
     opt.step()
     losses.append(float(loss))
+    if it % 50 == 49:                                      # sampling calls between training steps share the engine's buffers
+        for prec in ("bf16", "fp32"):
+            model.set_precision(prec)
+            with torch.no_grad():
+                ns = torch.randint(1, bench.N_PART + 1, (33,), generator=g)
+                smask = (torch.arange(bench.N_PART)[None, :] < ns[:, None]).float().unsqueeze(-1)
+                out = model.sample(33, mask=smask.to(dev), ode_solver="midpoint", ode_steps=5)
+            assert bool(torch.isfinite(out).all()), (it, prec)
 assert all(l == l and l < 1e4 for l in losses), losses[-5:]
 if losses:
     print("eager: %d random-shape steps ok, loss %.3f -> %.3f (%.1f s)" % (n_eager, sum(losses[:20]) / 20, sum(losses[-20:]) / 20, time.time() - t0))
