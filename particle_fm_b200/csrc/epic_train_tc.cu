@@ -683,17 +683,33 @@ __global__ void __launch_bounds__(256) tt_head_bwd_kernel(const TtCommon p) {
   __syncthreads();
   float* out = p.dact + (size_t)(1 + 2 * p.L) * p.stage_stride;
   const uint32_t* sg = p.sgn + (size_t)(1 + 2 * p.L) * p.sgn_stride;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * 32; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i >> 5), c = (int)(i & 31) * 4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int f = 0; f < F; ++f) {
-      const float d = p.dpre3[(size_t)r * F + f];
-      a.x = fmaf(w3[(c + 0) * F + f], d, a.x); a.y = fmaf(w3[(c + 1) * F + f], d, a.y);
-      a.z = fmaf(w3[(c + 2) * F + f], d, a.z); a.w = fmaf(w3[(c + 3) * F + f], d, a.w);
+  // two rows per iteration: the (row -> dpre3, sign word) loads of both are in flight together
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * 32; i += 2 * stride) {
+    const int c = (int)(i & 31) * 4;
+    const int r0 = (int)(i >> 5);
+    const bool two = i + stride < (long long)rows * 32;
+    const int r1 = two ? (int)((i + stride) >> 5) : r0;
+    float d0[8], d1[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      d0[f] = f < F ? p.dpre3[(size_t)r0 * F + f] : 0.f;
+      d1[f] = f < F ? p.dpre3[(size_t)r1 * F + f] : 0.f;
     }
-    const uint32_t e = sg[(size_t)r * 4 + (c >> 5)] >> (c & 31);
-    a.x *= (e & 1u) ? 1.f : p.slope; a.y *= (e & 2u) ? 1.f : p.slope; a.z *= (e & 4u) ? 1.f : p.slope; a.w *= (e & 8u) ? 1.f : p.slope;
-    *reinterpret_cast<float4*>(out + (size_t)r * TT_H + c) = a;
+    const uint32_t e0 = sg[(size_t)r0 * 4 + (c >> 5)] >> (c & 31), e1 = sg[(size_t)r1 * 4 + (c >> 5)] >> (c & 31);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      if (f < F) {
+        const float w0 = w3[(c + 0) * F + f], w1 = w3[(c + 1) * F + f], w2 = w3[(c + 2) * F + f], w3v = w3[(c + 3) * F + f];
+        a.x = fmaf(w0, d0[f], a.x); a.y = fmaf(w1, d0[f], a.y); a.z = fmaf(w2, d0[f], a.z); a.w = fmaf(w3v, d0[f], a.w);
+        b.x = fmaf(w0, d1[f], b.x); b.y = fmaf(w1, d1[f], b.y); b.z = fmaf(w2, d1[f], b.z); b.w = fmaf(w3v, d1[f], b.w);
+      }
+    }
+    a.x *= (e0 & 1u) ? 1.f : p.slope; a.y *= (e0 & 2u) ? 1.f : p.slope; a.z *= (e0 & 4u) ? 1.f : p.slope; a.w *= (e0 & 8u) ? 1.f : p.slope;
+    b.x *= (e1 & 1u) ? 1.f : p.slope; b.y *= (e1 & 2u) ? 1.f : p.slope; b.z *= (e1 & 4u) ? 1.f : p.slope; b.w *= (e1 & 8u) ? 1.f : p.slope;
+    *reinterpret_cast<float4*>(out + (size_t)r0 * TT_H + c) = a;
+    if (two) *reinterpret_cast<float4*>(out + (size_t)r1 * TT_H + c) = b;
   }
 }
 
