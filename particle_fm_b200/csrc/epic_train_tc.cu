@@ -434,35 +434,59 @@ struct TtCommon {
 };
 
 // stem: y (flow-matching interpolation or the given input) -> yact;  h1 = lrelu(fc_l1(y)) -> act[0] (+ sign bits).
-// One warp per row, lane = 4 consecutive columns.
-__global__ void __launch_bounds__(256) tt_stem_kernel(const TtCommon p) {
+// One warp per row, lane = 4 consecutive columns; a warp works on TWO rows at a time so that their chains of dependent
+// index loads (row -> jet -> particle slot -> inputs) overlap.
+__global__ void __launch_bounds__(256, 4) tt_stem_kernel(const TtCommon p) {
   const int lane = threadIdx.x & 31;
   const int rows = *p.n_total;
   const Lin L1 = p.lin[LIN_L1];
-  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
-    const int j = p.rowjet[r];
-    const int part = p.ridx[(size_t)j * p.N + (r - p.rowoff[j])];
-    float4 a = *reinterpret_cast<const float4*>(p.beff + (size_t)j * p.bstride + L1.bias_off + lane * 4);
-    for (int c = 0; c < p.Kx; ++c) {
-      const size_t gi = ((size_t)j * p.N + part) * p.Kx + c;
-      float y;
-      if (p.loss_kind >= 0) {                                  // losses.py:56, :115-116, :320
-        const float x = p.x_in[gi], t = p.tjet[j], z = p.noise0[gi];
-        if (p.loss_kind == PFM_LOSS_FM_OT) y = (1.f - t) * x + (p.sigma + (1.f - p.sigma) * t) * z;
-        else if (p.loss_kind == PFM_LOSS_CFM) y = ((1.f - t) * x + t * z) + p.sigma * p.noise1[gi];
-        else y = x + t * z;
-      } else {
-        y = p.x_in[gi];
-      }
-      if (lane == 0) p.yact[(size_t)r * p.Kx + c] = y;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(L1.Wt + (size_t)(L1.m_off + p.xin_off + c) * L1.ldo + lane * 4));
-      a.x = fmaf(w.x, y, a.x); a.y = fmaf(w.y, y, a.y); a.z = fmaf(w.z, y, a.z); a.w = fmaf(w.w, y, a.w);
+  const int wg = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  for (int r0 = wg * 2; r0 < rows; r0 += nw * 2) {
+    const bool two = r0 + 1 < rows;
+    const int rr[2] = {r0, two ? r0 + 1 : r0};
+    int j[2], part[2];
+    float tj[2];
+    float4 a[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) j[i] = p.rowjet[rr[i]];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      part[i] = p.ridx[(size_t)j[i] * p.N + (rr[i] - p.rowoff[j[i]])];
+      tj[i] = p.loss_kind >= 0 ? p.tjet[j[i]] : 0.f;
+      a[i] = *reinterpret_cast<const float4*>(p.beff + (size_t)j[i] * p.bstride + L1.bias_off + lane * 4);
     }
-    a.x = tt_lrelu(a.x, p.slope); a.y = tt_lrelu(a.y, p.slope); a.z = tt_lrelu(a.z, p.slope); a.w = tt_lrelu(a.w, p.slope);
-    *reinterpret_cast<float4*>(p.act + (size_t)r * TT_H + lane * 4) = a;
-    uint32_t b = ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << ((lane & 7) * 4);
-    b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
-    if ((lane & 7) == 0) p.sgn[(size_t)r * 4 + (lane >> 3)] = b;
+    for (int c = 0; c < p.Kx; ++c) {
+      float y[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const size_t gi = ((size_t)j[i] * p.N + part[i]) * p.Kx + c;
+        if (p.loss_kind >= 0) {                                  // losses.py:56, :115-116, :320
+          const float x = p.x_in[gi], t = tj[i], z = p.noise0[gi];
+          if (p.loss_kind == PFM_LOSS_FM_OT) y[i] = (1.f - t) * x + (p.sigma + (1.f - p.sigma) * t) * z;
+          else if (p.loss_kind == PFM_LOSS_CFM) y[i] = ((1.f - t) * x + t * z) + p.sigma * p.noise1[gi];
+          else y[i] = x + t * z;
+        } else {
+          y[i] = p.x_in[gi];
+        }
+      }
+      const float4 w = __ldg(reinterpret_cast<const float4*>(L1.Wt + (size_t)(L1.m_off + p.xin_off + c) * L1.ldo + lane * 4));
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (lane == 0 && (i == 0 || two)) p.yact[(size_t)rr[i] * p.Kx + c] = y[i];
+        a[i].x = fmaf(w.x, y[i], a[i].x); a[i].y = fmaf(w.y, y[i], a[i].y); a[i].z = fmaf(w.z, y[i], a[i].z); a[i].w = fmaf(w.w, y[i], a[i].w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 o = a[i];
+      o.x = tt_lrelu(o.x, p.slope); o.y = tt_lrelu(o.y, p.slope); o.z = tt_lrelu(o.z, p.slope); o.w = tt_lrelu(o.w, p.slope);
+      uint32_t b = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << ((lane & 7) * 4);
+      b |= __shfl_xor_sync(0xffffffffu, b, 1); b |= __shfl_xor_sync(0xffffffffu, b, 2); b |= __shfl_xor_sync(0xffffffffu, b, 4);
+      if (i == 0 || two) {
+        *reinterpret_cast<float4*>(p.act + (size_t)rr[i] * TT_H + lane * 4) = o;
+        if ((lane & 7) == 0) p.sgn[(size_t)rr[i] * 4 + (lane >> 3)] = b;
+      }
+    }
   }
 }
 
@@ -1036,7 +1060,7 @@ int tt_train_forward(pfm_epic* h, const TrainFwdArgs& a, cudaStream_t st) {
   const int jet_ctas = a.B;
   tt_beff_kernel<<<a.B, 256, 0, st>>>(h->tbias, a.tbias_per_jet, a.has_cbias ? h->cbias : nullptr, h->bstride, p.beff);
   if (a.loss_kind < 0) tt_out_init_kernel<<<a.B, 128, 0, st>>>(a.x_out, h->plan.n_real, a.N * c.feats);
-  tt_stem_kernel<<<(a.B * a.N + 7) / 8 < 16 * grid_rows ? (a.B * a.N + 7) / 8 : 16 * grid_rows, 256, 0, st>>>(p);
+  tt_stem_kernel<<<(a.B * a.N + 15) / 16 < 8 * grid_rows ? (a.B * a.N + 15) / 16 : 8 * grid_rows, 256, 0, st>>>(p);
   h->last_launches += 2;
   {   // fc_l2: h0 = lrelu(h1 . W^T + b + h1)     (epic.py:364-367)
     RowLinP q; memset(&q, 0, sizeof(q));
