@@ -63,7 +63,7 @@ __global__ void tbias_kernel(const Lin* __restrict__ lin, const float* __restric
 static constexpr int TB_ROWS = 8;
 static constexpr int TB_KMAX = 64;         // time-code width handled here (2 * frequencies = 32 in the shipped configs)
 
-__global__ void __launch_bounds__(128) tbias_rows_kernel(const Lin* __restrict__ lin, const float* __restrict__ code, int t_dim,
+__global__ void __launch_bounds__(128, 8) tbias_rows_kernel(const Lin* __restrict__ lin, const float* __restrict__ code, int t_dim,
                                                          const float* __restrict__ code_in, int t_in, float* __restrict__ tbias,
                                                          int bstride, int rows) {
   __shared__ __align__(16) float sc[TB_ROWS][TB_KMAX];
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(128) tbias_rows_kernel(const Lin* __restrict__
   const int row0 = blockIdx.x * TB_ROWS;
   const int nr = rows - row0 < TB_ROWS ? rows - row0 : TB_ROWS;
   const int T = L.t_len;                                   // <= TB_KMAX (checked by the caller)
+  const bool t4 = (T & 3) == 0;
   for (int i = threadIdx.x; i < TB_ROWS * TB_KMAX; i += blockDim.x) {
     const int r = i / TB_KMAX, k = i % TB_KMAX;
     sc[r][k] = (r < nr && k < T) ? code[(size_t)(row0 + r) * t_dim + k] : 0.f;
@@ -92,9 +93,15 @@ __global__ void __launch_bounds__(128) tbias_rows_kernel(const Lin* __restrict__
           for (int r = 0; r < TB_ROWS; ++r) {
             const float4 c = *reinterpret_cast<const float4*>(&sc[r][k0 + k]);
             acc[r] = fmaf(w[k], c.x, acc[r]);
-            if (k0 + k + 1 < T) acc[r] = fmaf(w[k + 1], c.y, acc[r]);
-            if (k0 + k + 2 < T) acc[r] = fmaf(w[k + 2], c.z, acc[r]);
-            if (k0 + k + 3 < T) acc[r] = fmaf(w[k + 3], c.w, acc[r]);
+            if (t4) {                                       // T a multiple of 4 (every shipped config): no per-term guard
+              acc[r] = fmaf(w[k + 1], c.y, acc[r]);
+              acc[r] = fmaf(w[k + 2], c.z, acc[r]);
+              acc[r] = fmaf(w[k + 3], c.w, acc[r]);
+            } else {
+              if (k0 + k + 1 < T) acc[r] = fmaf(w[k + 1], c.y, acc[r]);
+              if (k0 + k + 2 < T) acc[r] = fmaf(w[k + 2], c.z, acc[r]);
+              if (k0 + k + 3 < T) acc[r] = fmaf(w[k + 3], c.w, acc[r]);
+            }
           }
         }
       }
