@@ -534,7 +534,7 @@ __device__ __forceinline__ float tt_colsum_get(const float* __restrict__ red, in
 
 // Forward of one per-jet unit (unit 0 = stem fc_g1 / fc_g2, unit l+1 = EPiC layer l): pooling of the unit's input h,
 // global MLP, effective biases of the layer's two local linears (epic.py:369-380, :160-196).
-// One CTA of 256 threads per jet (latency-bound: every phase keeps 8-16 independent loads in flight per thread).
+// One CTA of 256 threads per jet, four CTAs per SM: a chain of short phases, each about one global round trip long.
 __global__ void __launch_bounds__(256, 4) tt_jet_fwd_kernel(const TtCommon p, int unit, long long* prof) {
   long long pt = prof ? clock64() : 0, pc[6] = {0, 0, 0, 0, 0, 0};
 #define JF_PROF(k) do { if (prof) { const long long n_ = clock64(); pc[k] += n_ - pt; pt = n_; } } while (0)
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256, 4) tt_jet_fwd_kernel(const TtCommon p, in
   }
   __syncthreads();
   JF_PROF(2);
-  {   // fc_g1 / fc_global1.  The phase is bound by the number of memory instructions (five co-resident CTAs issue them through
+  {   // fc_g1 / fc_global1.  The phase is bound by the number of memory instructions (the co-resident CTAs of an SM issue them through
       // one LSU), so a thread takes 4 output columns with one 16-byte weight load per k and the 8 warps split K; the partial
       // sums meet in shared memory.
     const int K = 2 * H + (unit > 0 ? Z : 0);
