@@ -41,13 +41,15 @@ per_eval = ms / nfe(short)
 gen = B / (per_eval * nfe(c["steps"]) * 1e-3)
 # training
 x = (5.0 * torch.randn(B, c["N"], c["F"], generator=g) * mask).cuda()
-opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=5e-5)
-def step():
-    opt.zero_grad(set_to_none=True)
-    loss = m.loss(x, mask=mk, cond=cond)
-    loss.backward()
-    torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
-    opt.step()
+from particle_fm_b200.optim import FusedClipAdamW
+from particle_fm_b200.launch import GraphedTrainStep
+opt = FusedClipAdamW(m.parameters(), lr=1e-3, weight_decay=5e-5, max_grad_norm=0.5, device_step_count=True)
+_graphed = None
+def step():          # fused clip + AdamW, the whole step replayed from a CUDA graph (as bench.py's training leg)
+    global _graphed
+    if _graphed is None:
+        _graphed = GraphedTrainStep(m, opt, x, mk, cond)
+    _graphed(x, mk, cond)
 if B <= 8192:
     for _ in range(3):
         step()
