@@ -133,3 +133,28 @@ def test_block_noise_is_independent_of_the_partition():
         assert not torch.equal(block_noise(0, n, N, F, seed + 1), whole)
     finally:
         gen.NOISE_BLOCK = old
+
+
+def test_training_fast_path_pieces_fail_loudly_without_cuda():
+    """The fused optimizer and the graphed step are CUDA-only (no CPU fallback); the direct-gradient switch nests and restores."""
+    from particle_fm_b200 import _lib, training
+    from particle_fm_b200.launch import GraphedTrainStep
+    from particle_fm_b200.optim import FusedClipAdamW
+    w = torch.nn.Parameter(torch.ones(4))
+    opt = FusedClipAdamW([w], lr=1e-3)
+    w.grad = torch.ones(4)
+    with pytest.raises(_lib.PfmError):
+        opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert opt.step() is None                           # nothing to do without gradients
+    with pytest.raises(NotImplementedError):
+        FusedClipAdamW([{"params": [w]}, {"params": [torch.nn.Parameter(torch.ones(2))]}])
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(None, opt, torch.zeros(2, 3, 3), torch.ones(2, 3, 1))
+    assert training._DIRECT_GRADS is False
+    with training.direct_param_grads():
+        assert training._DIRECT_GRADS is True
+        with training.direct_param_grads():
+            assert training._DIRECT_GRADS is True
+        assert training._DIRECT_GRADS is True
+    assert training._DIRECT_GRADS is False

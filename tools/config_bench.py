@@ -1,4 +1,4 @@
-"""Throughput of BASELINE.json's other EPiC configurations at their full layer sizes (fp32 kernels; the bf16 tcgen05 kernel is
+"""Throughput of BASELINE.json's other EPiC configurations at their full layer sizes (third argument: fp32 or bf16; the tcgen05 kernels are
 specialised for H = 128): generation (midpoint, extrapolated from a short run to the configured ode_steps) and training.
 python tools/config_bench.py [c1|c3|c5u|c5c] [B]"""
 import os, sys
